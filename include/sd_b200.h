@@ -1,0 +1,213 @@
+/*
+ * sd_b200.h -- C ABI of the B200-native cascaded-regression engine.
+ *
+ * This is the drop-in boundary for the hot path of patrikhuber/superviseddescent
+ * (HOG projection -> LinearRegressor::learn -> predict/detect cascade).  Plain C:
+ * opaque handles, raw pointers, explicit sizes, int status codes.  No C++ / torch
+ * types cross this boundary.  The C++14 header shells in
+ * superviseddescent_b200/include/ (same class names and call signatures as the
+ * reference) and the ctypes binding in superviseddescent_b200/ sit on top of it.
+ *
+ * Conventions (reference: SURVEY.md 8b)
+ *   - matrices are row-major float32, one sample per row (cv::Mat CV_32FC1 as the
+ *     reference uses it, regressors.hpp:202-206); `ld` = row stride in floats.
+ *   - landmark rows are [x_0..x_{L-1}, y_0..y_{L-1}] (adaptive_vlhog.hpp:96-97).
+ *   - images are 8-bit single channel (adaptive_vlhog.hpp:115-120 grey path).
+ *   - pointers named d_* are DEVICE pointers, h_* are HOST pointers.
+ *   - every call is asynchronous on the context's stream unless it returns host
+ *     data; sd_sync() waits.  Functions are re-entrant on distinct contexts.
+ *   - return value 0 = SD_OK; otherwise an sd_status and sd_last_error(ctx) holds
+ *     a message.  There is NO CPU fallback: without a usable GPU every compute
+ *     entry point fails with SD_ERR_CUDA.
+ *
+ * Citations are file:line under the reference tree (/root/reference).
+ */
+#ifndef SD_B200_H
+#define SD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define SD_API __attribute__((visibility("default")))
+#else
+#define SD_API
+#endif
+
+typedef enum {
+    SD_OK = 0,
+    SD_ERR_INVALID = 1,    /* bad argument / shape (the reference asserts) */
+    SD_ERR_CUDA = 2,       /* CUDA runtime / driver failure, or no GPU */
+    SD_ERR_IO = 3,         /* model file could not be opened/parsed (model.hpp:199 throws) */
+    SD_ERR_MISSING_ID = 4, /* eye identifier not among the landmarks (helpers.hpp:144,153 throws) */
+    SD_ERR_NUMERIC = 5,    /* non-finite result / non-positive pivot */
+    SD_ERR_UNSUPPORTED = 6
+} sd_status;
+
+typedef struct sd_ctx sd_ctx;       /* one per host thread / stream */
+typedef struct sd_model sd_model;   /* rcr::detection_model resident on the device */
+
+/* rcr::HoGParam (adaptive_vlhog.hpp:41-60); same field order as its cereal archive */
+typedef struct {
+    int32_t variant;             /* 0 = VlHogVariantDalalTriggs, 1 = VlHogVariantUoctti (hog.h:70) */
+    int32_t num_cells;
+    int32_t cell_size;
+    int32_t num_bins;            /* undirected orientations K */
+    float relative_patch_size;   /* patch width as a fraction of the inter-eye distance */
+} sd_hog_param;
+
+/* superviseddescent::Regulariser (regressors.hpp:87-169) */
+typedef struct {
+    int32_t type;                /* 0 = Manual, 1 = MatrixNorm (regressors.hpp:93-97) */
+    float param;                 /* lambda, or the factor applied to ||AtA||_F / N */
+    int32_t regularise_last_row; /* 0: the bias row gets no lambda (regressors.hpp:143-146) */
+} sd_regulariser;
+
+/* NormalisationStrategy of the optimiser: NoNormalisation (superviseddescent.hpp:60-74)
+ * or rcr::InterEyeDistanceNormalisation (model.hpp:84-116).  Eye landmarks are given as
+ * row indices into the landmark list (the host shells resolve the string ids). */
+typedef struct {
+    int32_t kind;                /* 0 = none, 1 = inter-eye distance */
+    int32_t n_right, n_left;     /* 1..4 each */
+    int32_t right_idx[4];
+    int32_t left_idx[4];
+} sd_normalisation;
+
+/* A batch of equally sized 8UC1 images resident on the device. */
+typedef struct {
+    const uint8_t* d_data;
+    int32_t width, height;
+    int32_t row_stride;          /* bytes */
+    int64_t image_stride;        /* bytes between consecutive images */
+    int32_t count;
+} sd_image_batch;
+
+/* ---- context --------------------------------------------------------------------------- */
+/* stream: a cudaStream_t owned by the caller (e.g. torch's current stream), or NULL to let
+ * the context create its own non-blocking stream. */
+SD_API int sd_ctx_create(int device, void* stream, sd_ctx** out);
+SD_API void sd_ctx_destroy(sd_ctx* ctx);
+SD_API const char* sd_last_error(const sd_ctx* ctx);
+SD_API int sd_sync(sd_ctx* ctx);
+SD_API const char* sd_version(void);
+/* number of kernels of THIS library launched on ctx since creation (bench.py's gpu_launches) */
+SD_API int64_t sd_launch_count(const sd_ctx* ctx);
+
+/* device / pinned-host memory for hosts that do not bring their own allocator */
+SD_API int sd_malloc(sd_ctx* ctx, size_t bytes, void** d_ptr);
+SD_API int sd_free(sd_ctx* ctx, void* d_ptr);
+SD_API int sd_host_alloc(sd_ctx* ctx, size_t bytes, void** h_ptr);   /* pinned */
+SD_API int sd_host_free(sd_ctx* ctx, void* h_ptr);
+SD_API int sd_memcpy_h2d(sd_ctx* ctx, void* d_dst, const void* h_src, size_t bytes);  /* async */
+SD_API int sd_memcpy_d2h(sd_ctx* ctx, void* h_dst, const void* d_src, size_t bytes);  /* async */
+SD_API int sd_memset(sd_ctx* ctx, void* d_dst, int value, size_t bytes);
+
+/* ---- projection h: rcr::HogTransform::operator() batched (adaptive_vlhog.hpp:109-185) -- */
+/* D = L * num_cells^2 * (3K+4 | 4K) + 1 */
+SD_API int sd_hog_feature_length(int num_landmarks, const sd_hog_param* p);
+/* For sample i: image = images[d_image_index ? d_image_index[i] : i], landmarks = d_x[i, 0:2L].
+ * Writes the reference's feature row (per landmark [dim][cell col][cell row], then bias 1)
+ * to d_A[i*ld .. i*ld + D).  Columns [D, ld) are left untouched.  hog.c:174-204,595-728,857-1062
+ * run fused with the crop / zero-pad / cv::resize glue of adaptive_vlhog.hpp:123-176. */
+SD_API int sd_hog_batch(sd_ctx* ctx, const sd_image_batch* images, const int32_t* d_image_index,
+                        const float* d_x, int64_t ldx, int num_samples, int num_landmarks,
+                        const sd_normalisation* eyes, const sd_hog_param* p,
+                        float* d_A, int64_t ld);
+/* parity taps (integer results that must match the reference exactly): per (sample, landmark)
+ * patch centre/half size, and optionally the resized u8 patches and per-pixel orientation bins. */
+SD_API int sd_hog_debug(sd_ctx* ctx, const sd_image_batch* images, const int32_t* d_image_index,
+                        const float* d_x, int64_t ldx, int num_samples, int num_landmarks,
+                        const sd_normalisation* eyes, const sd_hog_param* p,
+                        int32_t* d_geometry /* N*L*3: cx, cy, half */,
+                        uint8_t* d_patches /* N*L*fs*fs or NULL */,
+                        int8_t* d_bins /* N*L*fs*fs or NULL, -1 on border / zero gradient */);
+
+/* ---- regressor: LinearRegressor<Solver> (regressors.hpp:318-400) ------------------------ */
+/* Solver::solve (regressors.hpp:199-234 == verbose_solver.hpp:53-111):
+ *   X = (A^T A + Lambda)^-1 A^T B ;  A: N x D, B: N x M, X: D x M (ldx_out = M).
+ * lambda_out (host, may be NULL) receives the lambda actually applied (regressors.hpp:126-148).
+ * n_train_global: the N used in the MatrixNorm rule (== N on one GPU; the global sample count
+ * when the Gram was summed over ranks).  Phase timings (ms) of the last call, named as the
+ * reference's VerbosePartialPivLUSolver prints them, are available from sd_solver_timings. */
+SD_API int sd_learn(sd_ctx* ctx, const float* d_A, int64_t lda, const float* d_B, int64_t ldb,
+                    int N, int D, int M, const sd_regulariser* reg, float* d_X, float* lambda_out);
+/* The same, split at the multi-GPU exchange point (superviseddescent.hpp:207 / SURVEY 8e):
+ *   1. sd_gram      : d_G[Dx(D+M)] = [A^T A | A^T B] of the local rows (upper triangle of the
+ *                     D x D part is valid; row stride ldg >= D+M)
+ *   2. (caller)     : allreduce d_G over ranks
+ *   3. sd_solve_gram: regularise with n_train_global and solve, replicated on every rank */
+SD_API int sd_gram(sd_ctx* ctx, const float* d_A, int64_t lda, const float* d_B, int64_t ldb,
+                   int N, int D, int M, float* d_G, int64_t ldg);
+SD_API int sd_solve_gram(sd_ctx* ctx, float* d_G, int64_t ldg, int D, int M,
+                         const sd_regulariser* reg, int n_train_global, float* d_X, float* lambda_out);
+/* LinearRegressor::predict (regressors.hpp:377-381): out[N x M] = values[N x D] * X[D x M] */
+SD_API int sd_predict(sd_ctx* ctx, const float* d_values, int64_t ldv, int N, int D,
+                      const float* d_X, int M, float* d_out, int64_t ldo);
+/* LinearRegressor::test (regressors.hpp:361-369): ||values X - labels||_2 / ||labels||_2 */
+SD_API int sd_test_residual(sd_ctx* ctx, const float* d_values, int64_t ldv, const float* d_labels,
+                            int64_t ldl, int N, int D, const float* d_X, int M, double* residual_out);
+/* timings of the last sd_learn / sd_solve_gram: [0] "At * A", [1] "AtA + Reg", [2] "Decomposition",
+ * [3] "solve()" in milliseconds (verbose_solver.hpp:66-103) */
+SD_API int sd_solver_timings(sd_ctx* ctx, float ms_out[4]);
+/* precision of the tensor-core Gram: 0 = 3xTF32 split (fp32-class, default), 1 = single TF32 pass,
+ * 2 = force the fp32 SIMT kernel */
+SD_API int sd_set_gram_mode(sd_ctx* ctx, int mode);
+
+/* ---- cascade steps: SupervisedDescentOptimiser (superviseddescent.hpp:165-344) ---------- */
+/* b_i = (x_i - x_gt_i) (.) norm(x_i)     (superviseddescent.hpp:199-205) */
+SD_API int sd_cascade_targets(sd_ctx* ctx, const float* d_x, const float* d_x_gt, int N, int P,
+                              const sd_normalisation* norm, float* d_B, int64_t ldb);
+/* x_next_i = x_i - (A_i X) (.) (1 / norm(x_i))   (superviseddescent.hpp:209-215, 296-301, 336-339)
+ * d_x_next may alias d_x. */
+SD_API int sd_cascade_update(sd_ctx* ctx, const float* d_A, int64_t lda, int N, int D,
+                             const float* d_X, int P, const float* d_x, const sd_normalisation* norm,
+                             float* d_x_next);
+/* observed = features - templates (superviseddescent.hpp:191-197), in place on A */
+SD_API int sd_subtract_templates(sd_ctx* ctx, float* d_A, int64_t lda, const float* d_T, int64_t ldt,
+                                 int N, int D);
+
+/* ---- rcr::detection_model (model.hpp:122-219) -------------------------------------------- */
+/* load_detection_model / save_detection_model (model.hpp:192-219): cereal binary, byte compatible */
+SD_API int sd_model_load(sd_ctx* ctx, const char* path, sd_model** out);
+SD_API int sd_model_save(sd_ctx* ctx, const sd_model* m, const char* path);
+/* build a model from trained parts (detection_model ctor, model.hpp:128-129); weights are host
+ * pointers, one D_s x 2L matrix per level; ids are NUL-terminated strings. */
+SD_API int sd_model_create(sd_ctx* ctx, int num_levels, int num_landmarks,
+                           const float* const* h_weights, const sd_regulariser* regs,
+                           const sd_hog_param* hog_params, const float* h_mean,
+                           const char* const* landmark_ids,
+                           const char* const* right_eye_ids, int n_right,
+                           const char* const* left_eye_ids, int n_left, sd_model** out);
+SD_API void sd_model_destroy(sd_model* m);
+SD_API int sd_model_num_levels(const sd_model* m);
+SD_API int sd_model_num_landmarks(const sd_model* m);
+SD_API int sd_model_hog_param(const sd_model* m, int level, sd_hog_param* out);
+SD_API int sd_model_regulariser(const sd_model* m, int level, sd_regulariser* out);
+SD_API int sd_model_normalisation(const sd_model* m, sd_normalisation* out);
+SD_API int sd_model_get_mean(const sd_model* m, float* h_mean /* 2L */);            /* get_mean, model.hpp:159 */
+SD_API int sd_model_get_weights(const sd_model* m, int level, float* h_w /* D x 2L */, int* rows, int* cols);
+SD_API const char* sd_model_landmark_id(const sd_model* m, int i);
+/* rcr::align_mean (model.hpp:64-76); host-side, a few flops */
+SD_API int sd_align_mean(const float* h_mean, int num_landmarks, int box_x, int box_y, int box_w, int box_h,
+                         float scaling_x, float scaling_y, float translation_x, float translation_y,
+                         float* h_out);
+/* detection_model::detect(image, initialisation) batched, everything on the device
+ * (model.hpp:147-157 -> superviseddescent.hpp:323-344).  d_x0: B x 2L initial landmarks. */
+SD_API int sd_detect_batch_device(sd_ctx* ctx, const sd_model* m, const sd_image_batch* images,
+                                  const float* d_x0, int count, float* d_landmarks);
+/* detection_model::detect(image, facebox) batched with HOST buffers (model.hpp:132-144): aligns the
+ * mean to each box, copies the frames host->device in chunks overlapped with compute, runs the cascade
+ * and copies the B x 2L landmarks back.  h_images: count x height x row_stride bytes (8UC1; pinned
+ * memory makes the copies asynchronous); h_boxes: count x 4 (x, y, w, h). */
+SD_API int sd_detect_batch_host(sd_ctx* ctx, const sd_model* m, const uint8_t* h_images, int count,
+                                int width, int height, int row_stride, const int32_t* h_boxes,
+                                float* h_landmarks);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SD_B200_H */

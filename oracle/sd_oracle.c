@@ -270,9 +270,9 @@ double orc_get_ied(const float* row, int L, const int32_t* ridx, int nr, const i
 {
     float rx = 0.f, ry = 0.f, lx = 0.f, ly = 0.f;
     for (int i = 0; i < nr; ++i) { rx += row[ridx[i]]; ry += row[ridx[i] + L]; }
-    rx /= (float)nr; ry /= (float)nr;
+    { float inv = 1.f / (float)nr; rx = rx * inv; ry = ry * inv; }   /* cv::Vec /= float multiplies by 1.f/alpha */
     for (int i = 0; i < nl; ++i) { lx += row[lidx[i]]; ly += row[lidx[i] + L]; }
-    lx /= (float)nl; ly /= (float)nl;
+    { float inv = 1.f / (float)nl; lx = lx * inv; ly = ly * inv; }
     double dx = (double)(rx - lx), dy = (double)(ry - ly);
     return sqrt(dx * dx + dy * dy);
 }

@@ -1,0 +1,516 @@
+"""Host-side mirror of the reference's public interface for the hot path, on top of the C ABI.
+
+Class and method names follow patrikhuber/superviseddescent:
+  Regulariser, LinearRegressor                  include/superviseddescent/regressors.hpp:87-169, 318-400
+  SupervisedDescentOptimiser, NoNormalisation    include/superviseddescent/superviseddescent.hpp:60-74, 85-361
+  HoGParam, HogTransform                         include/rcr/adaptive_vlhog.hpp:41-60, 70-195
+  InterEyeDistanceNormalisation, align_mean,
+  detection_model, load/save_detection_model     include/rcr/model.hpp:64-219
+
+The C++14 header shells (superviseddescent_b200/include/) are the drop-in for C++ callers; this module
+is the same surface for Python callers, the tests and bench.py.  Matrices are row-major float32, one
+sample per row; on the device they are torch CUDA tensors (torch = allocator + stream + distributed
+plumbing only -- every computation below is a kernel of libsd_b200.so).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+from typing import Callable, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _capi
+from ._capi import HogParam as HoGParam  # same field names as rcr::HoGParam
+from ._capi import ImageBatchC, NormalisationC, RegulariserC, SdError, ptr
+
+
+def _check(ctx, rc: int) -> None:
+    if rc != 0:
+        msg = _capi.lib().sd_last_error(ctx).decode() if ctx else "no context"
+        raise SdError(rc, msg)
+
+
+class Context:
+    """One sd_ctx bound to a device and to torch's current stream on it."""
+
+    def __init__(self, device: int = 0):
+        if not torch.cuda.is_available():
+            raise SdError(2, "no CUDA device: the B200 engine has no CPU fallback")
+        self.device = int(device)
+        torch.cuda.set_device(self.device)
+        self.stream = torch.cuda.current_stream(self.device)
+        self._h = C.c_void_p()
+        rc = _capi.lib().sd_ctx_create(self.device, C.c_void_p(self.stream.cuda_stream), C.byref(self._h))
+        if rc != 0:
+            raise SdError(rc, "sd_ctx_create failed (is a CUDA device visible?)")
+
+    @property
+    def h(self):
+        return self._h
+
+    def sync(self):
+        _check(self._h, _capi.lib().sd_sync(self._h))
+
+    def launches(self) -> int:
+        return int(_capi.lib().sd_launch_count(self._h))
+
+    def set_gram_mode(self, mode: int):
+        """0 = 3xTF32 tensor-core Gram (default), 1 = single-pass TF32, 2 = fp32 SIMT."""
+        _check(self._h, _capi.lib().sd_set_gram_mode(self._h, int(mode)))
+
+    def solver_timings(self):
+        out = (C.c_float * 4)()
+        _check(self._h, _capi.lib().sd_solver_timings(self._h, out))
+        return {"At * A": out[0], "AtA + Reg": out[1], "Decomposition": out[2], "solve()": out[3]}
+
+    def close(self):
+        if self._h:
+            _capi.lib().sd_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_default_ctx: Optional[Context] = None
+
+
+def default_context() -> Context:
+    global _default_ctx
+    if _default_ctx is None:
+        dev = torch.cuda.current_device() if torch.cuda.is_available() else 0
+        _default_ctx = Context(dev)
+    return _default_ctx
+
+
+def _dev(a, ctx: Context, dtype=torch.float32) -> torch.Tensor:
+    if isinstance(a, torch.Tensor):
+        t = a.to(device=f"cuda:{ctx.device}", dtype=dtype)
+    else:
+        t = torch.from_numpy(np.ascontiguousarray(a)).to(device=f"cuda:{ctx.device}", dtype=dtype)
+    return t.contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# regressors.hpp
+# ------------------------------------------------------------------------------------------------
+class RegularisationType(enum.IntEnum):
+    Manual = 0
+    MatrixNorm = 1
+
+
+class Regulariser:
+    """superviseddescent::Regulariser (regressors.hpp:87-169)."""
+
+    RegularisationType = RegularisationType
+
+    def __init__(self, regularisation_type: RegularisationType = RegularisationType.Manual, param: float = 0.0,
+                 regularise_last_row: bool = True):
+        self.regularisation_type = RegularisationType(regularisation_type)
+        self.param = float(param)
+        self.regularise_last_row = bool(regularise_last_row)
+
+    def c(self) -> RegulariserC:
+        return RegulariserC(int(self.regularisation_type), self.param, int(self.regularise_last_row))
+
+
+class LinearRegressor:
+    """superviseddescent::LinearRegressor<Solver> (regressors.hpp:318-400); the Solver is the B200 one."""
+
+    def __init__(self, regulariser: Optional[Regulariser] = None, ctx: Optional[Context] = None):
+        self.regulariser = regulariser or Regulariser()
+        self.ctx = ctx
+        self.x: Optional[torch.Tensor] = None   # D x M, device
+        self.last_lambda: Optional[float] = None
+
+    def _ctx(self) -> Context:
+        if self.ctx is None:
+            self.ctx = default_context()
+        return self.ctx
+
+    def learn(self, data, labels) -> bool:
+        """regressors.hpp:345-350 -> Solver::solve (:199-234).  Always returns True, like the reference."""
+        ctx = self._ctx()
+        A = _dev(data, ctx)
+        B = _dev(labels, ctx)
+        N, D = A.shape
+        M = B.shape[1]
+        X = torch.empty((D, M), dtype=torch.float32, device=A.device)
+        lam = C.c_float(0)
+        reg = self.regulariser.c()
+        _check(ctx.h, _capi.lib().sd_learn(ctx.h, ptr(A), C.c_int64(A.stride(0)), ptr(B), C.c_int64(B.stride(0)),
+                                           N, D, M, C.byref(reg), ptr(X), C.byref(lam)))
+        self.x = X
+        self.last_lambda = lam.value
+        return True
+
+    def predict(self, values) -> torch.Tensor:
+        """regressors.hpp:377-381: values * x."""
+        ctx = self._ctx()
+        V = _dev(values, ctx)
+        if V.dim() == 1:
+            V = V.reshape(1, -1)
+        N, D = V.shape
+        M = self.x.shape[1]
+        out = torch.empty((N, M), dtype=torch.float32, device=V.device)
+        _check(ctx.h, _capi.lib().sd_predict(ctx.h, ptr(V), C.c_int64(V.stride(0)), N, D, ptr(self.x), M, ptr(out), C.c_int64(M)))
+        return out
+
+    def test(self, data, labels) -> float:
+        """regressors.hpp:361-369: normalised least-squares residual."""
+        ctx = self._ctx()
+        V = _dev(data, ctx)
+        Lb = _dev(labels, ctx)
+        res = C.c_double(0)
+        _check(ctx.h, _capi.lib().sd_test_residual(ctx.h, ptr(V), C.c_int64(V.stride(0)), ptr(Lb), C.c_int64(Lb.stride(0)),
+                                                   V.shape[0], V.shape[1], ptr(self.x), self.x.shape[1], C.byref(res)))
+        return res.value
+
+
+# ------------------------------------------------------------------------------------------------
+# normalisation strategies
+# ------------------------------------------------------------------------------------------------
+class NoNormalisation:
+    """superviseddescent.hpp:60-74."""
+
+    def c(self, num_landmarks: int) -> NormalisationC:
+        return NormalisationC(0, 0, 0, (C.c_int32 * 4)(), (C.c_int32 * 4)())
+
+
+class InterEyeDistanceNormalisation:
+    """rcr::InterEyeDistanceNormalisation (model.hpp:84-116): normaliser = 1 / IED(params)."""
+
+    def __init__(self, model_landmarks_list: Sequence[str], right_eye_identifiers: Sequence[str],
+                 left_eye_identifiers: Sequence[str]):
+        self.model_landmarks_list = [str(s) for s in model_landmarks_list]
+        self.right_eye_identifiers = [str(s) for s in right_eye_identifiers]
+        self.left_eye_identifiers = [str(s) for s in left_eye_identifiers]
+
+    def _idx(self, ids, which):
+        out = []
+        for s in ids:
+            if s not in self.model_landmarks_list:
+                # helpers.hpp:144,153 throw std::runtime_error with this text
+                raise RuntimeError(f"one of given {which}EyeIdentifiers ids not present in lms")
+            out.append(self.model_landmarks_list.index(s))
+        return out
+
+    def c(self, num_landmarks: int = 0) -> NormalisationC:
+        r = self._idx(self.right_eye_identifiers, "right")
+        l = self._idx(self.left_eye_identifiers, "left")
+        if not (1 <= len(r) <= 4 and 1 <= len(l) <= 4):
+            raise ValueError("1..4 eye identifiers per eye are supported")
+        return NormalisationC(1, len(r), len(l), (C.c_int32 * 4)(*(r + [0] * (4 - len(r)))), (C.c_int32 * 4)(*(l + [0] * (4 - len(l)))))
+
+
+# ------------------------------------------------------------------------------------------------
+# rcr::HogTransform (adaptive_vlhog.hpp:70-195), batched
+# ------------------------------------------------------------------------------------------------
+class HogTransform:
+    """Projection functor h.  images: (count, H, W) uint8 (8UC1) on host or device.
+
+    __call__(parameters, regressor_level, training_index) keeps the reference's meaning
+    (adaptive_vlhog.hpp:109) but takes ALL rows at once: parameters is (N, 2L) and training_index an
+    optional (N,) int array (default: row i uses image i, as train()/test() do).  A single (2L,) row
+    with an int training_index is accepted too (predict()'s call shape, superviseddescent.hpp:332).
+    """
+
+    def __init__(self, images, hog_params: Sequence[HoGParam], model_landmarks_list: Sequence[str],
+                 right_eye_identifiers: Sequence[str], left_eye_identifiers: Sequence[str], ctx: Optional[Context] = None):
+        self.ctx = ctx or default_context()
+        imgs = images if isinstance(images, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(images))
+        if imgs.dim() == 2:
+            imgs = imgs.unsqueeze(0)
+        if imgs.dtype != torch.uint8 or imgs.dim() != 3:
+            raise ValueError("images must be (count, H, W) uint8 (single channel)")
+        self.images = imgs.to(f"cuda:{self.ctx.device}").contiguous()
+        self.hog_params = list(hog_params)
+        self.norm = InterEyeDistanceNormalisation(model_landmarks_list, right_eye_identifiers, left_eye_identifiers)
+        self.num_landmarks = len(self.norm.model_landmarks_list)
+
+    def batch(self) -> ImageBatchC:
+        n, h, w = self.images.shape
+        return ImageBatchC(C.c_void_p(self.images.data_ptr()), w, h, self.images.stride(1), self.images.stride(0), n)
+
+    def feature_length(self, level: int) -> int:
+        return _capi.lib().sd_hog_feature_length(self.num_landmarks, C.byref(self.hog_params[level]))
+
+    def into(self, parameters: torch.Tensor, level: int, out: torch.Tensor, image_index: Optional[torch.Tensor] = None):
+        """Writes the feature rows into out[:, :D] (out may be wider: extended [A | b] operand)."""
+        ctx = self.ctx
+        n = parameters.shape[0]
+        eyes = self.norm.c()
+        ib = self.batch()
+        idx_ptr = ptr(image_index) if image_index is not None else C.c_void_p(0)
+        _check(ctx.h, _capi.lib().sd_hog_batch(ctx.h, C.byref(ib), idx_ptr, ptr(parameters), C.c_int64(parameters.stride(0)),
+                                               n, self.num_landmarks, C.byref(eyes), C.byref(self.hog_params[level]),
+                                               ptr(out), C.c_int64(out.stride(0))))
+
+    def __call__(self, parameters, regressor_level: int, training_index=None) -> torch.Tensor:
+        ctx = self.ctx
+        x = _dev(parameters, ctx)
+        single = x.dim() == 1
+        if single:
+            x = x.reshape(1, -1)
+        idx = None
+        if training_index is not None:
+            if np.isscalar(training_index):
+                training_index = [int(training_index)] * x.shape[0]
+            idx = _dev(np.asarray(training_index, dtype=np.int32), ctx, dtype=torch.int32)
+        elif single:
+            idx = torch.zeros(1, dtype=torch.int32, device=x.device)
+        D = self.feature_length(regressor_level)
+        out = torch.empty((x.shape[0], D), dtype=torch.float32, device=x.device)
+        self.into(x, regressor_level, out, idx)
+        return out[0] if single else out
+
+    def debug(self, parameters, level: int, training_index=None):
+        """Integer parity taps: (geometry [N,L,3] = cx,cy,half ; patches [N,L,fs,fs] u8 ; bins [N,L,fs,fs] i8)."""
+        ctx = self.ctx
+        x = _dev(parameters, ctx)
+        n = x.shape[0]
+        p = self.hog_params[level]
+        fs = p.num_cells * p.cell_size
+        L = self.num_landmarks
+        geo = torch.empty((n, L, 3), dtype=torch.int32, device=x.device)
+        patches = torch.empty((n, L, fs, fs), dtype=torch.uint8, device=x.device)
+        bins = torch.empty((n, L, fs, fs), dtype=torch.int8, device=x.device)
+        idx = None
+        if training_index is not None:
+            idx = _dev(np.asarray(training_index, dtype=np.int32), ctx, dtype=torch.int32)
+        eyes = self.norm.c()
+        ib = self.batch()
+        _check(ctx.h, _capi.lib().sd_hog_debug(ctx.h, C.byref(ib), ptr(idx), ptr(x), C.c_int64(x.stride(0)), n, L,
+                                               C.byref(eyes), C.byref(p), ptr(geo), ptr(patches), ptr(bins)))
+        return geo, patches, bins
+
+
+# ------------------------------------------------------------------------------------------------
+# superviseddescent.hpp: the cascade
+# ------------------------------------------------------------------------------------------------
+class SupervisedDescentOptimiser:
+    """superviseddescent::SupervisedDescentOptimiser<LinearRegressor, Normalisation> (superviseddescent.hpp:85-361).
+
+    projection: either a HogTransform (stays on the device) or any callable
+    h(x_row: np.ndarray, regressor_level: int, sample_index: int) -> row / float, evaluated on the host
+    exactly as the reference evaluates user functors (superviseddescent.hpp:178-189).
+    """
+
+    def __init__(self, regressors: List[LinearRegressor], normalisation=None, ctx: Optional[Context] = None):
+        self.regressors = list(regressors)
+        self.normalisation_strategy = normalisation or NoNormalisation()
+        self.ctx = ctx
+
+    def _ctx(self) -> Context:
+        if self.ctx is None:
+            self.ctx = default_context()
+        for r in self.regressors:
+            if r.ctx is None:
+                r.ctx = self.ctx
+        return self.ctx
+
+    # -- projection of all rows into an (N, ld) buffer with `extra` spare columns on the right
+    def _project(self, h, x: torch.Tensor, level: int, extra: int) -> (torch.Tensor, int):
+        ctx = self._ctx()
+        n = x.shape[0]
+        if isinstance(h, HogTransform):
+            D = h.feature_length(level)
+            ld = (D + extra + 3) // 4 * 4
+            buf = torch.empty((n, ld), dtype=torch.float32, device=x.device)
+            h.into(x, level, buf)
+            return buf, D
+        xs = x.cpu().numpy()
+        rows = [np.atleast_1d(np.asarray(h(xs[i].copy(), level, i), dtype=np.float32)).ravel() for i in range(n)]
+        D = rows[0].size
+        ld = (D + extra + 3) // 4 * 4
+        host = np.zeros((n, ld), dtype=np.float32)
+        host[:, :D] = np.stack(rows)
+        return _dev(host, ctx), D
+
+    def train(self, parameters, initialisations, templates, projection, on_training_epoch_callback=None, group=None):
+        """superviseddescent.hpp:165-219.  `group`: optional torch.distributed process group -- each rank
+        passes its own shard of rows; one all-reduce of [AtA | Atb] per level."""
+        import torch.distributed as dist
+        ctx = self._ctx()
+        lib = _capi.lib()
+        x_gt = _dev(parameters, ctx)
+        cur = _dev(initialisations, ctx).clone()
+        n, P = cur.shape
+        tmpl = _dev(templates, ctx) if templates is not None and np.size(templates) > 0 else None
+        n_global = n
+        if group is not None:
+            t = torch.tensor([n], dtype=torch.int64, device=cur.device)
+            dist.all_reduce(t, group=group)
+            n_global = int(t.item())
+        for level, reg in enumerate(self.regressors):
+            norm = self.normalisation_strategy.c(P // 2)
+            A, D = self._project(projection, cur, level, extra=P)             # 1) features (:173-189)
+            if tmpl is not None:                                             #    observed = features - templates (:191-197)
+                _check(ctx.h, lib.sd_subtract_templates(ctx.h, ptr(A), C.c_int64(A.stride(0)), ptr(tmpl), C.c_int64(tmpl.stride(0)), n, D))
+            Bv = A[:, D:D + P]                                               # 2) b = (x - x_gt) .* norm(x)  (:199-205)
+            _check(ctx.h, lib.sd_cascade_targets(ctx.h, ptr(cur), ptr(x_gt), n, P, C.byref(norm), ptr(Bv), C.c_int64(A.stride(0))))
+            ldg = (D + P + 3) // 4 * 4                                       # 3) learn (:207)
+            G = torch.empty((D, ldg), dtype=torch.float32, device=cur.device)
+            _check(ctx.h, lib.sd_gram(ctx.h, ptr(A), C.c_int64(A.stride(0)), ptr(Bv), C.c_int64(A.stride(0)), n, D, P, ptr(G), C.c_int64(ldg)))
+            if group is not None:
+                dist.all_reduce(G, group=group)                              #    the one collective per level
+            X = torch.empty((D, P), dtype=torch.float32, device=cur.device)
+            lam = C.c_float(0)
+            rc_ = reg.regulariser.c()
+            _check(ctx.h, lib.sd_solve_gram(ctx.h, ptr(G), C.c_int64(ldg), D, P, C.byref(rc_), n_global, ptr(X), C.byref(lam)))
+            reg.x, reg.last_lambda = X, lam.value
+            nxt = torch.empty_like(cur)                                      # 4) x <- x - (A X) .* 1/norm(x) (:209-215)
+            _check(ctx.h, lib.sd_cascade_update(ctx.h, ptr(A), C.c_int64(A.stride(0)), n, D, ptr(X), P, ptr(cur), C.byref(norm), ptr(nxt)))
+            cur = nxt
+            if on_training_epoch_callback is not None:                       # 5) callback (:217)
+                on_training_epoch_callback(cur)
+        return cur
+
+    def test(self, initialisations, templates, projection, on_regressor_iteration_callback=None):
+        """superviseddescent.hpp:262-306."""
+        ctx = self._ctx()
+        lib = _capi.lib()
+        cur = _dev(initialisations, ctx).clone()
+        if cur.dim() == 1:
+            cur = cur.reshape(1, -1)
+        n, P = cur.shape
+        tmpl = _dev(templates, ctx) if templates is not None and np.size(templates) > 0 else None
+        for level, reg in enumerate(self.regressors):
+            norm = self.normalisation_strategy.c(P // 2)
+            A, D = self._project(projection, cur, level, extra=0)
+            if tmpl is not None:
+                _check(ctx.h, lib.sd_subtract_templates(ctx.h, ptr(A), C.c_int64(A.stride(0)), ptr(tmpl), C.c_int64(tmpl.stride(0)), n, D))
+            nxt = torch.empty_like(cur)
+            _check(ctx.h, lib.sd_cascade_update(ctx.h, ptr(A), C.c_int64(A.stride(0)), n, D, ptr(reg.x), P, ptr(cur), C.byref(norm), ptr(nxt)))
+            cur = nxt
+            if on_regressor_iteration_callback is not None:
+                on_regressor_iteration_callback(cur)
+        return cur
+
+    def predict(self, initialisations, templates, projection):
+        """superviseddescent.hpp:323-344 (same arithmetic as test(), no callback)."""
+        return self.test(initialisations, templates, projection)
+
+
+# ------------------------------------------------------------------------------------------------
+# rcr/model.hpp
+# ------------------------------------------------------------------------------------------------
+def align_mean(mean, facebox, scaling_x=1.0, scaling_y=1.0, translation_x=0.0, translation_y=0.0) -> np.ndarray:
+    """rcr::align_mean (model.hpp:64-76); facebox = (x, y, width, height)."""
+    mean = np.ascontiguousarray(mean, dtype=np.float32).ravel()
+    out = np.empty_like(mean)
+    rc = _capi.lib().sd_align_mean(mean.ctypes.data_as(C.c_void_p), mean.size // 2, int(facebox[0]), int(facebox[1]),
+                                   int(facebox[2]), int(facebox[3]), C.c_float(scaling_x), C.c_float(scaling_y),
+                                   C.c_float(translation_x), C.c_float(translation_y), out.ctypes.data_as(C.c_void_p))
+    if rc:
+        raise SdError(rc, "sd_align_mean")
+    return out
+
+
+class detection_model:
+    """rcr::detection_model (model.hpp:122-183) resident on the GPU."""
+
+    def __init__(self, handle, ctx: Context):
+        self._m = handle
+        self.ctx = ctx
+        lib = _capi.lib()
+        self.num_levels = lib.sd_model_num_levels(handle)
+        self.num_landmarks = lib.sd_model_num_landmarks(handle)
+        self.landmark_ids = [lib.sd_model_landmark_id(handle, i).decode() for i in range(self.num_landmarks)]
+
+    @classmethod
+    def from_parts(cls, optimised_model: SupervisedDescentOptimiser, mean, landmark_ids, hog_params, right_eye_ids,
+                   left_eye_ids, ctx: Optional[Context] = None) -> "detection_model":
+        """detection_model(optimised_model, mean, landmark_ids, hog_params, right_eye_ids, left_eye_ids) (model.hpp:128)."""
+        ctx = ctx or default_context()
+        S = len(optimised_model.regressors)
+        ws = [np.ascontiguousarray(r.x.cpu().numpy(), dtype=np.float32) for r in optimised_model.regressors]
+        wp = (C.c_void_p * S)(*[w.ctypes.data_as(C.c_void_p) for w in ws])
+        regs = (RegulariserC * S)(*[r.regulariser.c() for r in optimised_model.regressors])
+        hps = (HoGParam * S)(*hog_params)
+        mean = np.ascontiguousarray(mean, dtype=np.float32).ravel()
+        ids = (C.c_char_p * len(landmark_ids))(*[str(s).encode() for s in landmark_ids])
+        rid = (C.c_char_p * len(right_eye_ids))(*[str(s).encode() for s in right_eye_ids])
+        lid = (C.c_char_p * len(left_eye_ids))(*[str(s).encode() for s in left_eye_ids])
+        h = C.c_void_p()
+        _check(ctx.h, _capi.lib().sd_model_create(ctx.h, S, len(landmark_ids), wp, regs, hps, mean.ctypes.data_as(C.c_void_p),
+                                                  ids, rid, len(right_eye_ids), lid, len(left_eye_ids), C.byref(h)))
+        return cls(h, ctx)
+
+    def get_mean(self) -> np.ndarray:
+        out = np.empty(2 * self.num_landmarks, dtype=np.float32)
+        _capi.lib().sd_model_get_mean(self._m, out.ctypes.data_as(C.c_void_p))
+        return out
+
+    def hog_param(self, level: int) -> HoGParam:
+        p = HoGParam()
+        _capi.lib().sd_model_hog_param(self._m, level, C.byref(p))
+        return p
+
+    def weights(self, level: int) -> np.ndarray:
+        r, c = C.c_int(0), C.c_int(0)
+        _capi.lib().sd_model_get_weights(self._m, level, None, C.byref(r), C.byref(c))
+        out = np.empty((r.value, c.value), dtype=np.float32)
+        _capi.lib().sd_model_get_weights(self._m, level, out.ctypes.data_as(C.c_void_p), None, None)
+        return out
+
+    def detect(self, image, facebox_or_initialisation) -> np.ndarray:
+        """detect(image, facebox) / detect(image, initialisation) (model.hpp:132-157): one frame, returns the 2L row."""
+        image = np.ascontiguousarray(image, dtype=np.uint8)
+        arg = np.asarray(facebox_or_initialisation)
+        if arg.size == 4:
+            return self.detect_batch(image[None], np.asarray(arg, dtype=np.int32)[None])[0]
+        x0 = _dev(np.asarray(arg, dtype=np.float32).reshape(1, -1), self.ctx)
+        imgs = _dev(image[None], self.ctx, dtype=torch.uint8)
+        return self.detect_batch_device(imgs, x0).cpu().numpy()[0]
+
+    def detect_batch(self, images: np.ndarray, boxes: np.ndarray) -> np.ndarray:
+        """Batched detect(image, facebox) with HOST buffers (copies are part of the call)."""
+        if isinstance(images, torch.Tensor):
+            images_np = images.numpy()
+        else:
+            images_np = np.ascontiguousarray(images, dtype=np.uint8)
+        n, h, w = images_np.shape
+        boxes = np.ascontiguousarray(boxes, dtype=np.int32).reshape(n, 4)
+        out = np.empty((n, 2 * self.num_landmarks), dtype=np.float32)
+        _check(self.ctx.h, _capi.lib().sd_detect_batch_host(self.ctx.h, self._m, images_np.ctypes.data_as(C.c_void_p), n, w, h,
+                                                            images_np.strides[1], boxes.ctypes.data_as(C.c_void_p),
+                                                            out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def detect_batch_device(self, images: torch.Tensor, x0: torch.Tensor) -> torch.Tensor:
+        """Batched detect(image, initialisation), frames and landmarks already resident in HBM."""
+        n, h, w = images.shape
+        ib = ImageBatchC(C.c_void_p(images.data_ptr()), w, h, images.stride(1), images.stride(0), n)
+        out = torch.empty((n, 2 * self.num_landmarks), dtype=torch.float32, device=images.device)
+        _check(self.ctx.h, _capi.lib().sd_detect_batch_device(self.ctx.h, self._m, C.byref(ib), ptr(x0), n, ptr(out)))
+        return out
+
+    def save(self, filename: str) -> None:
+        _check(self.ctx.h, _capi.lib().sd_model_save(self.ctx.h, self._m, filename.encode()))
+
+    def __del__(self):
+        try:
+            if self._m:
+                _capi.lib().sd_model_destroy(self._m)
+                self._m = None
+        except Exception:
+            pass
+
+
+def load_detection_model(filename: str, ctx: Optional[Context] = None) -> detection_model:
+    """rcr::load_detection_model (model.hpp:192-205)."""
+    ctx = ctx or default_context()
+    h = C.c_void_p()
+    _check(ctx.h, _capi.lib().sd_model_load(ctx.h, filename.encode(), C.byref(h)))
+    return detection_model(h, ctx)
+
+
+def save_detection_model(model: detection_model, filename: str) -> None:
+    """rcr::save_detection_model (model.hpp:214-219)."""
+    model.save(filename)

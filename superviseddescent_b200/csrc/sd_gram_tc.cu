@@ -1,0 +1,425 @@
+// Tensor-core SYRK for sm_100a:  C[i,j] = beta*C[i,j] + alpha * sum_k S[k,i]*S[k,j]  (upper-triangle tiles)
+//
+// This is LinearRegressor::learn's "At * A" (reference verbose_solver.hpp:67, regressors.hpp:208) with
+// A^T b folded in as extra columns, and the trailing update of the blocked Cholesky that replaces
+// PartialPivLU (verbose_solver.hpp:89).  S is row-major [K x NJ] -- one sample per row, exactly as the
+// optimiser stacks the feature rows (superviseddescent.hpp:186-189) -- so BOTH MMA operands are
+// "MN-major" (the contraction index K is the slow one).  For 32-bit operands tcgen05 accepts MN-major
+// tiles only in the 128B-swizzle / 32B-atom shared-memory layout, which TMA produces directly
+// (CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): no transposition of A anywhere.
+//
+// Precision: kind::tf32 keeps 10 mantissa bits.  passes == 3 runs the 3xTF32 split
+//     a = hi + lo,  hi = rna_tf32(a), lo = rna_tf32(a - hi);   a_i*a_j ~= hi_i*hi_j + hi_i*lo_j + lo_i*hi_j
+// (relative error ~2^-21 per product, fp32 accumulation in TMEM) on operands pre-split in HBM by
+// split_tf32_kernel; passes == 1 is a single TF32 pass on the raw operand.
+//
+// Kernel shape (persistent, one CTA per SM, 192 threads):
+//   warp 0      TMA producer   : 4-stage ring of [hi|lo] x [A 128 cols | B 256 cols] x 16 samples
+//   warp 1      MMA issuer     : tcgen05.mma cta_group::1 kind::tf32, M=128 N=256 K=8, accumulators in TMEM
+//   warps 2..5  epilogue       : tcgen05.ld 32x32b -> alpha/beta -> global (double-buffered TMEM: 2 x 256 cols)
+#include "sd_internal.cuh"
+
+#include <cuda.h>
+
+#include <cstring>
+#include <vector>
+
+namespace {
+
+constexpr int BM = 128;          // rows of C per tile   (operand "A": columns i of S)
+constexpr int BN = 256;          // cols of C per tile   (operand "B": columns j of S)
+constexpr int BK = 16;           // samples (rows of S) per pipeline stage
+constexpr int STAGES = 4;
+constexpr int BOX_COLS = 32;     // 32 floats = 128 B = swizzle span
+constexpr int BOX_BYTES = BOX_COLS * 4 * BK;              // 2 KB
+constexpr int A_BLOCKS = BM / BOX_COLS;                   // 4
+constexpr int B_BLOCKS = BN / BOX_COLS;                   // 8
+constexpr int OPER_BYTES_A = A_BLOCKS * BOX_BYTES;        // 8 KB
+constexpr int OPER_BYTES_B = B_BLOCKS * BOX_BYTES;        // 16 KB
+constexpr int STAGE_BYTES = 2 * (OPER_BYTES_A + OPER_BYTES_B);   // hi + lo: 48 KB
+constexpr int TC_THREADS = 192;
+constexpr int TMEM_COLS = 512;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+
+// super-tile for L2 reuse: tiles that run concurrently share (GI*128 + GJ*256) operand columns
+constexpr int GI = 12, GJ = 12;
+
+// ---- PTX wrappers ----------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// bounded wait: a protocol bug must trap (context error), never hang the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 8000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_commit(uint64_t* bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, MN-major operand in the 128B-swizzle / 32B-atom layout
+// (cute::UMMA::SmemDescriptor: start [0,14), LBO [16,30), SBO [32,46), version [46,48) = 1,
+//  layout_type [61,64) = 1 = SWIZZLE_128B_BASE32B; all offsets in 16-byte units)
+//   LBO = byte distance between consecutive 32-float (128 B) column blocks  = one TMA box  (2 KB)
+//   SBO = byte distance between consecutive 4-row swizzle atoms along K    = 512 B
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(BOX_BYTES >> 4) << 16;
+    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)1 << 61;
+    return d;
+}
+
+// cute::UMMA::InstrDescriptor: c_format F32 [4,6)=1, a/b_format TF32 [7,10)/[10,13)=2, a/b_major MN [15],[16]=1,
+// n_dim = N>>3 at [17,23), m_dim = M>>4 at [24,29)
+constexpr uint32_t kInstrDesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                                ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+struct TcArgs {
+    int K, MI, NJ;
+    float* C;
+    long long ldc;
+    float alpha, beta;
+    int passes;          // 1 or 3
+    const int2* tiles;   // (ti, tj) per tile
+    int num_tiles;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+syrk_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, const TcArgs a)
+{
+    extern __shared__ unsigned char smem_raw[];
+    // 1024-byte alignment for the swizzled tiles
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* full_bar = bars;                  // [STAGES]
+    uint64_t* empty_bar = bars + STAGES;        // [STAGES]
+    uint64_t* tmem_full = bars + 2 * STAGES;    // [2]
+    uint64_t* tmem_empty = bars + 2 * STAGES + 2;   // [2]
+    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_k = (a.K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_lo) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_base_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            const uint32_t tx_bytes = (a.passes == 3) ? STAGE_BYTES : (OPER_BYTES_A + OPER_BYTES_B);
+            for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
+                const int2 tile = a.tiles[t];
+                const int i0 = tile.x * BM, j0 = tile.y * BN;
+                for (int kb = 0; kb < num_k; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+                    unsigned char* sa_hi = smem + stage * STAGE_BYTES;
+                    unsigned char* sb_hi = sa_hi + OPER_BYTES_A;
+                    unsigned char* sa_lo = sb_hi + OPER_BYTES_B;
+                    unsigned char* sb_lo = sa_lo + OPER_BYTES_A;
+                    const int k0 = kb * BK;
+#pragma unroll
+                    for (int cb = 0; cb < A_BLOCKS; ++cb) tma_load_2d(sa_hi + cb * BOX_BYTES, &map_hi, &full_bar[stage], i0 + cb * BOX_COLS, k0);
+#pragma unroll
+                    for (int cb = 0; cb < B_BLOCKS; ++cb) tma_load_2d(sb_hi + cb * BOX_BYTES, &map_hi, &full_bar[stage], j0 + cb * BOX_COLS, k0);
+                    if (a.passes == 3) {
+#pragma unroll
+                        for (int cb = 0; cb < A_BLOCKS; ++cb) tma_load_2d(sa_lo + cb * BOX_BYTES, &map_lo, &full_bar[stage], i0 + cb * BOX_COLS, k0);
+#pragma unroll
+                        for (int cb = 0; cb < B_BLOCKS; ++cb) tma_load_2d(sb_lo + cb * BOX_BYTES, &map_lo, &full_bar[stage], j0 + cb * BOX_COLS, k0);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        uint32_t stage = 0, phase = 0;
+        uint32_t buf = 0, buf_phase = 0;
+        for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
+            mbar_wait(&tmem_empty[buf], buf_phase ^ 1);      // epilogue has drained this accumulator
+            tcgen05_fence_after();
+            const uint32_t tmem_d = tmem_base + buf * BN;
+            for (int kb = 0; kb < num_k; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
+                tcgen05_fence_after();
+                if (lane == 0) {
+                    const uint32_t sa_hi = smem_u32(smem + stage * STAGE_BYTES);
+                    const uint32_t sb_hi = sa_hi + OPER_BYTES_A;
+                    const uint32_t sa_lo = sb_hi + OPER_BYTES_B;
+                    const uint32_t sb_lo = sa_lo + OPER_BYTES_A;
+#pragma unroll
+                    for (int ks = 0; ks < BK / 8; ++ks) {
+                        const uint32_t koff = ks * 8 * 128;      // 8 rows of 128 B per UMMA K step
+                        const uint32_t first = (kb == 0 && ks == 0) ? 0u : 1u;
+                        if (a.passes == 3) {
+                            tcgen05_mma_tf32(tmem_d, make_desc(sa_lo + koff), make_desc(sb_hi + koff), kInstrDesc, first);
+                            tcgen05_mma_tf32(tmem_d, make_desc(sa_hi + koff), make_desc(sb_lo + koff), kInstrDesc, 1u);
+                            tcgen05_mma_tf32(tmem_d, make_desc(sa_hi + koff), make_desc(sb_hi + koff), kInstrDesc, 1u);
+                        } else {
+                            tcgen05_mma_tf32(tmem_d, make_desc(sa_hi + koff), make_desc(sb_hi + koff), kInstrDesc, first);
+                        }
+                    }
+                    tcgen05_commit(&empty_bar[stage]);                        // smem slot free once these MMAs retire
+                    if (kb == num_k - 1) tcgen05_commit(&tmem_full[buf]);     // accumulator complete
+                }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+            if (++buf == 2) { buf = 0; buf_phase ^= 1; }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int q = warp & 3;                       // TMEM lane quarter this warp may access
+        uint32_t buf = 0, buf_phase = 0;
+        const bool vec_ok = (a.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.C) & 15) == 0);
+        for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
+            const int2 tile = a.tiles[t];
+            const int i = tile.x * BM + q * 32 + lane;
+            const int j0 = tile.y * BN;
+            mbar_wait(&tmem_full[buf], buf_phase);
+            tcgen05_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN;
+            float* crow = a.C + (long long)i * a.ldc;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(taddr + c0, r);
+                tmem_ld_wait();
+                if (i < a.MI) {
+                    const int j = j0 + c0;
+                    if (vec_ok && j + 32 <= a.NJ) {
+#pragma unroll
+                        for (int v = 0; v < 8; ++v) {
+                            float4 o;
+                            o.x = a.alpha * __uint_as_float(r[4 * v + 0]);
+                            o.y = a.alpha * __uint_as_float(r[4 * v + 1]);
+                            o.z = a.alpha * __uint_as_float(r[4 * v + 2]);
+                            o.w = a.alpha * __uint_as_float(r[4 * v + 3]);
+                            float4* p = reinterpret_cast<float4*>(crow + j + 4 * v);
+                            if (a.beta != 0.f) {
+                                const float4 old = *p;
+                                o.x = fmaf(a.beta, old.x, o.x); o.y = fmaf(a.beta, old.y, o.y);
+                                o.z = fmaf(a.beta, old.z, o.z); o.w = fmaf(a.beta, old.w, o.w);
+                            }
+                            *p = o;
+                        }
+                    } else {
+#pragma unroll
+                        for (int v = 0; v < 32; ++v) {
+                            if (j + v < a.NJ) {
+                                float o = a.alpha * __uint_as_float(r[v]);
+                                if (a.beta != 0.f) o = fmaf(a.beta, crow[j + v], o);
+                                crow[j + v] = o;
+                            }
+                        }
+                    }
+                }
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+            if (++buf == 2) { buf = 0; buf_phase ^= 1; }
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// hi = rna_tf32(s), lo = rna_tf32(s - hi); columns [NJ, ldw) are zero-filled
+__global__ void split_tf32_kernel(const float* __restrict__ S, long long lds, int K, int NJ,
+                                  float* __restrict__ hi, float* __restrict__ lo, long long ldw)
+{
+    const long long total = (long long)K * (ldw / 4);
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const long long k = idx / (ldw / 4);
+        const int c = (int)(idx - k * (ldw / 4)) * 4;
+        float v[4], h[4], l[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] = (c + e < NJ) ? S[k * lds + c + e] : 0.f;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            uint32_t hb, lb;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v[e]));
+            h[e] = __uint_as_float(hb);
+            const float d = __fsub_rn(v[e], h[e]);
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(d));
+            l[e] = __uint_as_float(lb);
+        }
+        *reinterpret_cast<float4*>(hi + k * ldw + c) = make_float4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<float4*>(lo + k * ldw + c) = make_float4(l[0], l[1], l[2], l[3]);
+    }
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode_fn()
+{
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+    }
+    return fn;
+}
+
+int make_map(sd_ctx* ctx, CUtensorMap* map, const float* base, int64_t ld, int rows, int cols)
+{
+    PFN_encodeTiled enc = get_encode_fn();
+    if (!enc) return sd_fail(ctx, SD_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)BOX_COLS, (cuuint32_t)BK};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return sd_fail(ctx, SD_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return SD_OK;
+}
+
+}  // namespace
+
+bool sd_syrk_tc_supported(const float* d_S, int64_t lds, int K, int MI, int NJ, const float* d_C, int64_t ldc)
+{
+    (void)MI; (void)NJ; (void)d_C; (void)ldc;
+    // TMA needs a 16-byte aligned base and row pitch
+    return K >= 1 && (reinterpret_cast<uintptr_t>(d_S) & 15) == 0 && (lds % 4) == 0;
+}
+
+int sd_syrk_tc(sd_ctx* ctx, const float* d_S, int64_t lds, int K, int MI, int NJ, float* d_C, int64_t ldc,
+               float alpha, float beta, int passes)
+{
+    if (MI <= 0 || NJ <= 0 || K <= 0) return SD_OK;
+    SD_REQUIRE(ctx, passes == 1 || passes == 3, "passes must be 1 or 3");
+    const float* hi = d_S;
+    const float* lo = d_S;
+    int64_t ldw = lds;
+    if (passes == 3) {
+        ldw = ((int64_t)NJ + 3) / 4 * 4;
+        float* whi = (float*)sd_workspace(ctx, SD_WS_SPLIT_HI, (size_t)K * ldw * sizeof(float));
+        float* wlo = (float*)sd_workspace(ctx, SD_WS_SPLIT_LO, (size_t)K * ldw * sizeof(float));
+        if (!whi || !wlo) return SD_ERR_CUDA;
+        const int64_t work = (int64_t)K * (ldw / 4);
+        const int blocks = sd_div_up(work, 256) > 8 * ctx->sm_count ? 8 * ctx->sm_count : sd_div_up(work, 256);
+        split_tf32_kernel<<<blocks, 256, 0, ctx->stream>>>(d_S, lds, K, NJ, whi, wlo, ldw);
+        SD_LAUNCH_CHECK(ctx, "split_tf32_kernel");
+        hi = whi;
+        lo = wlo;
+    }
+    CUtensorMap map_hi, map_lo;
+    int rc = make_map(ctx, &map_hi, hi, ldw, K, NJ);
+    if (rc) return rc;
+    rc = make_map(ctx, &map_lo, lo, ldw, K, NJ);
+    if (rc) return rc;
+
+    // tile list, ordered by super-tiles so that concurrently running tiles share operand columns in L2
+    const int TI = sd_div_up(MI, BM), TJ = sd_div_up(NJ, BN);
+    std::vector<int2> tiles;
+    tiles.reserve((size_t)TI * TJ / 2 + TI + TJ);
+    for (int si = 0; si < TI; si += GI)
+        for (int sj = 0; sj < TJ; sj += GJ)
+            for (int ti = si; ti < si + GI && ti < TI; ++ti)
+                for (int tj = sj; tj < sj + GJ && tj < TJ; ++tj)
+                    if (tj * BN + BN - 1 >= ti * BM) tiles.push_back(make_int2(ti, tj));
+    if (tiles.empty()) return SD_OK;
+    int2* d_tiles = (int2*)sd_workspace(ctx, SD_WS_DIAGINV, tiles.size() * sizeof(int2));
+    if (!d_tiles) return SD_ERR_CUDA;
+    SD_CUDA(ctx, cudaMemcpyAsync(d_tiles, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
+
+    TcArgs a;
+    a.K = K; a.MI = MI; a.NJ = NJ; a.C = d_C; a.ldc = ldc; a.alpha = alpha; a.beta = beta; a.passes = passes;
+    a.tiles = d_tiles; a.num_tiles = (int)tiles.size();
+    SD_CUDA(ctx, cudaFuncSetAttribute(syrk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    const int grid = a.num_tiles < ctx->sm_count ? a.num_tiles : ctx->sm_count;
+    syrk_tc_kernel<<<grid, TC_THREADS, SMEM_BYTES, ctx->stream>>>(map_hi, map_lo, a);
+    SD_LAUNCH_CHECK(ctx, "syrk_tc_kernel");
+    return SD_OK;
+}

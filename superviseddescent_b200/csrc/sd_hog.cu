@@ -1,0 +1,449 @@
+// Batched per-landmark HOG projection: the CUDA restatement of rcr::HogTransform::operator()
+// (reference include/rcr/adaptive_vlhog.hpp:109-185) fused with VLFeat's vl_hog_put_image /
+// vl_hog_extract (reference include/rcr/hog.c:595-728, :857-1062).
+//
+// One CTA per (sample, landmark) patch.  Everything between the 8-bit source image in HBM and the
+// feature row in HBM lives in shared memory:
+//   geometry (IED -> half patch size, cvRound centre)            adaptive_vlhog.hpp:123,132-133
+//   zero-padded crop + cv::resize INTER_LINEAR (fixed point)     adaptive_vlhog.hpp:135-155
+//   gradient, orientation arg-max (integer result, bit exact)    hog.c:631-672
+//   bilinear spatial vote, gathered per cell (no atomics)        hog.c:697-724
+//   cell energy, 2x2-block normalisation in double, clamp 0.2    hog.c:875-1053
+//   per-dimension transpose + landmark concatenation + bias      adaptive_vlhog.hpp:166-183
+//
+// Arithmetic that decides an INTEGER result (crop centre, half size, resize taps, orientation bin)
+// is written with explicit round-to-nearest intrinsics so that no FMA contraction can change it;
+// the reference is built for baseline x86-64 (mul then add).  The only deviation from the
+// reference's value stream is the summation ORDER of the float votes inside a cell histogram
+// (fixed, deterministic tree here; raster order there): ~1e-7 relative.
+#include "sd_internal.cuh"
+
+#include <cmath>
+
+namespace {
+
+constexpr int kHogThreads = 256;
+constexpr int kHogWarps = kHogThreads / 32;
+
+struct HogArgs {
+    const uint8_t* images;
+    int width, height, row_stride;
+    long long image_stride;
+    int image_count;
+    const int* image_index;
+    const float* x;
+    long long ldx;
+    int N, L;
+    sd_eyes_dev eyes;
+    int variant, nc, cs, K, fs, dd;
+    float rel;
+    float ox[SD_MAX_BINS], oy[SD_MAX_BINS];
+    float* A;
+    long long ld;
+    int* geometry;
+    uint8_t* patches;
+    int8_t* bins;
+    int* status;
+};
+
+// shared-memory carve-up (same function on host and device)
+struct HogSmem {
+    int patch, bin, r1, xofs, yofs0, yofs1, xa, yb, sbin, sw1, sw2, lo, hi, hist, energy, fac, priv, feat, total;
+};
+
+__host__ __device__ inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
+
+__host__ __device__ inline HogSmem hog_smem_layout(int fs, int nc, int K, int dd)
+{
+    HogSmem s;
+    const int cells = nc * nc;
+    int o = 0;
+    s.patch = o;  o = align_up(o + fs * fs, 16);
+    s.bin = o;    o = align_up(o + fs * fs, 16);
+    int r1 = fs * fs * 4;                                   // gradient modulus, later the clamped hc values (double)
+    if (cells * K * 32 > r1) r1 = cells * K * 32;
+    s.r1 = o;     o = align_up(o + r1, 16);
+    s.xofs = o;   o += fs * 4;
+    s.yofs0 = o;  o += fs * 4;
+    s.yofs1 = o;  o += fs * 4;
+    s.xa = o;     o += fs * 4;                              // 2 x int16
+    s.yb = o;     o += fs * 4;
+    s.sbin = o;   o += fs * 4;
+    s.sw1 = o;    o += fs * 4;
+    s.sw2 = o;    o += fs * 4;
+    s.lo = o;     o += nc * 4;
+    s.hi = o;     o += nc * 4;
+    s.hist = o;   o += cells * 2 * K * 4;
+    s.energy = o; o = align_up(o + cells * 4, 16);
+    s.fac = o;    o += cells * 4 * 8;
+    s.priv = o;   o += kHogWarps * 2 * K * 32 * 4;
+    s.feat = o;   o += cells * dd * 4;
+    s.total = align_up(o, 16);
+    return s;
+}
+
+__device__ __forceinline__ int clip_index(int x, int a, int b) { return x >= a ? (x < b ? x : b - 1) : a; }
+
+__device__ __forceinline__ short sat_short(int v) { return (short)(v > 32767 ? 32767 : (v < -32768 ? -32768 : v)); }
+
+template <int KT>
+__global__ void __launch_bounds__(kHogThreads) hog_patch_kernel(const HogArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int K = KT > 0 ? KT : a.K;
+    const int fs = a.fs, nc = a.nc, cs = a.cs, dd = a.dd;
+    const int cells = nc * nc;
+    const HogSmem lay = hog_smem_layout(fs, nc, K, dd);
+    uint8_t* s_patch = smem + lay.patch;
+    int8_t* s_bin = reinterpret_cast<int8_t*>(smem + lay.bin);
+    float* s_gmag = reinterpret_cast<float*>(smem + lay.r1);
+    double* s_hc = reinterpret_cast<double*>(smem + lay.r1);
+    int* s_xofs = reinterpret_cast<int*>(smem + lay.xofs);
+    int* s_yofs0 = reinterpret_cast<int*>(smem + lay.yofs0);
+    int* s_yofs1 = reinterpret_cast<int*>(smem + lay.yofs1);
+    short2* s_xa = reinterpret_cast<short2*>(smem + lay.xa);
+    short2* s_yb = reinterpret_cast<short2*>(smem + lay.yb);
+    int* s_sbin = reinterpret_cast<int*>(smem + lay.sbin);
+    float* s_sw1 = reinterpret_cast<float*>(smem + lay.sw1);
+    float* s_sw2 = reinterpret_cast<float*>(smem + lay.sw2);
+    int* s_lo = reinterpret_cast<int*>(smem + lay.lo);
+    int* s_hi = reinterpret_cast<int*>(smem + lay.hi);
+    float* s_hist = reinterpret_cast<float*>(smem + lay.hist);
+    float* s_energy = reinterpret_cast<float*>(smem + lay.energy);
+    double* s_fac = reinterpret_cast<double*>(smem + lay.fac);
+    float* s_priv = reinterpret_cast<float*>(smem + lay.priv);
+    float* s_feat = reinterpret_cast<float*>(smem + lay.feat);
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const long long patch_id = blockIdx.x;
+    const int sample = (int)(patch_id / a.L);
+    const int lm = (int)(patch_id - (long long)sample * a.L);
+
+    // ---- S0: geometry (every thread, redundantly) -----------------------------------------
+    const float* __restrict__ row = a.x + (long long)sample * a.ldx;
+    const double ied = sd_device_ied(row, a.L, a.eyes);
+    // adaptive_vlhog.hpp:123  int half = std::round(float rel * double ied / 2)
+    int half = (int)round(__dmul_rn(__dmul_rn((double)a.rel, ied), 0.5));
+    if (half < 1) {   // cv::resize would throw on the empty ROI; flag it and keep going
+        half = 1;
+        if (tid == 0 && a.status) atomicOr(a.status, 1);
+    }
+    const int P = 2 * half;
+    const int cx = __float2int_rn(row[lm]);            // cvRound, :132
+    const int cy = __float2int_rn(row[lm + a.L]);      // :133
+    int img_idx = a.image_index ? a.image_index[sample] : sample;
+    if (img_idx < 0 || img_idx >= a.image_count) {
+        img_idx = 0;
+        if (tid == 0 && a.status) atomicOr(a.status, 2);
+    }
+    const uint8_t* __restrict__ img = a.images + (long long)img_idx * a.image_stride;
+    if (tid == 0 && a.geometry) {
+        a.geometry[patch_id * 3 + 0] = cx;
+        a.geometry[patch_id * 3 + 1] = cy;
+        a.geometry[patch_id * 3 + 2] = half;
+    }
+
+    // interpolation tables of cv::resize (INTER_LINEAR, 8U, 11-bit fixed point) and the spatial
+    // binning tables of vl_hog_put_image (hog.c:697-709)
+    for (int t = tid; t < fs; t += kHogThreads) {
+        const double inv_scale = __ddiv_rn((double)fs, (double)P);
+        const double scale = __ddiv_rn(1.0, inv_scale);
+        float f = (float)__dadd_rn(__dmul_rn((double)t + 0.5, scale), -0.5);
+        const int s = (int)floorf(f);
+        f = __fsub_rn(f, (float)s);
+        int sx = s;
+        float fx = f;
+        if (sx < 0) { fx = 0.f; sx = 0; }
+        if (sx >= P - 1) { fx = 0.f; sx = P - 1; }
+        s_xofs[t] = sx;
+        s_xa[t] = make_short2(sat_short(__float2int_rn(__fmul_rn(__fsub_rn(1.f, fx), 2048.f))),
+                              sat_short(__float2int_rn(__fmul_rn(fx, 2048.f))));
+        s_yofs0[t] = clip_index(s, 0, P);
+        s_yofs1[t] = clip_index(s + 1, 0, P);
+        s_yb[t] = make_short2(sat_short(__float2int_rn(__fmul_rn(__fsub_rn(1.f, f), 2048.f))),
+                              sat_short(__float2int_rn(__fmul_rn(f, 2048.f))));
+
+        const float h = (float)__dadd_rn(__ddiv_rn((double)t + 0.5, (double)cs), -0.5);
+        int b = (int)h;                                   // vl_floor_f, hog.h:52-58
+        if (!(h >= 0.f || (float)b == h)) b -= 1;
+        const float w2 = __fsub_rn(h, (float)b);
+        s_sbin[t] = b;
+        s_sw2[t] = w2;
+        s_sw1[t] = (float)__dadd_rn(1.0, -(double)w2);
+    }
+    for (int i = tid; i < kHogWarps * 2 * K * 32; i += kHogThreads) s_priv[i] = 0.f;
+    __syncthreads();
+
+    // ---- S1: zero-padded crop + fixed-point bilinear resize straight from the frame ----------
+    const int x0 = cx - half, y0 = cy - half;
+    const int W = a.width, H = a.height, stride = a.row_stride;
+    for (int idx = tid; idx < fs * fs; idx += kHogThreads) {
+        const int dy = idx / fs, dx = idx - dy * fs;
+        const int sx = s_xofs[dx];
+        const short2 xa = s_xa[dx];
+        const short2 yb = s_yb[dy];
+        const int ix0 = x0 + sx, ix1 = ix0 + 1;
+        const int iy0 = y0 + s_yofs0[dy], iy1 = y0 + s_yofs1[dy];
+        const bool cx0 = (unsigned)ix0 < (unsigned)W, cx1 = (unsigned)ix1 < (unsigned)W && xa.y != 0;
+        const bool ry0 = (unsigned)iy0 < (unsigned)H, ry1 = (unsigned)iy1 < (unsigned)H;
+        const uint8_t* r0 = img + (long long)iy0 * stride;
+        const uint8_t* r1 = img + (long long)iy1 * stride;
+        const int p00 = (ry0 && cx0) ? __ldg(r0 + ix0) : 0;
+        const int p01 = (ry0 && cx1) ? __ldg(r0 + ix1) : 0;
+        const int p10 = (ry1 && cx0) ? __ldg(r1 + ix0) : 0;
+        const int p11 = (ry1 && cx1) ? __ldg(r1 + ix1) : 0;
+        const int t0 = p00 * xa.x + p01 * xa.y;
+        const int t1 = p10 * xa.x + p11 * xa.y;
+        const int v = ((((int)yb.x * (t0 >> 4)) >> 16) + (((int)yb.y * (t1 >> 4)) >> 16) + 2) >> 2;
+        s_patch[idx] = (uint8_t)v;
+        if (a.patches) a.patches[patch_id * fs * fs + idx] = (uint8_t)v;
+    }
+    // per cell-column pixel ranges that vote into it (same for rows: square patch, square cells)
+    if (tid < nc) {
+        int lo = fs, hi = -1;
+        for (int t = 1; t <= fs - 2; ++t) {
+            const int b = s_sbin[t];
+            if (b == tid || b == tid - 1) { if (t < lo) lo = t; hi = t; }
+        }
+        s_lo[tid] = lo;
+        s_hi[tid] = hi;
+    }
+    __syncthreads();
+
+    // ---- S2: gradient + orientation arg-max per interior pixel (hog.c:631-672) ---------------
+    for (int idx = tid; idx < fs * fs; idx += kHogThreads) {
+        const int y = idx / fs, x = idx - y * fs;
+        int bin = -1;
+        float g = 0.f;
+        if (x >= 1 && x <= fs - 2 && y >= 1 && y <= fs - 2) {
+            const float gx = (float)((int)s_patch[idx + 1] - (int)s_patch[idx - 1]);
+            const float gy = (float)((int)s_patch[idx + fs] - (int)s_patch[idx - fs]);
+            const float g2 = __fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy));
+            if (g2 > 0.f) {
+                g = __fsqrt_rn(g2);
+                // (float)((double)gx / max((double)g, 1e-10)) == gx / g in float: double rounding is
+                // innocuous for division when the wide format has >= 2p+2 bits (53 >= 50).
+                const float ux = __fdiv_rn(gx, g);
+                const float uy = __fdiv_rn(gy, g);
+                float best = 0.f;
+#pragma unroll
+                for (int k = 0; k < (KT > 0 ? KT : SD_MAX_BINS); ++k) {
+                    if (KT == 0 && k >= K) break;
+                    float s = __fadd_rn(__fmul_rn(ux, a.ox[k]), __fmul_rn(uy, a.oy[k]));
+                    int b = k;
+                    if (s < 0.f) { s = -s; b += K; }
+                    if (s > best) { best = s; bin = b; }   // strict >, ascending k
+                }
+            }
+        }
+        s_bin[idx] = (int8_t)bin;
+        s_gmag[idx] = g;
+        if (a.bins) a.bins[patch_id * fs * fs + idx] = (int8_t)bin;
+    }
+    __syncthreads();
+
+    // ---- S3: spatial vote, gathered per cell by one warp (hog.c:697-724) ---------------------
+    {
+        float* priv = s_priv + warp * (2 * K * 32);
+        for (int c = warp; c < cells; c += kHogWarps) {
+            const int cj = c / nc, ci = c - cj * nc;      // cell row (y), cell column (x)
+            const int xlo = s_lo[ci], xhi = s_hi[ci], ylo = s_lo[cj], yhi = s_hi[cj];
+            const int ww = xhi - xlo + 1, hh = yhi - ylo + 1;
+            if (ww > 0 && hh > 0) {
+                const int count = ww * hh;
+                for (int t = lane; t < count; t += 32) {
+                    const int ry = t / ww;
+                    const int px = xlo + (t - ry * ww), py = ylo + ry;
+                    const int idx = py * fs + px;
+                    const int b = s_bin[idx];
+                    if (b >= 0) {
+                        const float wx = (s_sbin[px] == ci) ? s_sw1[px] : s_sw2[px];
+                        const float wy = (s_sbin[py] == cj) ? s_sw1[py] : s_sw2[py];
+                        const float v = __fmul_rn(__fmul_rn(s_gmag[idx], wx), wy);   // grad * wx * wy
+                        priv[b * 32 + lane] = __fadd_rn(priv[b * 32 + lane], v);
+                    }
+                }
+            }
+            __syncwarp();
+            for (int b = 0; b < 2 * K; ++b) {
+                float v = priv[b * 32 + lane];
+                priv[b * 32 + lane] = 0.f;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
+                if (lane == 0) s_hist[b * cells + c] = v;
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+
+    // ---- S4: undirected cell energy (hog.c:875-890) -------------------------------------------
+    for (int c = tid; c < cells; c += kHogThreads) {
+        float e = 0.f;
+        for (int k = 0; k < K; ++k) {
+            const float h = __fadd_rn(s_hist[k * cells + c], s_hist[(k + K) * cells + c]);
+            e = __fadd_rn(e, __fmul_rn(h, h));
+        }
+        s_energy[c] = e;
+    }
+    __syncthreads();
+
+    // ---- S5: the four block factors of each cell, in double (hog.c:930-982) ------------------
+    for (int i = tid; i < cells * 4; i += kHogThreads) {
+        const int c = i >> 2, f = i & 3;
+        const int y = c / nc, x = c - y * nc;
+        const int xm = max(x - 1, 0), xp = min(x + 1, nc - 1);
+        const int ym = max(y - 1, 0), yp = min(y + 1, nc - 1);
+        // factor1: n1+n2+n4+n5, factor2: n2+n3+n5+n6, factor3: n4+n5+n7+n8, factor4: n5+n6+n8+n9
+        const int xa = (f & 1) ? x : xm, xb = (f & 1) ? xp : x;
+        const int ya = (f & 2) ? y : ym, yb = (f & 2) ? yp : y;
+        double s = (double)s_energy[xa + ya * nc];
+        s = __dadd_rn(s, (double)s_energy[xb + ya * nc]);
+        s = __dadd_rn(s, (double)s_energy[xa + yb * nc]);
+        s = __dadd_rn(s, (double)s_energy[xb + yb * nc]);
+        s = __dadd_rn(s, 1e-4);
+        s_fac[i] = __ddiv_rn(1.0, sqrt(s));
+    }
+    __syncthreads();
+
+    // ---- S6: normalise, clamp at 0.2, project (hog.c:985-1044); s_gmag is dead, reuse as s_hc -
+    for (int i = tid; i < cells * K; i += kHogThreads) {
+        const int k = i / cells, c = i - k * cells;
+        const int cj = c / nc, ci = c - cj * nc;
+        const int oc = ci * nc + cj;                        // per-dimension transpose, adaptive_vlhog.hpp:168-174
+        const double ha = (double)s_hist[k * cells + c];
+        const double hb = (double)s_hist[(k + K) * cells + c];
+        double sa = 0.0, sb = 0.0, sc = 0.0;
+        double hcv[4];
+#pragma unroll
+        for (int f = 0; f < 4; ++f) {
+            const double fac = s_fac[c * 4 + f];
+            double haf = __dmul_rn(fac, ha);
+            double hbf = __dmul_rn(fac, hb);
+            double hcf = __dadd_rn(haf, hbf);
+            haf = (0.2 < haf) ? 0.2 : haf;
+            hbf = (0.2 < hbf) ? 0.2 : hbf;
+            hcf = (0.2 < hcf) ? 0.2 : hcf;
+            hcv[f] = hcf;
+            sa = (f == 0) ? haf : __dadd_rn(sa, haf);
+            sb = (f == 0) ? hbf : __dadd_rn(sb, hbf);
+            sc = (f == 0) ? hcf : __dadd_rn(sc, hcf);
+            s_hc[(c * K + k) * 4 + f] = hcf;
+        }
+        if (a.variant == 1) {                               // UoCTTI
+            s_feat[k * cells + oc] = (float)__dmul_rn(0.5, sa);
+            s_feat[(k + K) * cells + oc] = (float)__dmul_rn(0.5, sb);
+            s_feat[(k + 2 * K) * cells + oc] = (float)__dmul_rn(0.5, sc);
+        } else {                                            // Dalal-Triggs
+#pragma unroll
+            for (int f = 0; f < 4; ++f) s_feat[(k + f * K) * cells + oc] = (float)hcv[f];
+        }
+    }
+    __syncthreads();
+
+    // ---- S7: texture dims = 1/sqrt(18) * sum_k hc_f, summed in ascending k (hog.c:1046-1053) -
+    if (a.variant == 1) {
+        for (int i = tid; i < cells * 4; i += kHogThreads) {
+            const int c = i >> 2, f = i & 3;
+            const int cj = c / nc, ci = c - cj * nc;
+            double t = 0.0;
+            for (int k = 0; k < K; ++k) t = __dadd_rn(t, s_hc[(c * K + k) * 4 + f]);
+            const float c18 = __fdiv_rn(1.0f, __fsqrt_rn(18.0f));
+            s_feat[(3 * K + f) * cells + ci * nc + cj] = (float)__dmul_rn((double)c18, t);
+        }
+        __syncthreads();
+    }
+
+    // ---- S8: coalesced write of this landmark's slice of the feature row ---------------------
+    if (a.A) {
+        const int per_lm = cells * dd;
+        float* __restrict__ out = a.A + (long long)sample * a.ld + (long long)lm * per_lm;
+        for (int i = tid; i < per_lm; i += kHogThreads) out[i] = s_feat[i];
+        if (lm == 0 && tid == 0) a.A[(long long)sample * a.ld + (long long)a.L * per_lm] = 1.0f;   // bias, :182-183
+    }
+}
+
+int launch_hog(sd_ctx* ctx, const sd_image_batch* images, const int32_t* d_image_index, const float* d_x,
+               int64_t ldx, int N, int L, const sd_normalisation* eyes, const sd_hog_param* p, float* d_A,
+               int64_t ld, int32_t* d_geometry, uint8_t* d_patches, int8_t* d_bins)
+{
+    SD_REQUIRE(ctx, images && images->d_data && d_x && p, "null argument");
+    SD_REQUIRE(ctx, N >= 0 && L >= 1, "bad sample / landmark count");
+    SD_REQUIRE(ctx, p->variant == 0 || p->variant == 1, "unknown HOG variant");
+    SD_REQUIRE(ctx, p->num_bins >= 1 && p->num_bins <= SD_MAX_BINS, "num_bins must be in [1,16]");
+    SD_REQUIRE(ctx, p->num_cells >= 1 && p->cell_size >= 1, "bad cell configuration");
+    const int fs = p->num_cells * p->cell_size;
+    SD_REQUIRE(ctx, fs > 3 && fs <= 256, "resized patch must be 4..256 px (hog.c:545-546 asserts > 3)");
+    SD_REQUIRE(ctx, (fs + p->cell_size / 2) / p->cell_size == p->num_cells, "hogWidth != num_cells");
+    SD_REQUIRE(ctx, ldx >= 2 * L, "ldx < 2L");
+    if (N == 0) return SD_OK;
+    if (!eyes || eyes->kind != 1) return sd_fail(ctx, SD_ERR_INVALID, "HogTransform needs the eye landmark indices (adaptive patch size)");
+
+    HogArgs a;
+    int rc = sd_eyes_to_dev(ctx, eyes, L, &a.eyes);
+    if (rc) return rc;
+    a.images = images->d_data;
+    a.width = images->width; a.height = images->height; a.row_stride = images->row_stride;
+    a.image_stride = images->image_stride; a.image_count = images->count;
+    a.image_index = d_image_index;
+    if (!d_image_index) SD_REQUIRE(ctx, images->count >= N, "fewer images than samples and no image index");
+    a.x = d_x; a.ldx = ldx; a.N = N; a.L = L;
+    a.variant = p->variant; a.nc = p->num_cells; a.cs = p->cell_size; a.K = p->num_bins; a.fs = fs;
+    a.dd = p->variant == 1 ? 3 * p->num_bins + 4 : 4 * p->num_bins;
+    a.rel = p->relative_patch_size;
+    for (int k = 0; k < SD_MAX_BINS; ++k) { a.ox[k] = 0.f; a.oy[k] = 0.f; }
+    for (int k = 0; k < p->num_bins; ++k) {              // hog.c:195-204 (host libm, as the reference)
+        const double angle = k * 3.141592653589793 / p->num_bins;
+        a.ox[k] = (float)cos(angle);
+        a.oy[k] = (float)sin(angle);
+    }
+    a.A = d_A; a.ld = ld;
+    if (d_A) SD_REQUIRE(ctx, ld >= (int64_t)L * a.nc * a.nc * a.dd + 1, "ld < feature length");
+    a.geometry = d_geometry; a.patches = d_patches; a.bins = d_bins;
+    a.status = reinterpret_cast<int*>(ctx->d_scratch);   // bit 0: empty patch, bit 1: bad image index
+
+    const HogSmem lay = hog_smem_layout(fs, a.nc, a.K, a.dd);
+    SD_REQUIRE(ctx, lay.total <= 227 * 1024, "HOG configuration needs more than 227 KB of shared memory");
+    const long long blocks = (long long)N * L;
+    SD_REQUIRE(ctx, blocks < 2147483647LL, "too many patches for one launch");
+    auto kern = hog_patch_kernel<0>;
+    if (a.K == 4) kern = hog_patch_kernel<4>;
+    else if (a.K == 9) kern = hog_patch_kernel<9>;
+    SD_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, lay.total));
+    kern<<<(unsigned)blocks, kHogThreads, lay.total, ctx->stream>>>(a);
+    SD_LAUNCH_CHECK(ctx, "hog_patch_kernel");
+    return SD_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sd_hog_feature_length(int num_landmarks, const sd_hog_param* p)
+{
+    if (!p) return -1;
+    const int dd = p->variant == 1 ? 3 * p->num_bins + 4 : 4 * p->num_bins;
+    return num_landmarks * p->num_cells * p->num_cells * dd + 1;
+}
+
+int sd_hog_batch(sd_ctx* ctx, const sd_image_batch* images, const int32_t* d_image_index, const float* d_x,
+                 int64_t ldx, int num_samples, int num_landmarks, const sd_normalisation* eyes,
+                 const sd_hog_param* p, float* d_A, int64_t ld)
+{
+    if (!ctx) return SD_ERR_INVALID;
+    SD_REQUIRE(ctx, d_A, "null output");
+    return launch_hog(ctx, images, d_image_index, d_x, ldx, num_samples, num_landmarks, eyes, p, d_A, ld,
+                      nullptr, nullptr, nullptr);
+}
+
+int sd_hog_debug(sd_ctx* ctx, const sd_image_batch* images, const int32_t* d_image_index, const float* d_x,
+                 int64_t ldx, int num_samples, int num_landmarks, const sd_normalisation* eyes,
+                 const sd_hog_param* p, int32_t* d_geometry, uint8_t* d_patches, int8_t* d_bins)
+{
+    if (!ctx) return SD_ERR_INVALID;
+    return launch_hog(ctx, images, d_image_index, d_x, ldx, num_samples, num_landmarks, eyes, p, nullptr, 0,
+                      d_geometry, d_patches, d_bins);
+}
+
+}  // extern "C"

@@ -1,0 +1,116 @@
+// Internal definitions shared by the .cu translation units of libsd_b200.so.
+// Nothing here is part of the C ABI (include/sd_b200.h).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "sd_b200.h"
+
+#define SD_MAX_EYES 4
+#define SD_MAX_BINS 16   // undirected orientations K supported by the HOG kernel
+
+enum { SD_WS_GRAM_EXT = 0, SD_WS_SPLIT_HI, SD_WS_SPLIT_LO, SD_WS_FEATURES, SD_WS_SCRATCH, SD_WS_DIAGINV,
+       SD_WS_PARTIAL, SD_WS_COUNT };
+
+struct sd_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    cudaStream_t copy_stream = nullptr;   // host<->device staging for sd_detect_batch_host
+    std::string err;
+    int64_t launches = 0;
+    int sm_count = 148;
+    int gram_mode = 0;
+    float timings[4] = {0, 0, 0, 0};
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    void* ws[SD_WS_COUNT] = {};
+    size_t ws_bytes[SD_WS_COUNT] = {};
+    // pinned scratch for small device->host results (lambda, residual, status flags)
+    void* h_scratch = nullptr;
+    void* d_scratch = nullptr;   // 4 KB
+    // staging buffers of sd_detect_batch_host
+    void* d_stage[2] = {nullptr, nullptr};
+    size_t stage_bytes[2] = {0, 0};
+    cudaEvent_t stage_ev[2] = {nullptr, nullptr};
+    cudaEvent_t stage_done[2] = {nullptr, nullptr};
+};
+
+int sd_fail(sd_ctx* ctx, int code, const char* fmt, ...);
+int sd_check_cuda(sd_ctx* ctx, cudaError_t e, const char* what);
+// grow-only workspace; returns nullptr (and sets the error) on failure
+void* sd_workspace(sd_ctx* ctx, int slot, size_t bytes);
+
+#define SD_CUDA(ctx, call)                                                        \
+    do {                                                                          \
+        cudaError_t _e = (call);                                                  \
+        if (_e != cudaSuccess) return sd_check_cuda((ctx), _e, #call);            \
+    } while (0)
+
+#define SD_LAUNCH_CHECK(ctx, name)                                                \
+    do {                                                                          \
+        (ctx)->launches++;                                                        \
+        cudaError_t _e = cudaGetLastError();                                      \
+        if (_e != cudaSuccess) return sd_check_cuda((ctx), _e, name);             \
+    } while (0)
+
+#define SD_REQUIRE(ctx, cond, msg)                                                \
+    do {                                                                          \
+        if (!(cond)) return sd_fail((ctx), SD_ERR_INVALID, "%s: %s", __func__, msg); \
+    } while (0)
+
+static inline int sd_div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---- internal entry points shared between translation units ---------------------------------
+
+// C[i,j] = beta*C[i,j] + alpha * sum_{k<K} S[k,i] * S[k,j]   for i < MI, j < NJ, restricted to the
+// tiles that intersect j >= i (upper triangle).  S: K x NJ row-major (lds), C: MI x NJ (ldc).
+// Used for the Gram matrix [A^T A | A^T B] and for the Cholesky trailing update.
+int sd_syrk_update(sd_ctx* ctx, const float* d_S, int64_t lds, int K, int MI, int NJ,
+                   float* d_C, int64_t ldc, float alpha, float beta);
+int sd_syrk_simt(sd_ctx* ctx, const float* d_S, int64_t lds, int K, int MI, int NJ,
+                 float* d_C, int64_t ldc, float alpha, float beta);
+int sd_syrk_tc(sd_ctx* ctx, const float* d_S, int64_t lds, int K, int MI, int NJ,
+               float* d_C, int64_t ldc, float alpha, float beta, int passes);
+bool sd_syrk_tc_supported(const float* d_S, int64_t lds, int K, int MI, int NJ, const float* d_C, int64_t ldc);
+
+// device-side normalisation factors, shared by the HOG and cascade kernels
+struct sd_eyes_dev {
+    int kind;
+    int n_right, n_left;
+    int right_idx[SD_MAX_EYES];
+    int left_idx[SD_MAX_EYES];
+};
+int sd_eyes_to_dev(sd_ctx* ctx, const sd_normalisation* n, int num_landmarks, sd_eyes_dev* out);
+
+#ifdef __CUDACC__
+// Inter-eye distance exactly as helpers.hpp:136-160 evaluates it: eye centres are float sums
+// scaled by the float reciprocal of the count (cv::Vec /= float), the difference is taken in float,
+// squares are accumulated in double (cv::norm NORM_L2) and the root is a double sqrt.
+__device__ __forceinline__ double sd_device_ied(const float* __restrict__ row, int L, const sd_eyes_dev& e)
+{
+    float rx = 0.f, ry = 0.f, lx = 0.f, ly = 0.f;
+    for (int i = 0; i < e.n_right; ++i) {
+        rx = __fadd_rn(rx, row[e.right_idx[i]]);
+        ry = __fadd_rn(ry, row[e.right_idx[i] + L]);
+    }
+    const float ir = __fdiv_rn(1.0f, (float)e.n_right);
+    rx = __fmul_rn(rx, ir);
+    ry = __fmul_rn(ry, ir);
+    for (int i = 0; i < e.n_left; ++i) {
+        lx = __fadd_rn(lx, row[e.left_idx[i]]);
+        ly = __fadd_rn(ly, row[e.left_idx[i] + L]);
+    }
+    const float il = __fdiv_rn(1.0f, (float)e.n_left);
+    lx = __fmul_rn(lx, il);
+    ly = __fmul_rn(ly, il);
+    const double dx = (double)__fsub_rn(rx, lx);
+    const double dy = (double)__fsub_rn(ry, ly);
+    return sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+}
+#endif

@@ -1,0 +1,738 @@
+// LinearRegressor / Solver / cascade-step kernels of libsd_b200.so.
+//
+//   sd_gram            [A^T A | A^T B]                         regressors.hpp:208,225 (verbose_solver.hpp:67,94)
+//   sd_solve_gram      lambda rule + diagonal + factorise/solve regressors.hpp:126-148,215-225
+//   sd_learn           = sd_gram + sd_solve_gram                regressors.hpp:345-350
+//   sd_predict         values * x                               regressors.hpp:377-381
+//   sd_test_residual   ||pred - labels|| / ||labels||           regressors.hpp:361-369
+//   sd_cascade_targets b = (x - x_gt) (.) norm(x)               superviseddescent.hpp:199-205
+//   sd_cascade_update  x <- x - (A X) (.) 1/norm(x)             superviseddescent.hpp:209-215,296-301,336-339
+//
+// Factorisation: the reference calls Eigen::PartialPivLU on A^T A + Lambda.  That matrix is symmetric
+// positive definite whenever lambda > 0 with an all-ones bias column (hard part 2), so for
+// D > kLuMaxDim a blocked right-looking Cholesky (G = U^T U) is used, whose trailing update is the same
+// "Gram-like" product as A^T A and runs on the tensor-core SYRK (sd_gram_tc.cu).  For D <= kLuMaxDim a
+// single-CTA LU with partial pivoting restates the reference's solver operation by operation (this is
+// the path the reference's unit tests exercise, including lambda = 0).
+#include "sd_internal.cuh"
+
+#include <cmath>
+#include <cstring>
+
+namespace {
+
+constexpr int kLuMaxDim = 256;   // D up to which the faithful partial-pivot LU is used
+constexpr int kCholNb = 128;     // Cholesky block size
+
+// =================================================================================================
+// SIMT SYRK-like update: C[i,j] = beta*C[i,j] + alpha * sum_k S[k,i]*S[k,j]  (upper-triangle tiles)
+// =================================================================================================
+constexpr int ST = 64;    // tile edge
+constexpr int SK = 16;    // k chunk
+
+__global__ void __launch_bounds__(256) syrk_simt_kernel(const float* __restrict__ S, long long lds, int K, int MI, int NJ,
+                                                        float* __restrict__ C, long long ldc, float alpha, float beta,
+                                                        float* __restrict__ partial, int k_per_split)
+{
+    const int tj = blockIdx.x, ti = blockIdx.y;
+    if (tj * ST + ST - 1 < ti * ST) return;               // tile entirely below the diagonal
+    __shared__ __align__(16) float As[SK][ST + 4];
+    __shared__ __align__(16) float Bs[SK][ST + 4];
+    const int tid = threadIdx.x;
+    const int ty = tid >> 4, tx = tid & 15;
+    const int i0 = ti * ST, j0 = tj * ST;
+    const int kbeg = blockIdx.z * k_per_split;
+    const int kend = min(K, kbeg + k_per_split);
+    float acc[4][4] = {};
+    const int lk = tid >> 4;          // 0..15 : row of the k chunk
+    const int lc = (tid & 15) * 4;    // 0..60 : column inside the tile
+    for (int k0 = kbeg; k0 < kend; k0 += SK) {
+        const int k = k0 + lk;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int ia = i0 + lc + e, jb = j0 + lc + e;
+            As[lk][lc + e] = (k < kend && ia < MI) ? S[(long long)k * lds + ia] : 0.f;
+            Bs[lk][lc + e] = (k < kend && jb < NJ) ? S[(long long)k * lds + jb] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < SK; ++kk) {
+            const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+            const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(av[r], bv[c], acc[r][c]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int i = i0 + ty * 4 + r;
+        if (i >= MI) continue;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int j = j0 + tx * 4 + c;
+            if (j >= NJ) continue;
+            if (partial) {
+                partial[((long long)blockIdx.z * MI + i) * NJ + j] = acc[r][c];
+            } else {
+                float* p = C + (long long)i * ldc + j;
+                *p = (beta == 0.f) ? alpha * acc[r][c] : fmaf(alpha, acc[r][c], beta * (*p));
+            }
+        }
+    }
+}
+
+__global__ void syrk_reduce_kernel(const float* __restrict__ partial, int splits, int MI, int NJ,
+                                   float* __restrict__ C, long long ldc, float alpha, float beta)
+{
+    const long long total = (long long)MI * NJ;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(idx / NJ), j = (int)(idx - (long long)i * NJ);
+        if ((j / ST) * ST + ST - 1 < (i / ST) * ST) continue;      // tile not computed
+        float s = 0.f;
+        for (int z = 0; z < splits; ++z) s += partial[(long long)z * total + idx];   // fixed order
+        float* p = C + (long long)i * ldc + j;
+        *p = (beta == 0.f) ? alpha * s : fmaf(alpha, s, beta * (*p));
+    }
+}
+
+// =================================================================================================
+// GEMM NN: C[N x M] = beta*C + alpha * A[N x D] * B[D x M], with the cascade-update epilogue
+// =================================================================================================
+constexpr int GT = 64, GK = 16;
+
+struct GemmEpilogue {
+    int mode;                 // 0: plain store, 1: x_next = x - acc * (1/norm(x))
+    const float* x;           // mode 1: current landmarks [N x M]
+    float* x_next;
+    sd_eyes_dev eyes;
+};
+
+__global__ void __launch_bounds__(256) gemm_nn_kernel(const float* __restrict__ A, long long lda, int N, int D,
+                                                      const float* __restrict__ B, long long ldb, int M,
+                                                      float* __restrict__ C, long long ldc, float alpha, float beta,
+                                                      const GemmEpilogue ep)
+{
+    __shared__ __align__(16) float As[GK][GT + 4];     // transposed: As[k][row]
+    __shared__ __align__(16) float Bs[GK][GT + 4];
+    __shared__ float s_scale[GT];
+    const int tid = threadIdx.x;
+    const int ty = tid >> 4, tx = tid & 15;
+    const int r0 = blockIdx.y * GT, c0 = blockIdx.x * GT;
+    if (ep.mode == 1 && tid < GT) {
+        const int r = r0 + tid;
+        float inv_n = 1.0f;
+        if (r < N && ep.eyes.kind == 1) {
+            const double ied = sd_device_ied(ep.x + (long long)r * M, M / 2, ep.eyes);
+            const float n = (float)__ddiv_rn(1.0, ied);      // ones / ied           (model.hpp:97)
+            inv_n = __fdiv_rn(1.0f, n);                      // 1 / normalisation    (superviseddescent.hpp:213)
+        }
+        s_scale[tid] = inv_n;
+    }
+    float acc[4][4] = {};
+    const int la_r = tid >> 2;           // 0..63 row
+    const int la_k = (tid & 3) * 4;      // 0..12 k offset
+    const int lb_k = tid >> 4;           // 0..15
+    const int lb_c = (tid & 15) * 4;     // 0..60
+    for (int k0 = 0; k0 < D; k0 += GK) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int r = r0 + la_r, k = k0 + la_k + e;
+            As[la_k + e][la_r] = (r < N && k < D) ? A[(long long)r * lda + k] : 0.f;
+            const int kb = k0 + lb_k, c = c0 + lb_c + e;
+            Bs[lb_k][lb_c + e] = (kb < D && c < M) ? B[(long long)kb * ldb + c] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < GK; ++kk) {
+            const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+            const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(av[r], bv[c], acc[r][c]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int i = r0 + ty * 4 + r;
+        if (i >= N) continue;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int j = c0 + tx * 4 + c;
+            if (j >= M) continue;
+            if (ep.mode == 1) {
+                const float upd = __fmul_rn(acc[r][c], s_scale[ty * 4 + r]);
+                ep.x_next[(long long)i * M + j] = __fsub_rn(ep.x[(long long)i * M + j], upd);
+            } else {
+                float* p = C + (long long)i * ldc + j;
+                *p = (beta == 0.f) ? alpha * acc[r][c] : fmaf(alpha, acc[r][c], beta * (*p));
+            }
+        }
+    }
+}
+
+int launch_gemm_nn(sd_ctx* ctx, const float* A, int64_t lda, int N, int D, const float* B, int64_t ldb, int M,
+                   float* C, int64_t ldc, float alpha, float beta, const GemmEpilogue& ep)
+{
+    if (N <= 0 || M <= 0) return SD_OK;
+    dim3 grid(sd_div_up(M, GT), sd_div_up(N, GT));
+    SD_REQUIRE(ctx, grid.y <= 65535, "too many rows for one GEMM launch");
+    gemm_nn_kernel<<<grid, 256, 0, ctx->stream>>>(A, lda, N, D, B, ldb, M, C, ldc, alpha, beta, ep);
+    SD_LAUNCH_CHECK(ctx, "gemm_nn_kernel");
+    return SD_OK;
+}
+
+// =================================================================================================
+// small element-wise kernels
+// =================================================================================================
+__global__ void pack_ext_kernel(const float* __restrict__ A, long long lda, const float* __restrict__ B, long long ldb,
+                                int N, int D, int M, float* __restrict__ E, long long lde)
+{
+    const long long total = (long long)N * lde;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const long long n = idx / lde;
+        const int c = (int)(idx - n * lde);
+        float v = 0.f;
+        if (c < D) v = A[n * lda + c];
+        else if (c < D + M) v = B[n * ldb + (c - D)];
+        E[idx] = v;
+    }
+}
+
+__global__ void targets_kernel(const float* __restrict__ x, const float* __restrict__ x_gt, int N, int P,
+                               const sd_eyes_dev eyes, float* __restrict__ B, long long ldb)
+{
+    const int i = blockIdx.x * blockDim.y + threadIdx.y;
+    if (i >= N) return;
+    float n = 1.0f;
+    if (eyes.kind == 1) n = (float)__ddiv_rn(1.0, sd_device_ied(x + (long long)i * P, P / 2, eyes));
+    for (int j = threadIdx.x; j < P; j += blockDim.x)
+        B[(long long)i * ldb + j] = __fmul_rn(__fsub_rn(x[(long long)i * P + j], x_gt[(long long)i * P + j]), n);
+}
+
+__global__ void subtract_kernel(float* __restrict__ A, long long lda, const float* __restrict__ T, long long ldt, int N, int D)
+{
+    const long long total = (long long)N * D;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const long long n = idx / D;
+        const int c = (int)(idx - n * D);
+        A[n * lda + c] = __fsub_rn(A[n * lda + c], T[n * ldt + c]);
+    }
+}
+
+// ---- regulariser (regressors.hpp:126-148) ---------------------------------------------------------
+// sum of squares of the full symmetric D x D matrix from its upper triangle, in double (cv::norm)
+__global__ void frob_upper_kernel(const float* __restrict__ G, long long ldg, int D, double* __restrict__ out)
+{
+    double s = 0.0;
+    const long long total = (long long)D * D;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(idx / D), j = (int)(idx - (long long)i * D);
+        if (j < i) continue;
+        const double v = (double)G[(long long)i * ldg + j];
+        s += (j == i) ? v * v : 2.0 * v * v;
+    }
+    __shared__ double red[256];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[blockIdx.x] = red[0];
+}
+
+// scal[0] <- lambda ; then the diagonal gets lambda (0 for the bias row if !regularise_last_row)
+__global__ void lambda_kernel(const double* __restrict__ partial, int nparts, int type, float param, int n_train, float* __restrict__ scal)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        float lambda = param;
+        if (type == 1) {
+            double s = 0.0;
+            for (int i = 0; i < nparts; ++i) s += partial[i];
+            // lambda * (float)cv::norm(AtA) / (float)num_training_elements  (regressors.hpp:135)
+            lambda = __fdiv_rn(__fmul_rn(param, (float)sqrt(s)), (float)n_train);
+        }
+        scal[0] = lambda;
+    }
+}
+
+__global__ void add_diag_kernel(float* __restrict__ G, long long ldg, int D, const float* __restrict__ scal, int regularise_last_row)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= D) return;
+    const float lambda = (i == D - 1 && !regularise_last_row) ? 0.0f : scal[0];
+    G[(long long)i * ldg + i] = __fadd_rn(G[(long long)i * ldg + i], lambda);
+}
+
+// ---- LU with partial pivoting, single CTA (regressors.hpp:224-225 for small systems) ---------------
+// G: D x W row-major (W = D + M: matrix and right-hand sides side by side).  On exit the RHS columns hold X.
+__global__ void __launch_bounds__(1024) lu_small_kernel(float* __restrict__ G, long long ldg, int D, int M, int* __restrict__ status)
+{
+    __shared__ float s_val[32];
+    __shared__ int s_idx[32];
+    __shared__ int s_piv;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int W = D + M;
+    // mirror the upper triangle into the lower one (the SYRK only wrote tiles with j >= i)
+    for (int idx = tid; idx < D * D; idx += nthr) {
+        const int i = idx / D, j = idx - i * D;
+        if (j < i) G[(long long)i * ldg + j] = G[(long long)j * ldg + i];
+    }
+    __syncthreads();
+    for (int k = 0; k < D; ++k) {
+        // pivot search: largest |G[i][k]|, first occurrence wins (ascending i), as the oracle
+        float best = -1.f;
+        int bi = k;
+        for (int i = k + tid; i < D; i += nthr) {
+            const float v = fabsf(G[(long long)i * ldg + k]);
+            if (v > best) { best = v; bi = i; }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_down_sync(0xffffffffu, best, o);
+            const int oi = __shfl_down_sync(0xffffffffu, bi, o);
+            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        }
+        if ((tid & 31) == 0) { s_val[tid >> 5] = best; s_idx[tid >> 5] = bi; }
+        __syncthreads();
+        if (tid < 32) {
+            best = tid < (nthr >> 5) ? s_val[tid] : -1.f;
+            bi = tid < (nthr >> 5) ? s_idx[tid] : 0x7fffffff;
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_down_sync(0xffffffffu, best, o);
+                const int oi = __shfl_down_sync(0xffffffffu, bi, o);
+                if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+            }
+            if (tid == 0) {
+                s_piv = bi;
+                if (!(best > 0.f)) atomicOr(status, 4);    // singular: the reference would return inf/nan
+            }
+        }
+        __syncthreads();
+        const int piv = s_piv;
+        if (piv != k) {
+            for (int j = tid; j < W; j += nthr) {
+                const float t = G[(long long)k * ldg + j];
+                G[(long long)k * ldg + j] = G[(long long)piv * ldg + j];
+                G[(long long)piv * ldg + j] = t;
+            }
+        }
+        __syncthreads();
+        const float pv = G[(long long)k * ldg + k];
+        // multipliers
+        for (int i = k + 1 + tid; i < D; i += nthr) G[(long long)i * ldg + k] = __fdiv_rn(G[(long long)i * ldg + k], pv);
+        __syncthreads();
+        // trailing update incl. right-hand sides (un-fused mul/sub: the oracle's x86 arithmetic)
+        const int rows = D - k - 1, cols = W - k - 1;
+        for (int idx = tid; idx < rows * cols; idx += nthr) {
+            const int i = k + 1 + idx / cols, j = k + 1 + idx % cols;
+            const float l = G[(long long)i * ldg + k];
+            if (l != 0.f) G[(long long)i * ldg + j] = __fsub_rn(G[(long long)i * ldg + j], __fmul_rn(l, G[(long long)k * ldg + j]));
+        }
+        __syncthreads();
+    }
+    // back substitution, one thread per right-hand side column
+    for (int c = tid; c < M; c += nthr) {
+        for (int i = D - 1; i >= 0; --i) {
+            float r = G[(long long)i * ldg + D + c];
+            for (int k = i + 1; k < D; ++k) r = __fsub_rn(r, __fmul_rn(G[(long long)i * ldg + k], G[(long long)k * ldg + D + c]));
+            G[(long long)i * ldg + D + c] = __fdiv_rn(r, G[(long long)i * ldg + i]);
+        }
+    }
+}
+
+__global__ void copy_block_kernel(const float* __restrict__ src, long long lds, int rows, int cols, float* __restrict__ dst, long long ldd)
+{
+    const long long total = (long long)rows * cols;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const long long r = idx / cols;
+        const int c = (int)(idx - r * cols);
+        dst[r * ldd + c] = src[r * lds + c];
+    }
+}
+
+// ---- blocked Cholesky G = U^T U (upper), right-looking ---------------------------------------------
+// factor one nb x nb diagonal block in shared memory
+__global__ void __launch_bounds__(512) potrf_block_kernel(float* __restrict__ G, long long ldg, int nb, int* __restrict__ status)
+{
+    extern __shared__ float sU[];   // nb x (nb+1)
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int ld = nb + 1;
+    for (int idx = tid; idx < nb * nb; idx += nthr) {
+        const int i = idx / nb, j = idx - i * nb;
+        sU[i * ld + j] = (j >= i) ? G[(long long)i * ldg + j] : 0.f;
+    }
+    __syncthreads();
+    for (int k = 0; k < nb; ++k) {
+        const float akk = sU[k * ld + k];
+        if (!(akk > 0.f) && tid == 0) atomicOr(status, 8);   // not positive definite
+        const float d = sqrtf(fabsf(akk) > 0.f ? fabsf(akk) : 1.f);
+        __syncthreads();
+        for (int j = k + tid; j < nb; j += nthr) sU[k * ld + j] = (j == k) ? d : sU[k * ld + j] / d;
+        __syncthreads();
+        const int rem = nb - k - 1;
+        for (int idx = tid; idx < rem * rem; idx += nthr) {
+            const int i = k + 1 + idx / rem, j = k + 1 + idx % rem;
+            if (j >= i) sU[i * ld + j] = fmaf(-sU[k * ld + i], sU[k * ld + j], sU[i * ld + j]);
+        }
+        __syncthreads();
+    }
+    for (int idx = tid; idx < nb * nb; idx += nthr) {
+        const int i = idx / nb, j = idx - i * nb;
+        if (j >= i) G[(long long)i * ldg + j] = sU[i * ld + j];
+    }
+}
+
+// U12 <- U11^-T * G12 : forward substitution, one thread per column of the row panel (in place).
+// U11 (nb x nb, upper) is staged in shared memory; the column lives in shared memory as well.
+__global__ void __launch_bounds__(128) trsm_panel_kernel(const float* __restrict__ U11, long long ldu, int nb,
+                                                         float* __restrict__ P, long long ldp, int cols)
+{
+    extern __shared__ float sm[];
+    float* sU = sm;                       // nb x (nb+1)
+    float* sY = sm + nb * (nb + 1);       // nb x 128 (column per thread)
+    const int tid = threadIdx.x;
+    const int ld = nb + 1;
+    for (int idx = tid; idx < nb * nb; idx += blockDim.x) {
+        const int i = idx / nb, j = idx - i * nb;
+        sU[i * ld + j] = (j >= i) ? U11[(long long)i * ldu + j] : 0.f;
+    }
+    __syncthreads();
+    const int c = blockIdx.x * blockDim.x + tid;
+    if (c >= cols) return;
+    for (int r = 0; r < nb; ++r) {
+        float v = P[(long long)r * ldp + c];
+        float s0 = 0.f, s1 = 0.f;
+        int p = 0;
+        for (; p + 1 < r; p += 2) {
+            s0 = fmaf(sU[p * ld + r], sY[p * 128 + tid], s0);
+            s1 = fmaf(sU[(p + 1) * ld + r], sY[(p + 1) * 128 + tid], s1);
+        }
+        if (p < r) s0 = fmaf(sU[p * ld + r], sY[p * 128 + tid], s0);
+        v = (v - (s0 + s1)) / sU[r * ld + r];
+        sY[r * 128 + tid] = v;
+        P[(long long)r * ldp + c] = v;
+    }
+}
+
+// X_j <- U_jj^-1 * Y_j : back substitution of one diagonal block, one thread per right-hand side
+__global__ void __launch_bounds__(256) trsv_block_kernel(const float* __restrict__ U, long long ldu, int nb,
+                                                         float* __restrict__ Y, long long ldy, int M)
+{
+    extern __shared__ float sm[];
+    float* sU = sm;                    // nb x (nb+1)
+    const int ld = nb + 1;
+    for (int idx = threadIdx.x; idx < nb * nb; idx += blockDim.x) {
+        const int i = idx / nb, j = idx - i * nb;
+        sU[i * ld + j] = (j >= i) ? U[(long long)i * ldu + j] : 0.f;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < M; c += blockDim.x) {
+        for (int i = nb - 1; i >= 0; --i) {
+            float r = Y[(long long)i * ldy + c];
+            for (int k = i + 1; k < nb; ++k) r = fmaf(-sU[i * ld + k], Y[(long long)k * ldy + c], r);
+            Y[(long long)i * ldy + c] = r / sU[i * ld + i];
+        }
+    }
+}
+
+int cholesky_solve(sd_ctx* ctx, float* G, int64_t ldg, int D, int M, float* X)
+{
+    int* status = reinterpret_cast<int*>(ctx->d_scratch);
+    const int W = D + M;
+    const size_t smem_potrf = (size_t)kCholNb * (kCholNb + 1) * 4;
+    const size_t smem_trsm = smem_potrf + (size_t)kCholNb * 128 * 4;
+    SD_CUDA(ctx, cudaFuncSetAttribute(potrf_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_potrf));
+    SD_CUDA(ctx, cudaFuncSetAttribute(trsm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_trsm));
+    SD_CUDA(ctx, cudaFuncSetAttribute(trsv_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_potrf));
+    // ---- factorisation, carrying the right-hand side columns along (Y = U^-T R) ----
+    for (int j = 0; j < D; j += kCholNb) {
+        const int nb = (D - j < kCholNb) ? D - j : kCholNb;
+        float* Gjj = G + (int64_t)j * ldg + j;
+        potrf_block_kernel<<<1, 512, (size_t)nb * (nb + 1) * 4, ctx->stream>>>(Gjj, ldg, nb, status);
+        SD_LAUNCH_CHECK(ctx, "potrf_block_kernel");
+        const int cols = W - j - nb;
+        if (cols > 0) {
+            float* P = Gjj + nb;
+            trsm_panel_kernel<<<sd_div_up(cols, 128), 128, (size_t)nb * (nb + 1) * 4 + (size_t)nb * 128 * 4, ctx->stream>>>(Gjj, ldg, nb, P, ldg, cols);
+            SD_LAUNCH_CHECK(ctx, "trsm_panel_kernel");
+            const int rest = D - j - nb;
+            if (rest > 0) {
+                // [G22 | R2] -= U12^T [U12 | Y1]
+                int rc = sd_syrk_update(ctx, P, ldg, nb, rest, cols, G + (int64_t)(j + nb) * ldg + (j + nb), ldg, -1.0f, 1.0f);
+                if (rc) return rc;
+            }
+        }
+    }
+    SD_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));   // end of "Decomposition"
+    // ---- back substitution U X = Y, right-looking over block columns from the last ----
+    const int nblocks = sd_div_up(D, kCholNb);
+    GemmEpilogue ep;
+    memset(&ep, 0, sizeof(ep));
+    for (int b = nblocks - 1; b >= 0; --b) {
+        const int j = b * kCholNb;
+        const int nb = (D - j < kCholNb) ? D - j : kCholNb;
+        float* Yj = G + (int64_t)j * ldg + D;
+        trsv_block_kernel<<<1, 256, (size_t)nb * (nb + 1) * 4, ctx->stream>>>(G + (int64_t)j * ldg + j, ldg, nb, Yj, ldg, M);
+        SD_LAUNCH_CHECK(ctx, "trsv_block_kernel");
+        if (j > 0) {
+            // Y[0:j] -= U[0:j, j:j+nb] * X_j
+            int rc = launch_gemm_nn(ctx, G + j, ldg, j, nb, Yj, ldg, M, G + D, ldg, -1.0f, 1.0f, ep);
+            if (rc) return rc;
+        }
+    }
+    copy_block_kernel<<<sd_div_up((int64_t)D * M, 256) > 1024 ? 1024 : sd_div_up((int64_t)D * M, 256), 256, 0, ctx->stream>>>(G + D, ldg, D, M, X, M);
+    SD_LAUNCH_CHECK(ctx, "copy_block_kernel");
+    return SD_OK;
+}
+
+int check_status(sd_ctx* ctx, const char* what)
+{
+    int* h = reinterpret_cast<int*>(ctx->h_scratch);
+    SD_CUDA(ctx, cudaMemcpyAsync(h, ctx->d_scratch, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const int st = h[0];
+    if (st) {
+        SD_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch, 0, sizeof(int), ctx->stream));
+        if (st & 8) return sd_fail(ctx, SD_ERR_NUMERIC, "%s: regularised AtA is not positive definite (increase lambda)", what);
+        if (st & 4) return sd_fail(ctx, SD_ERR_NUMERIC, "%s: singular system (zero pivot)", what);
+        if (st & 2) return sd_fail(ctx, SD_ERR_INVALID, "%s: image index out of range", what);
+        if (st & 1) return sd_fail(ctx, SD_ERR_INVALID, "%s: empty HOG patch (inter-eye distance too small)", what);
+    }
+    return SD_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+// internal dispatch
+// =================================================================================================
+int sd_syrk_simt(sd_ctx* ctx, const float* d_S, int64_t lds, int K, int MI, int NJ, float* d_C, int64_t ldc,
+                 float alpha, float beta)
+{
+    if (MI <= 0 || NJ <= 0) return SD_OK;
+    dim3 grid(sd_div_up(NJ, ST), sd_div_up(MI, ST), 1);
+    SD_REQUIRE(ctx, grid.y <= 65535, "matrix too large for the SIMT SYRK");
+    const long long tiles = (long long)grid.x * grid.y;
+    int splits = 1;
+    if (tiles < 2LL * ctx->sm_count && K > 2048) {
+        splits = (int)((4LL * ctx->sm_count + tiles - 1) / tiles);
+        const int maxs = sd_div_up(K, 512);
+        if (splits > maxs) splits = maxs;
+        if (splits > 64) splits = 64;
+        if (splits < 1) splits = 1;
+    }
+    if (splits == 1) {
+        syrk_simt_kernel<<<grid, 256, 0, ctx->stream>>>(d_S, lds, K, MI, NJ, d_C, ldc, alpha, beta, nullptr, K);
+        SD_LAUNCH_CHECK(ctx, "syrk_simt_kernel");
+    } else {
+        float* partial = (float*)sd_workspace(ctx, SD_WS_PARTIAL, (size_t)splits * MI * NJ * sizeof(float));
+        if (!partial) return SD_ERR_CUDA;
+        const int kps = sd_div_up(sd_div_up(K, splits), SK) * SK;
+        grid.z = sd_div_up(K, kps);
+        syrk_simt_kernel<<<grid, 256, 0, ctx->stream>>>(d_S, lds, K, MI, NJ, d_C, ldc, alpha, beta, partial, kps);
+        SD_LAUNCH_CHECK(ctx, "syrk_simt_kernel(split)");
+        const int blocks = sd_div_up((int64_t)MI * NJ, 256) > 2048 ? 2048 : sd_div_up((int64_t)MI * NJ, 256);
+        syrk_reduce_kernel<<<blocks, 256, 0, ctx->stream>>>(partial, (int)grid.z, MI, NJ, d_C, ldc, alpha, beta);
+        SD_LAUNCH_CHECK(ctx, "syrk_reduce_kernel");
+    }
+    return SD_OK;
+}
+
+int sd_syrk_update(sd_ctx* ctx, const float* d_S, int64_t lds, int K, int MI, int NJ, float* d_C, int64_t ldc,
+                   float alpha, float beta)
+{
+    const bool big = (int64_t)MI * NJ >= 256LL * 256LL && K >= 64;
+    if (ctx->gram_mode != 2 && big && sd_syrk_tc_supported(d_S, lds, K, MI, NJ, d_C, ldc))
+        return sd_syrk_tc(ctx, d_S, lds, K, MI, NJ, d_C, ldc, alpha, beta, ctx->gram_mode == 1 ? 1 : 3);
+    return sd_syrk_simt(ctx, d_S, lds, K, MI, NJ, d_C, ldc, alpha, beta);
+}
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+int sd_gram(sd_ctx* ctx, const float* d_A, int64_t lda, const float* d_B, int64_t ldb, int N, int D, int M,
+            float* d_G, int64_t ldg)
+{
+    if (!ctx) return SD_ERR_INVALID;
+    SD_REQUIRE(ctx, d_A && d_G && N >= 1 && D >= 1 && M >= 0, "bad argument");
+    SD_REQUIRE(ctx, lda >= D && ldg >= D + M && (M == 0 || (d_B && ldb >= M)), "bad leading dimension");
+    const float* S = d_A;
+    int64_t lds = lda;
+    if (M > 0 && !(d_B == d_A + D && ldb == lda)) {
+        // A and B live apart: pack [A | B] (zero padded to a multiple of 4 columns) into the workspace
+        lds = ((int64_t)(D + M) + 3) / 4 * 4;
+        float* E = (float*)sd_workspace(ctx, SD_WS_GRAM_EXT, (size_t)N * lds * sizeof(float));
+        if (!E) return SD_ERR_CUDA;
+        const int blocks = sd_div_up((int64_t)N * lds, 256) > 4096 ? 4096 : sd_div_up((int64_t)N * lds, 256);
+        pack_ext_kernel<<<blocks, 256, 0, ctx->stream>>>(d_A, lda, d_B, ldb, N, D, M, E, lds);
+        SD_LAUNCH_CHECK(ctx, "pack_ext_kernel");
+        S = E;
+    }
+    return sd_syrk_update(ctx, S, lds, N, D, D + M, d_G, ldg, 1.0f, 0.0f);
+}
+
+int sd_solve_gram(sd_ctx* ctx, float* d_G, int64_t ldg, int D, int M, const sd_regulariser* reg, int n_train_global,
+                  float* d_X, float* lambda_out)
+{
+    if (!ctx) return SD_ERR_INVALID;
+    SD_REQUIRE(ctx, d_G && d_X && reg && D >= 1 && M >= 1 && ldg >= D + M, "bad argument");
+    SD_REQUIRE(ctx, reg->type == 0 || reg->type == 1, "unknown regularisation type");
+    SD_REQUIRE(ctx, n_train_global >= 1, "n_train_global must be >= 1");
+    float* scal = reinterpret_cast<float*>(ctx->d_scratch) + 16;
+    double* partial = reinterpret_cast<double*>(reinterpret_cast<char*>(ctx->d_scratch) + 1024);   // up to 256 doubles
+    SD_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+    int nparts = 0;
+    if (reg->type == 1) {
+        nparts = sd_div_up((int64_t)D * D, 256 * 64);
+        if (nparts > 256) nparts = 256;
+        if (nparts < 1) nparts = 1;
+        frob_upper_kernel<<<nparts, 256, 0, ctx->stream>>>(d_G, ldg, D, partial);
+        SD_LAUNCH_CHECK(ctx, "frob_upper_kernel");
+    }
+    lambda_kernel<<<1, 32, 0, ctx->stream>>>(partial, nparts, reg->type, reg->param, n_train_global, scal);
+    SD_LAUNCH_CHECK(ctx, "lambda_kernel");
+    add_diag_kernel<<<sd_div_up(D, 256), 256, 0, ctx->stream>>>(d_G, ldg, D, scal, reg->regularise_last_row);
+    SD_LAUNCH_CHECK(ctx, "add_diag_kernel");
+    SD_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+    int rc = SD_OK;
+    if (D <= kLuMaxDim) {
+        lu_small_kernel<<<1, 1024, 0, ctx->stream>>>(d_G, ldg, D, M, reinterpret_cast<int*>(ctx->d_scratch));
+        SD_LAUNCH_CHECK(ctx, "lu_small_kernel");
+        SD_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
+        const int blocks = sd_div_up((int64_t)D * M, 256);
+        copy_block_kernel<<<blocks, 256, 0, ctx->stream>>>(d_G + D, ldg, D, M, d_X, M);
+        SD_LAUNCH_CHECK(ctx, "copy_block_kernel");
+    } else {
+        rc = cholesky_solve(ctx, d_G, ldg, D, M, d_X);
+        if (rc) return rc;
+    }
+    SD_CUDA(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
+    if (lambda_out) {
+        float* h = reinterpret_cast<float*>(ctx->h_scratch) + 16;
+        SD_CUDA(ctx, cudaMemcpyAsync(h, scal, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        *lambda_out = *h;
+    }
+    return check_status(ctx, "solve");
+}
+
+int sd_learn(sd_ctx* ctx, const float* d_A, int64_t lda, const float* d_B, int64_t ldb, int N, int D, int M,
+             const sd_regulariser* reg, float* d_X, float* lambda_out)
+{
+    if (!ctx) return SD_ERR_INVALID;
+    SD_REQUIRE(ctx, M >= 1, "labels must have at least one column");
+    const int64_t ldg = ((int64_t)(D + M) + 3) / 4 * 4;
+    float* G = (float*)sd_workspace(ctx, SD_WS_SCRATCH, (size_t)D * ldg * sizeof(float));
+    if (!G) return SD_ERR_CUDA;
+    SD_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+    int rc = sd_gram(ctx, d_A, lda, d_B, ldb, N, D, M, G, ldg);
+    if (rc) return rc;
+    return sd_solve_gram(ctx, G, ldg, D, M, reg, N, d_X, lambda_out);
+}
+
+int sd_predict(sd_ctx* ctx, const float* d_values, int64_t ldv, int N, int D, const float* d_X, int M,
+               float* d_out, int64_t ldo)
+{
+    if (!ctx) return SD_ERR_INVALID;
+    SD_REQUIRE(ctx, d_values && d_X && d_out && N >= 0 && D >= 1 && M >= 1 && ldv >= D && ldo >= M, "bad argument");
+    GemmEpilogue ep;
+    memset(&ep, 0, sizeof(ep));
+    return launch_gemm_nn(ctx, d_values, ldv, N, D, d_X, M, M, d_out, ldo, 1.0f, 0.0f, ep);
+}
+
+__global__ void residual_kernel(const float* __restrict__ pred, const float* __restrict__ labels, long long ldl, int N, int M,
+                                double* __restrict__ out /* [2] */)
+{
+    double num = 0.0, den = 0.0;
+    const long long total = (long long)N * M;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const long long n = idx / M;
+        const int c = (int)(idx - n * M);
+        const float l = labels[n * ldl + c];
+        const double d = (double)__fsub_rn(pred[idx], l);
+        num += d * d;
+        den += (double)l * (double)l;
+    }
+    __shared__ double rn[256], rd[256];
+    rn[threadIdx.x] = num; rd[threadIdx.x] = den;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) { rn[threadIdx.x] += rn[threadIdx.x + o]; rd[threadIdx.x] += rd[threadIdx.x + o]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { atomicAdd(&out[0], rn[0]); atomicAdd(&out[1], rd[0]); }
+}
+
+int sd_test_residual(sd_ctx* ctx, const float* d_values, int64_t ldv, const float* d_labels, int64_t ldl, int N, int D,
+                     const float* d_X, int M, double* residual_out)
+{
+    if (!ctx) return SD_ERR_INVALID;
+    SD_REQUIRE(ctx, d_values && d_labels && d_X && residual_out && N >= 1, "bad argument");
+    float* pred = (float*)sd_workspace(ctx, SD_WS_PARTIAL, (size_t)N * M * sizeof(float));
+    if (!pred) return SD_ERR_CUDA;
+    int rc = sd_predict(ctx, d_values, ldv, N, D, d_X, M, pred, M);
+    if (rc) return rc;
+    double* acc = reinterpret_cast<double*>(reinterpret_cast<char*>(ctx->d_scratch) + 512);
+    SD_CUDA(ctx, cudaMemsetAsync(acc, 0, 2 * sizeof(double), ctx->stream));
+    const int blocks = sd_div_up((int64_t)N * M, 256) > 512 ? 512 : sd_div_up((int64_t)N * M, 256);
+    residual_kernel<<<blocks, 256, 0, ctx->stream>>>(pred, d_labels, ldl, N, M, acc);
+    SD_LAUNCH_CHECK(ctx, "residual_kernel");
+    double* h = reinterpret_cast<double*>(reinterpret_cast<char*>(ctx->h_scratch) + 512);
+    SD_CUDA(ctx, cudaMemcpyAsync(h, acc, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *residual_out = sqrt(h[0]) / sqrt(h[1]);
+    return SD_OK;
+}
+
+int sd_cascade_targets(sd_ctx* ctx, const float* d_x, const float* d_x_gt, int N, int P, const sd_normalisation* norm,
+                       float* d_B, int64_t ldb)
+{
+    if (!ctx) return SD_ERR_INVALID;
+    SD_REQUIRE(ctx, d_x && d_x_gt && d_B && N >= 0 && P >= 1 && ldb >= P, "bad argument");
+    if (N == 0) return SD_OK;
+    sd_eyes_dev eyes;
+    int rc = sd_eyes_to_dev(ctx, norm, P / 2, &eyes);
+    if (rc) return rc;
+    dim3 block(32, 8);
+    targets_kernel<<<sd_div_up(N, 8), block, 0, ctx->stream>>>(d_x, d_x_gt, N, P, eyes, d_B, ldb);
+    SD_LAUNCH_CHECK(ctx, "targets_kernel");
+    return SD_OK;
+}
+
+int sd_cascade_update(sd_ctx* ctx, const float* d_A, int64_t lda, int N, int D, const float* d_X, int P,
+                      const float* d_x, const sd_normalisation* norm, float* d_x_next)
+{
+    if (!ctx) return SD_ERR_INVALID;
+    SD_REQUIRE(ctx, d_A && d_X && d_x && d_x_next && N >= 0 && D >= 1 && P >= 1 && lda >= D, "bad argument");
+    GemmEpilogue ep;
+    memset(&ep, 0, sizeof(ep));
+    ep.mode = 1;
+    ep.x = d_x;
+    ep.x_next = d_x_next;
+    int rc = sd_eyes_to_dev(ctx, norm, P / 2, &ep.eyes);
+    if (rc) return rc;
+    SD_REQUIRE(ctx, P <= GT || d_x != d_x_next, "in-place update needs P <= 64");
+    return launch_gemm_nn(ctx, d_A, lda, N, D, d_X, P, P, nullptr, 0, 1.0f, 0.0f, ep);
+}
+
+int sd_subtract_templates(sd_ctx* ctx, float* d_A, int64_t lda, const float* d_T, int64_t ldt, int N, int D)
+{
+    if (!ctx) return SD_ERR_INVALID;
+    SD_REQUIRE(ctx, d_A && d_T && lda >= D && ldt >= D, "bad argument");
+    if (N <= 0) return SD_OK;
+    const int blocks = sd_div_up((int64_t)N * D, 256) > 4096 ? 4096 : sd_div_up((int64_t)N * D, 256);
+    subtract_kernel<<<blocks, 256, 0, ctx->stream>>>(d_A, lda, d_T, ldt, N, D);
+    SD_LAUNCH_CHECK(ctx, "subtract_kernel");
+    return SD_OK;
+}
+
+}  // extern "C"

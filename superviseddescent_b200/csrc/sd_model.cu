@@ -1,0 +1,403 @@
+// rcr::detection_model on the device: load / save (cereal binary, byte compatible with the reference's
+// face_landmarks_model_rcr_*.bin), align_mean, and the batched detect cascade.
+//
+//   file format    model.hpp:178-182 -> superviseddescent.hpp:356-360 -> regressors.hpp:395-399,164-168
+//                  -> utils/mat_cerealisation.hpp:42-99 ; model.hpp:111-115 ; adaptive_vlhog.hpp:55-59
+//   detect         model.hpp:132-157 -> superviseddescent.hpp:323-344 (predict: sequential over levels)
+#include "sd_internal.cuh"
+
+#include <cstring>
+#include <fstream>
+#include <string>
+#include <vector>
+
+struct sd_model {
+    int device = 0;
+    int num_levels = 0;
+    int num_landmarks = 0;
+    std::vector<int> rows, cols;
+    std::vector<std::vector<float>> weights;      // host copies (for save / getters)
+    std::vector<float*> d_weights;                // device copies
+    std::vector<sd_regulariser> regs;
+    std::vector<sd_hog_param> hog;
+    std::vector<float> mean;
+    std::vector<std::string> ids, right_ids, left_ids;
+    sd_normalisation norm{};
+};
+
+namespace {
+
+// ---- little-endian byte cursor over the whole file -------------------------------------------------
+struct Cursor {
+    const std::vector<unsigned char>& buf;
+    size_t pos = 0;
+    bool good = true;
+    explicit Cursor(const std::vector<unsigned char>& b) : buf(b) {}
+    template <class T> T get()
+    {
+        T v{};
+        if (pos + sizeof(T) > buf.size()) { good = false; return v; }
+        memcpy(&v, buf.data() + pos, sizeof(T));
+        pos += sizeof(T);
+        return v;
+    }
+    bool bytes(void* dst, size_t n)
+    {
+        if (pos + n > buf.size()) { good = false; return false; }
+        memcpy(dst, buf.data() + pos, n);
+        pos += n;
+        return true;
+    }
+    std::vector<std::string> strings()
+    {
+        std::vector<std::string> out;
+        const uint64_t n = get<uint64_t>();                 // cereal size_type
+        if (!good || n > buf.size()) { good = false; return out; }
+        for (uint64_t i = 0; i < n && good; ++i) {
+            const uint64_t len = get<uint64_t>();
+            if (!good || len > buf.size() - pos) { good = false; break; }
+            out.emplace_back(reinterpret_cast<const char*>(buf.data() + pos), (size_t)len);
+            pos += (size_t)len;
+        }
+        return out;
+    }
+    bool matrix(std::vector<float>& data, int& r, int& c)
+    {
+        r = get<int32_t>();
+        c = get<int32_t>();
+        const int32_t type = get<int32_t>();
+        (void)get<uint8_t>();                               // isContinuous: same bytes either way for a packed Mat
+        if (!good || type != 5 /* CV_32FC1 */ || r < 0 || c < 0) { good = false; return false; }
+        data.resize((size_t)r * c);
+        return bytes(data.data(), data.size() * sizeof(float));
+    }
+};
+
+struct Writer {
+    std::vector<unsigned char> out;
+    template <class T> void put(T v)
+    {
+        const unsigned char* p = reinterpret_cast<const unsigned char*>(&v);
+        out.insert(out.end(), p, p + sizeof(T));
+    }
+    void strings(const std::vector<std::string>& v)
+    {
+        put<uint64_t>(v.size());
+        for (const auto& s : v) { put<uint64_t>(s.size()); out.insert(out.end(), s.begin(), s.end()); }
+    }
+    void matrix(const std::vector<float>& d, int r, int c)
+    {
+        put<int32_t>(r); put<int32_t>(c); put<int32_t>(5); put<uint8_t>(1);
+        const unsigned char* p = reinterpret_cast<const unsigned char*>(d.data());
+        out.insert(out.end(), p, p + d.size() * sizeof(float));
+    }
+};
+
+int resolve_eyes(sd_ctx* ctx, sd_model* m)
+{
+    auto find = [&](const std::string& s) {
+        for (size_t i = 0; i < m->ids.size(); ++i) if (m->ids[i] == s) return (int)i;
+        return -1;
+    };
+    if (m->right_ids.empty() || m->left_ids.empty() || m->right_ids.size() > SD_MAX_EYES || m->left_ids.size() > SD_MAX_EYES)
+        return sd_fail(ctx, SD_ERR_INVALID, "a model needs 1..%d eye identifiers per eye", SD_MAX_EYES);
+    m->norm.kind = 1;
+    m->norm.n_right = (int)m->right_ids.size();
+    m->norm.n_left = (int)m->left_ids.size();
+    for (int i = 0; i < m->norm.n_right; ++i) {
+        m->norm.right_idx[i] = find(m->right_ids[i]);
+        if (m->norm.right_idx[i] < 0) return sd_fail(ctx, SD_ERR_MISSING_ID, "one of given rightEyeIdentifiers ids not present in lms");
+    }
+    for (int i = 0; i < m->norm.n_left; ++i) {
+        m->norm.left_idx[i] = find(m->left_ids[i]);
+        if (m->norm.left_idx[i] < 0) return sd_fail(ctx, SD_ERR_MISSING_ID, "one of given leftEyeIdentifiers ids not present in lms");
+    }
+    return SD_OK;
+}
+
+int validate_and_upload(sd_ctx* ctx, sd_model* m)
+{
+    const int L = m->num_landmarks;
+    if (L < 1 || (int)m->mean.size() != 2 * L) return sd_fail(ctx, SD_ERR_INVALID, "mean must have 2L entries");
+    for (int s = 0; s < m->num_levels; ++s) {
+        const int D = sd_hog_feature_length(L, &m->hog[s]);
+        if (m->rows[s] != D || m->cols[s] != 2 * L)
+            return sd_fail(ctx, SD_ERR_INVALID, "level %d: regressor is %dx%d but the HOG parameters give %dx%d", s, m->rows[s], m->cols[s], D, 2 * L);
+    }
+    int rc = resolve_eyes(ctx, m);
+    if (rc) return rc;
+    m->device = ctx->device;
+    m->d_weights.assign(m->num_levels, nullptr);
+    for (int s = 0; s < m->num_levels; ++s) {
+        const size_t bytes = m->weights[s].size() * sizeof(float);
+        SD_CUDA(ctx, cudaMalloc(&m->d_weights[s], bytes));
+        SD_CUDA(ctx, cudaMemcpyAsync(m->d_weights[s], m->weights[s].data(), bytes, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SD_OK;
+}
+
+int detect_device(sd_ctx* ctx, const sd_model* m, const sd_image_batch* images, const float* d_x0, int count,
+                  float* d_landmarks)
+{
+    const int L = m->num_landmarks, P = 2 * L;
+    if (count <= 0) return SD_OK;
+    // ping-pong landmark buffers
+    float* xa = (float*)sd_workspace(ctx, SD_WS_SCRATCH, (size_t)2 * count * P * sizeof(float));
+    if (!xa) return SD_ERR_CUDA;
+    float* xb = xa + (size_t)count * P;
+    SD_CUDA(ctx, cudaMemcpyAsync(xa, d_x0, (size_t)count * P * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+    int maxD = 0;
+    for (int s = 0; s < m->num_levels; ++s) maxD = m->rows[s] > maxD ? m->rows[s] : maxD;
+    const int64_t ld = ((int64_t)maxD + 3) / 4 * 4;
+    float* A = (float*)sd_workspace(ctx, SD_WS_FEATURES, (size_t)count * ld * sizeof(float));
+    if (!A) return SD_ERR_CUDA;
+    float* cur = xa;
+    float* nxt = xb;
+    for (int s = 0; s < m->num_levels; ++s) {               // superviseddescent.hpp:326-342
+        int rc = sd_hog_batch(ctx, images, nullptr, cur, P, count, L, &m->norm, &m->hog[s], A, ld);
+        if (rc) return rc;
+        rc = sd_cascade_update(ctx, A, ld, count, m->rows[s], m->d_weights[s], P, cur, &m->norm, nxt);
+        if (rc) return rc;
+        float* t = cur; cur = nxt; nxt = t;
+    }
+    SD_CUDA(ctx, cudaMemcpyAsync(d_landmarks, cur, (size_t)count * P * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+    return SD_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sd_align_mean(const float* h_mean, int L, int box_x, int box_y, int box_w, int box_h, float sx, float sy,
+                  float tx, float ty, float* h_out)
+{
+    if (!h_mean || !h_out || L < 1) return SD_ERR_INVALID;
+    // model.hpp:72-73.  OpenCV folds (m*s + 0.5f + t) * w + x into one scaled conversion
+    // m * (float)(s*w) + (float)((0.5 + t)*w + x), evaluated in float (mul, then add).
+    const float ax = (float)((double)sx * (double)box_w);
+    const float bx = (float)(((double)0.5f + (double)tx) * (double)box_w + (double)box_x);
+    const float ay = (float)((double)sy * (double)box_h);
+    const float by = (float)(((double)0.5f + (double)ty) * (double)box_h + (double)box_y);
+    for (int i = 0; i < L; ++i) {
+        volatile float px = h_mean[i] * ax;        // volatile: keep mul and add un-fused on any host compiler
+        h_out[i] = px + bx;
+        volatile float py = h_mean[i + L] * ay;
+        h_out[i + L] = py + by;
+    }
+    return SD_OK;
+}
+
+int sd_model_load(sd_ctx* ctx, const char* path, sd_model** out)
+{
+    if (!ctx || !path || !out) return SD_ERR_INVALID;
+    *out = nullptr;
+    std::ifstream f(path, std::ios::binary);
+    if (!f) return sd_fail(ctx, SD_ERR_IO, "The given model file could not be opened: %s", path);   // model.hpp:199
+    std::vector<unsigned char> buf((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    Cursor c(buf);
+    sd_model* m = new sd_model();
+    auto bail = [&](const char* why) { delete m; return sd_fail(ctx, SD_ERR_IO, "%s: %s", why, path); };
+
+    const uint64_t nreg = c.get<uint64_t>();                 // vector<LinearRegressor>
+    if (!c.good || nreg == 0 || nreg > 256) return bail("not a detection_model archive (regressor count)");
+    m->num_levels = (int)nreg;
+    m->rows.resize(nreg); m->cols.resize(nreg); m->weights.resize(nreg); m->regs.resize(nreg);
+    for (uint64_t i = 0; i < nreg; ++i) {
+        if (!c.matrix(m->weights[i], m->rows[i], m->cols[i])) return bail("truncated regressor matrix");
+        m->regs[i].type = c.get<int32_t>();                  // Regulariser: type, lambda, regularise_last_row
+        m->regs[i].param = c.get<float>();
+        m->regs[i].regularise_last_row = c.get<uint8_t>();
+    }
+    const auto n_ids = c.strings();                          // InterEyeDistanceNormalisation's own copies
+    const auto n_right = c.strings();
+    const auto n_left = c.strings();
+    int mr = 0, mc = 0;
+    if (!c.matrix(m->mean, mr, mc)) return bail("truncated mean");
+    m->ids = c.strings();
+    const uint64_t nhog = c.get<uint64_t>();
+    if (!c.good || nhog != nreg) return bail("hog_params count differs from the regressor count");
+    m->hog.resize(nhog);
+    for (uint64_t i = 0; i < nhog; ++i) {
+        m->hog[i].variant = c.get<int32_t>();
+        m->hog[i].num_cells = c.get<int32_t>();
+        m->hog[i].cell_size = c.get<int32_t>();
+        m->hog[i].num_bins = c.get<int32_t>();
+        m->hog[i].relative_patch_size = c.get<float>();
+    }
+    m->right_ids = c.strings();
+    m->left_ids = c.strings();
+    if (!c.good || c.pos != buf.size()) return bail("truncated archive or trailing bytes");
+    if (mr != 1 || n_ids != m->ids || n_right != m->right_ids || n_left != m->left_ids)
+        return bail("inconsistent archive (normaliser ids differ from the model's)");
+    m->num_landmarks = (int)m->ids.size();
+    int rc = validate_and_upload(ctx, m);
+    if (rc) { sd_model_destroy(m); return rc; }
+    *out = m;
+    return SD_OK;
+}
+
+int sd_model_save(sd_ctx* ctx, const sd_model* m, const char* path)
+{
+    if (!ctx || !m || !path) return SD_ERR_INVALID;
+    Writer w;
+    w.put<uint64_t>((uint64_t)m->num_levels);
+    for (int i = 0; i < m->num_levels; ++i) {
+        w.matrix(m->weights[i], m->rows[i], m->cols[i]);
+        w.put<int32_t>(m->regs[i].type);
+        w.put<float>(m->regs[i].param);
+        w.put<uint8_t>(m->regs[i].regularise_last_row ? 1 : 0);
+    }
+    w.strings(m->ids); w.strings(m->right_ids); w.strings(m->left_ids);
+    w.matrix(m->mean, 1, 2 * m->num_landmarks);
+    w.strings(m->ids);
+    w.put<uint64_t>((uint64_t)m->num_levels);
+    for (int i = 0; i < m->num_levels; ++i) {
+        w.put<int32_t>(m->hog[i].variant); w.put<int32_t>(m->hog[i].num_cells); w.put<int32_t>(m->hog[i].cell_size);
+        w.put<int32_t>(m->hog[i].num_bins); w.put<float>(m->hog[i].relative_patch_size);
+    }
+    w.strings(m->right_ids); w.strings(m->left_ids);
+    std::ofstream f(path, std::ios::binary);
+    if (!f) return sd_fail(ctx, SD_ERR_IO, "could not open %s for writing", path);
+    f.write(reinterpret_cast<const char*>(w.out.data()), (std::streamsize)w.out.size());
+    return f.good() ? SD_OK : sd_fail(ctx, SD_ERR_IO, "short write to %s", path);
+}
+
+int sd_model_create(sd_ctx* ctx, int num_levels, int num_landmarks, const float* const* h_weights,
+                    const sd_regulariser* regs, const sd_hog_param* hog_params, const float* h_mean,
+                    const char* const* landmark_ids, const char* const* right_eye_ids, int n_right,
+                    const char* const* left_eye_ids, int n_left, sd_model** out)
+{
+    if (!ctx || !out) return SD_ERR_INVALID;
+    *out = nullptr;
+    SD_REQUIRE(ctx, num_levels >= 1 && num_landmarks >= 1 && h_weights && regs && hog_params && h_mean && landmark_ids &&
+                        right_eye_ids && left_eye_ids, "null / empty argument");
+    sd_model* m = new sd_model();
+    m->num_levels = num_levels;
+    m->num_landmarks = num_landmarks;
+    for (int i = 0; i < num_landmarks; ++i) m->ids.emplace_back(landmark_ids[i]);
+    for (int i = 0; i < n_right; ++i) m->right_ids.emplace_back(right_eye_ids[i]);
+    for (int i = 0; i < n_left; ++i) m->left_ids.emplace_back(left_eye_ids[i]);
+    m->mean.assign(h_mean, h_mean + 2 * num_landmarks);
+    m->rows.resize(num_levels); m->cols.resize(num_levels); m->weights.resize(num_levels);
+    m->regs.assign(regs, regs + num_levels);
+    m->hog.assign(hog_params, hog_params + num_levels);
+    for (int s = 0; s < num_levels; ++s) {
+        m->rows[s] = sd_hog_feature_length(num_landmarks, &hog_params[s]);
+        m->cols[s] = 2 * num_landmarks;
+        m->weights[s].assign(h_weights[s], h_weights[s] + (size_t)m->rows[s] * m->cols[s]);
+    }
+    int rc = validate_and_upload(ctx, m);
+    if (rc) { sd_model_destroy(m); return rc; }
+    *out = m;
+    return SD_OK;
+}
+
+void sd_model_destroy(sd_model* m)
+{
+    if (!m) return;
+    cudaSetDevice(m->device);
+    for (float* p : m->d_weights) if (p) cudaFree(p);
+    delete m;
+}
+
+int sd_model_num_levels(const sd_model* m) { return m ? m->num_levels : -1; }
+int sd_model_num_landmarks(const sd_model* m) { return m ? m->num_landmarks : -1; }
+int sd_model_hog_param(const sd_model* m, int level, sd_hog_param* out)
+{
+    if (!m || !out || level < 0 || level >= m->num_levels) return SD_ERR_INVALID;
+    *out = m->hog[level];
+    return SD_OK;
+}
+int sd_model_regulariser(const sd_model* m, int level, sd_regulariser* out)
+{
+    if (!m || !out || level < 0 || level >= m->num_levels) return SD_ERR_INVALID;
+    *out = m->regs[level];
+    return SD_OK;
+}
+int sd_model_normalisation(const sd_model* m, sd_normalisation* out)
+{
+    if (!m || !out) return SD_ERR_INVALID;
+    *out = m->norm;
+    return SD_OK;
+}
+int sd_model_get_mean(const sd_model* m, float* h_mean)
+{
+    if (!m || !h_mean) return SD_ERR_INVALID;
+    memcpy(h_mean, m->mean.data(), m->mean.size() * sizeof(float));
+    return SD_OK;
+}
+int sd_model_get_weights(const sd_model* m, int level, float* h_w, int* rows, int* cols)
+{
+    if (!m || level < 0 || level >= m->num_levels) return SD_ERR_INVALID;
+    if (rows) *rows = m->rows[level];
+    if (cols) *cols = m->cols[level];
+    if (h_w) memcpy(h_w, m->weights[level].data(), m->weights[level].size() * sizeof(float));
+    return SD_OK;
+}
+const char* sd_model_landmark_id(const sd_model* m, int i)
+{
+    if (!m || i < 0 || i >= m->num_landmarks) return nullptr;
+    return m->ids[i].c_str();
+}
+
+int sd_detect_batch_device(sd_ctx* ctx, const sd_model* m, const sd_image_batch* images, const float* d_x0, int count,
+                           float* d_landmarks)
+{
+    if (!ctx) return SD_ERR_INVALID;
+    SD_REQUIRE(ctx, m && images && d_x0 && d_landmarks && count >= 0, "bad argument");
+    SD_REQUIRE(ctx, images->count >= count, "fewer images than faces");
+    return detect_device(ctx, m, images, d_x0, count, d_landmarks);
+}
+
+int sd_detect_batch_host(sd_ctx* ctx, const sd_model* m, const uint8_t* h_images, int count, int width, int height,
+                         int row_stride, const int32_t* h_boxes, float* h_landmarks)
+{
+    if (!ctx) return SD_ERR_INVALID;
+    SD_REQUIRE(ctx, m && h_images && h_boxes && h_landmarks && count >= 0 && width > 0 && height > 0 && row_stride >= width, "bad argument");
+    if (count == 0) return SD_OK;
+    const int L = m->num_landmarks, P = 2 * L;
+    const size_t frame_bytes = (size_t)height * row_stride;
+    // chunking: ~128 MB of frames per staging buffer, at least 1 face
+    int chunk = (int)((size_t)(128u << 20) / frame_bytes);
+    if (chunk < 1) chunk = 1;
+    if (chunk > count) chunk = count;
+    for (int b = 0; b < 2; ++b) {
+        if (ctx->stage_bytes[b] < (size_t)chunk * frame_bytes) {
+            if (ctx->d_stage[b]) { SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); SD_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream)); SD_CUDA(ctx, cudaFree(ctx->d_stage[b])); ctx->d_stage[b] = nullptr; }
+            SD_CUDA(ctx, cudaMalloc(&ctx->d_stage[b], (size_t)chunk * frame_bytes));
+            ctx->stage_bytes[b] = (size_t)chunk * frame_bytes;
+        }
+    }
+    // initial landmarks for every face: align_mean on the host (model.hpp:135), one small upload
+    std::vector<float> x0((size_t)count * P);
+    for (int i = 0; i < count; ++i)
+        sd_align_mean(m->mean.data(), L, h_boxes[4 * i], h_boxes[4 * i + 1], h_boxes[4 * i + 2], h_boxes[4 * i + 3], 1.f, 1.f, 0.f, 0.f, &x0[(size_t)i * P]);
+    float* d_x = (float*)sd_workspace(ctx, SD_WS_PARTIAL, (size_t)2 * count * P * sizeof(float));
+    if (!d_x) return SD_ERR_CUDA;
+    float* d_out = d_x + (size_t)count * P;
+    SD_CUDA(ctx, cudaMemcpyAsync(d_x, x0.data(), x0.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    // the copy stream must not run ahead of work already queued on the compute stream that still reads the staging buffers
+    SD_CUDA(ctx, cudaEventRecord(ctx->stage_done[0], ctx->stream));
+    SD_CUDA(ctx, cudaEventRecord(ctx->stage_done[1], ctx->stream));
+    int buf = 0;
+    for (int first = 0; first < count; first += chunk, buf ^= 1) {
+        const int n = (count - first < chunk) ? count - first : chunk;
+        SD_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->stage_done[buf], 0));
+        SD_CUDA(ctx, cudaMemcpyAsync(ctx->d_stage[buf], h_images + (size_t)first * frame_bytes, (size_t)n * frame_bytes,
+                                     cudaMemcpyHostToDevice, ctx->copy_stream));
+        SD_CUDA(ctx, cudaEventRecord(ctx->stage_ev[buf], ctx->copy_stream));
+        SD_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->stage_ev[buf], 0));
+        sd_image_batch ib;
+        ib.d_data = (const uint8_t*)ctx->d_stage[buf];
+        ib.width = width; ib.height = height; ib.row_stride = row_stride; ib.image_stride = (int64_t)frame_bytes; ib.count = n;
+        int rc = detect_device(ctx, m, &ib, d_x + (size_t)first * P, n, d_out + (size_t)first * P);
+        if (rc) return rc;
+        SD_CUDA(ctx, cudaEventRecord(ctx->stage_done[buf], ctx->stream));
+    }
+    SD_CUDA(ctx, cudaMemcpyAsync(h_landmarks, d_out, (size_t)count * P * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SD_OK;
+}
+
+}  // extern "C"
