@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 cascaded-regression engine.
+
+Metric (BASELINE.json): faces/sec, RCR 22-landmark detect with the reference's pre-trained
+face_landmarks_model_rcr_22.bin on 640x480 synthetic 8UC1 frames, batched, one face box per frame
+(config 3, "configs[2]").  A "step" = one pass of the detect cascade (4 levels: HOG -> feature x weight
+GEMM -> IED-scaled update) over one batch of B frames.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+
+  value        whole-job faces/s with frames + initial landmarks already resident in HBM
+  e2e          the same through the reference-facing call detection_model::detect(image, facebox)
+               batched with HOST (pinned) buffers: H2D of the frames and D2H of the landmarks are inside
+               the timed region
+  roofline     the dominant kernel (HOG, cascade level 0) against measured HBM bandwidth
+  cpu_baseline the reference's own hog.c (oracle/_ref) inside the restated HogTransform/predict glue,
+               timed on this box's host cores on a bounded sample
+  train        (N=1 only, extra) regressor-train seconds of a reduced RCR training config
+
+--impl reference times the CPU path alone (rank 0), same metric/config.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+MODEL = os.path.join(ROOT, "tests", "golden", "face_landmarks_model_rcr_22.bin")
+W_IMG, H_IMG = 640, 480
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def synth_boxes(count, seed):
+    """one square face box per frame, w=h in U{200..280}, fully inside the 640x480 frame."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    s = rng.integers(200, 281, size=count)
+    x = (rng.random(count) * (W_IMG - s - 40) + 20).astype(np.int64)
+    y = (rng.random(count) * (H_IMG - s - 40) + 20).astype(np.int64)
+    return np.stack([x, y, s, s], axis=1).astype(np.int32)
+
+
+def synth_frames_torch(count, seed, device):
+    """Low-pass filtered uniform noise (sigma = 3 px) stretched to 0..255, 8UC1, generated on the GPU."""
+    import torch
+    import torch.nn.functional as F
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    sigma, r = 3.0, 9
+    k = torch.exp(-0.5 * (torch.arange(-r, r + 1, device=device, dtype=torch.float32) / sigma) ** 2)
+    k = k / k.sum()
+    out = torch.empty((count, H_IMG, W_IMG), dtype=torch.uint8, device=device)
+    for i0 in range(0, count, 128):
+        n = min(128, count - i0)
+        x = torch.rand((n, 1, H_IMG + 2 * r, W_IMG + 2 * r), generator=g, device=device)
+        x = F.conv2d(x, k.view(1, 1, -1, 1))
+        x = F.conv2d(x, k.view(1, 1, 1, -1))
+        lo = x.amin(dim=(2, 3), keepdim=True)
+        hi = x.amax(dim=(2, 3), keepdim=True)
+        out[i0:i0 + n] = ((x - lo) / (hi - lo) * 255.0).round().clamp(0, 255).to(torch.uint8)[:, 0]
+    return out
+
+
+def synth_frames_numpy(count, seed):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import synth
+    return synth.smooth_images(count, H_IMG, W_IMG, seed)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_detect_rate(n_faces, threads, seed):
+    """Reference CPU path: oracle glue + the reference's hog.c when oracle/_ref is built."""
+    from oracle import oracle as O
+    O.build()
+    om = O.Model(MODEL)
+    use_ref = O.ref_available()
+    frames = synth_frames_numpy(min(n_faces, 64), seed)
+    reps = (n_faces + frames.shape[0] - 1) // frames.shape[0]
+    frames = np.concatenate([frames] * reps)[:n_faces]
+    boxes = synth_boxes(n_faces, seed)
+    om.detect_batch(frames[:threads], boxes[:threads], use_ref=use_ref, threads=threads)   # warm-up
+    t0 = time.perf_counter()
+    om.detect_batch(frames, boxes, use_ref=use_ref, threads=threads)
+    dt = time.perf_counter() - t0
+    return n_faces / dt, ("reference" if use_ref else "port"), dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = host_cores()
+    sample = max(cores * 8, 256)
+    rates = []
+    kind = "port"
+    for s in range(args.warmup + args.steps):
+        r, kind, dt = cpu_detect_rate(sample, cores, 1234 + s)
+        if s >= args.warmup:
+            rates.append((sample, dt))
+    faces = sum(a for a, _ in rates)
+    secs = sum(b for _, b in rates)
+    value = faces / secs
+    r1, _, _ = cpu_detect_rate(64, 1, 99)
+    line = {
+        "impl": "reference", "metric": "faces/sec RCR 22-landmark detect", "value": value, "unit": "faces/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(len(rates), 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[2]: RCR 22-landmark detect, face_landmarks_model_rcr_22.bin, 640x480 8UC1 synthetic frames, "
+                               f"{sample} faces per step on host cores", "frames_per_step": sample},
+        "cpu_baseline": {"value": value, "unit": "faces/s", "cores": cores, "kind": kind,
+                         "sample": f"{sample} faces/step x {args.steps} steps, one face per thread; single-thread (reference-faithful sequential predict): {r1:.1f} faces/s",
+                         "single_thread_value": r1},
+        "e2e": {"value": value, "unit": "faces/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from superviseddescent_b200 import api as sd
+    ctx = sd.Context(local)
+    model = sd.load_detection_model(MODEL, ctx)
+    B = args.batch
+    L = model.num_landmarks
+
+    frames = synth_frames_torch(B, 1234 + rank, dev)
+    boxes = synth_boxes(B, 1234 + rank)
+    mean = model.get_mean()
+    x0 = np.stack([sd.align_mean(mean, b) for b in boxes])
+    x0_dev = torch.from_numpy(x0).to(dev)
+    h_frames = torch.empty((B, H_IMG, W_IMG), dtype=torch.uint8).pin_memory()
+    h_frames.copy_(frames)
+    torch.cuda.synchronize()
+    h_np = h_frames.numpy()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world > 1:
+            t = torch.tensor([v], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return v
+
+    # ---------------- device-resident throughput ----------------
+    for _ in range(args.warmup):
+        out = model.detect_batch_device(frames, x0_dev)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = model.detect_batch_device(frames, x0_dev)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = ctx.launches() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * B * args.steps / (ms * 1e-3)
+
+    # ---------------- end to end through the host-buffer call ----------------
+    for _ in range(min(args.warmup, 2)):
+        lm = model.detect_batch(h_np, boxes)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        lm = model.detect_batch(h_np, boxes)
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    e2e = world * B * args.steps / (ms_e2e * 1e-3)
+    assert np.array_equal(lm, out.cpu().numpy()), "host and device paths disagree"
+
+    # ---------------- roofline of the dominant kernel: HOG, cascade level 0 ----------------
+    import ctypes as C
+    from superviseddescent_b200 import _capi
+    hp0 = model.hog_param(0)
+    D0 = _capi.lib().sd_hog_feature_length(L, C.byref(hp0))
+    ld = (D0 + 3) // 4 * 4
+    A = torch.empty((B, ld), dtype=torch.float32, device=dev)
+    norm = sd.NormalisationC()
+    _capi.lib().sd_model_normalisation(model._m, C.byref(norm))
+    ib = sd.ImageBatchC(C.c_void_p(frames.data_ptr()), W_IMG, H_IMG, frames.stride(1), frames.stride(0), B)
+
+    def hog0():
+        rc = _capi.lib().sd_hog_batch(ctx.h, C.byref(ib), None, _capi.ptr(x0_dev), C.c_int64(2 * L), B, L, C.byref(norm), C.byref(hp0), _capi.ptr(A), C.c_int64(ld))
+        assert rc == 0
+    for _ in range(3):
+        hog0()
+    torch.cuda.synchronize()
+    reps = max(5, args.steps)
+    e0.record()
+    for _ in range(reps):
+        hog0()
+    e1.record()
+    torch.cuda.synchronize()
+    hog_ms = e0.elapsed_time(e1) / reps
+    # algorithmic bytes: unique source pixels read once + the descriptor row written once
+    ri = [norm.right_idx[i] for i in range(norm.n_right)]
+    li = [norm.left_idx[i] for i in range(norm.n_left)]
+    ied = np.hypot(x0[:, ri].mean(1) - x0[:, li].mean(1), x0[:, [i + L for i in ri]].mean(1) - x0[:, [i + L for i in li]].mean(1))
+    P = 2 * np.round(hp0.relative_patch_size * ied / 2)
+    alg_bytes = float(np.sum(np.minimum(L * P * P, W_IMG * H_IMG)) + B * D0 * 4)
+    fs0 = hp0.num_cells * hp0.cell_size
+    alg_flops = float(B * L * fs0 * fs0 * (24 + 4 * hp0.num_bins))
+    peak, peak_src = measured_peaks()
+    achieved = alg_bytes / (hog_ms * 1e-3) / 1e9
+    roofline = {"kernel": f"hog_patch_kernel<{hp0.num_bins}> (cascade level 0, fs={fs0})", "bound": "hbm", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "ms_per_launch": hog_ms,
+                "algorithmic_bytes_per_launch": alg_bytes,
+                "note": "HOG is fp32-ALU/shared-memory bound (SURVEY 8d: ~40 flop/B); fp32 figure reported beside the HBM one",
+                "achieved_fp32_tflops": alg_flops / (hog_ms * 1e-3) / 1e12}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    line = {
+        "metric": "faces/sec RCR 22-landmark detect", "value": value, "unit": "faces/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[2]: RCR 22-landmark detect, pre-trained face_landmarks_model_rcr_22.bin, 640x480 8UC1 synthetic frames, batched",
+                   "frames_per_gpu": B, "global_batch": world * B, "cascade_levels": model.num_levels, "landmarks": L,
+                   "parallelism": f"face-batch sharded over {world} GPU(s), no collective",
+                   "l2": f"inputs ({B * W_IMG * H_IMG / 1e6:.0f} MB of frames per GPU) exceed the 126 MB L2"},
+        "e2e": {"value": e2e, "unit": "faces/s", "h2d_bytes_per_step": int(B * W_IMG * H_IMG + B * 2 * L * 4), "d2h_bytes_per_step": int(B * 2 * L * 4),
+                "ms_per_step": ms_e2e / args.steps, "api": "detection_model.detect_batch (sd_detect_batch_host), pinned host frames"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roofline,
+    }
+    if world == 1 and not args.no_cpu:
+        cores = host_cores()
+        n = max(256, cores * 32)
+        r, kind, dt = cpu_detect_rate(n, cores, 4321)
+        r1, _, _ = cpu_detect_rate(48, 1, 4322)
+        line["cpu_baseline"] = {"value": r, "unit": "faces/s", "cores": cores, "kind": kind,
+                                "sample": f"{n} faces of the same workload, one face per thread ({dt:.1f} s); single-thread reference-faithful predict: {r1:.1f} faces/s",
+                                "single_thread_value": r1}
+    if world > 1:
+        dist.destroy_process_group()
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=4096, help="frames per GPU per step")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -87,8 +87,10 @@ typedef struct {
 } sd_image_batch;
 
 /* ---- context --------------------------------------------------------------------------- */
-/* stream: a cudaStream_t owned by the caller (e.g. torch's current stream), or NULL to let
- * the context create its own non-blocking stream. */
+/* stream: a cudaStream_t owned by the caller (e.g. torch's current stream); NULL is the CUDA default
+ * stream (which is also torch's default stream); SD_STREAM_OWN lets the context create and own a
+ * non-blocking stream. */
+#define SD_STREAM_OWN ((void*)(intptr_t)-1)
 SD_API int sd_ctx_create(int device, void* stream, sd_ctx** out);
 SD_API void sd_ctx_destroy(sd_ctx* ctx);
 SD_API const char* sd_last_error(const sd_ctx* ctx);

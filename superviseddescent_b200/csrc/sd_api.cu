@@ -89,12 +89,12 @@ int sd_ctx_create(int device, void* stream, sd_ctx** out)
     ctx->device = device;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
-    if (stream) {
-        ctx->stream = (cudaStream_t)stream;
-        ctx->own_stream = false;
-    } else {
+    if (stream == SD_STREAM_OWN) {
         if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return SD_ERR_CUDA; }
         ctx->own_stream = true;
+    } else {
+        ctx->stream = (cudaStream_t)stream;   // NULL = the CUDA default stream (what torch calls its default stream)
+        ctx->own_stream = false;
     }
     bool ok = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
     for (int i = 0; i < 6 && ok; ++i) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;

@@ -13,10 +13,17 @@
 // (relative error ~2^-21 per product, fp32 accumulation in TMEM) on operands pre-split in HBM by
 // split_tf32_kernel; passes == 1 is a single TF32 pass on the raw operand.
 //
-// Kernel shape (persistent, one CTA per SM, 192 threads):
+// Accumulation: the tensor core adds into the fp32 TMEM accumulator with truncation, so a long chain
+// drifts low (measured: -1.6e-5 relative after 564 accumulating MMAs).  The chain is therefore cut every
+// KC = 128 samples (48 MMAs, ~1e-6): each chunk starts a fresh TMEM accumulator and the epilogue warps
+// fold the finished chunk into running sums held in REGISTERS with round-to-nearest adds, while the
+// tensor core already works on the next chunk in the other TMEM buffer.
+//
+// Kernel shape (persistent, one CTA per SM, 320 threads):
 //   warp 0      TMA producer   : 4-stage ring of [hi|lo] x [A 128 cols | B 256 cols] x 16 samples
 //   warp 1      MMA issuer     : tcgen05.mma cta_group::1 kind::tf32, M=128 N=256 K=8, accumulators in TMEM
-//   warps 2..5  epilogue       : tcgen05.ld 32x32b -> alpha/beta -> global (double-buffered TMEM: 2 x 256 cols)
+//   warps 2..9  epilogue       : tcgen05.ld 32x32b -> running sums (128 regs/thread) -> alpha/beta -> global
+//                                (double-buffered TMEM: 2 x 256 columns)
 #include "sd_internal.cuh"
 
 #include <cuda.h>
@@ -37,7 +44,9 @@ constexpr int B_BLOCKS = BN / BOX_COLS;                   // 8
 constexpr int OPER_BYTES_A = A_BLOCKS * BOX_BYTES;        // 8 KB
 constexpr int OPER_BYTES_B = B_BLOCKS * BOX_BYTES;        // 16 KB
 constexpr int STAGE_BYTES = 2 * (OPER_BYTES_A + OPER_BYTES_B);   // hi + lo: 48 KB
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;
+constexpr int KC_STAGES = 8;      // pipeline stages per accumulation chunk: KC = 8 * BK = 128 samples
+constexpr int EPI_WARPS = 8;
 constexpr int TMEM_COLS = 512;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
@@ -166,7 +175,7 @@ syrk_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 4); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_hi) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_lo) : "memory");
@@ -215,10 +224,14 @@ syrk_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
         uint32_t stage = 0, phase = 0;
         uint32_t buf = 0, buf_phase = 0;
         for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
-            mbar_wait(&tmem_empty[buf], buf_phase ^ 1);      // epilogue has drained this accumulator
-            tcgen05_fence_after();
-            const uint32_t tmem_d = tmem_base + buf * BN;
             for (int kb = 0; kb < num_k; ++kb) {
+                const bool chunk_first = (kb % KC_STAGES) == 0;
+                const bool chunk_last = (kb % KC_STAGES) == KC_STAGES - 1 || kb == num_k - 1;
+                if (chunk_first) {
+                    mbar_wait(&tmem_empty[buf], buf_phase ^ 1);      // epilogue has drained this accumulator
+                    tcgen05_fence_after();
+                }
+                const uint32_t tmem_d = tmem_base + buf * BN;
                 mbar_wait(&full_bar[stage], phase);
                 tcgen05_fence_after();
                 if (lane == 0) {
@@ -229,7 +242,7 @@ syrk_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
 #pragma unroll
                     for (int ks = 0; ks < BK / 8; ++ks) {
                         const uint32_t koff = ks * 8 * 128;      // 8 rows of 128 B per UMMA K step
-                        const uint32_t first = (kb == 0 && ks == 0) ? 0u : 1u;
+                        const uint32_t first = (chunk_first && ks == 0) ? 0u : 1u;
                         if (a.passes == 3) {
                             tcgen05_mma_tf32(tmem_d, make_desc(sa_lo + koff), make_desc(sb_hi + koff), kInstrDesc, first);
                             tcgen05_mma_tf32(tmem_d, make_desc(sa_hi + koff), make_desc(sb_lo + koff), kInstrDesc, 1u);
@@ -238,66 +251,72 @@ syrk_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
                             tcgen05_mma_tf32(tmem_d, make_desc(sa_hi + koff), make_desc(sb_hi + koff), kInstrDesc, first);
                         }
                     }
-                    tcgen05_commit(&empty_bar[stage]);                        // smem slot free once these MMAs retire
-                    if (kb == num_k - 1) tcgen05_commit(&tmem_full[buf]);     // accumulator complete
+                    tcgen05_commit(&empty_bar[stage]);                   // smem slot free once these MMAs retire
+                    if (chunk_last) tcgen05_commit(&tmem_full[buf]);     // chunk accumulator complete
                 }
                 __syncwarp();
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                if (chunk_last) { if (++buf == 2) { buf = 0; buf_phase ^= 1; } }
             }
-            if (++buf == 2) { buf = 0; buf_phase ^= 1; }
         }
     } else {
-        // ===================== epilogue (warps 2..5) =====================
+        // ===================== epilogue (warps 2..9) =====================
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;             // which 128 of the tile's 256 columns
         uint32_t buf = 0, buf_phase = 0;
         const bool vec_ok = (a.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.C) & 15) == 0);
+        const int num_chunks = (num_k + KC_STAGES - 1) / KC_STAGES;
         for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
             const int2 tile = a.tiles[t];
             const int i = tile.x * BM + q * 32 + lane;
-            const int j0 = tile.y * BN;
-            mbar_wait(&tmem_full[buf], buf_phase);
-            tcgen05_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN;
-            float* crow = a.C + (long long)i * a.ldc;
-#pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                uint32_t r[32];
-                tmem_ld_32x32b_x32(taddr + c0, r);
-                tmem_ld_wait();
-                if (i < a.MI) {
-                    const int j = j0 + c0;
-                    if (vec_ok && j + 32 <= a.NJ) {
+            const int j0 = tile.y * BN + half * 128;
+            float acc[128];
 #pragma unroll
-                        for (int v = 0; v < 8; ++v) {
-                            float4 o;
-                            o.x = a.alpha * __uint_as_float(r[4 * v + 0]);
-                            o.y = a.alpha * __uint_as_float(r[4 * v + 1]);
-                            o.z = a.alpha * __uint_as_float(r[4 * v + 2]);
-                            o.w = a.alpha * __uint_as_float(r[4 * v + 3]);
-                            float4* p = reinterpret_cast<float4*>(crow + j + 4 * v);
-                            if (a.beta != 0.f) {
-                                const float4 old = *p;
-                                o.x = fmaf(a.beta, old.x, o.x); o.y = fmaf(a.beta, old.y, o.y);
-                                o.z = fmaf(a.beta, old.z, o.z); o.w = fmaf(a.beta, old.w, o.w);
-                            }
-                            *p = o;
+            for (int v = 0; v < 128; ++v) acc[v] = 0.f;
+            for (int c = 0; c < num_chunks; ++c) {
+                mbar_wait(&tmem_full[buf], buf_phase);
+                tcgen05_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + half * 128;
+#pragma unroll
+                for (int c0 = 0; c0 < 128; c0 += 32) {
+                    uint32_t r[32];
+                    tmem_ld_32x32b_x32(taddr + c0, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int v = 0; v < 32; ++v) acc[c0 + v] = __fadd_rn(acc[c0 + v], __uint_as_float(r[v]));
+                }
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+                if (++buf == 2) { buf = 0; buf_phase ^= 1; }
+            }
+            if (i < a.MI) {
+                float* crow = a.C + (long long)i * a.ldc;
+                if (vec_ok && j0 + 128 <= a.NJ) {
+#pragma unroll
+                    for (int v = 0; v < 32; ++v) {
+                        float4 o;
+                        o.x = a.alpha * acc[4 * v + 0]; o.y = a.alpha * acc[4 * v + 1];
+                        o.z = a.alpha * acc[4 * v + 2]; o.w = a.alpha * acc[4 * v + 3];
+                        float4* p = reinterpret_cast<float4*>(crow + j0 + 4 * v);
+                        if (a.beta != 0.f) {
+                            const float4 old = *p;
+                            o.x = fmaf(a.beta, old.x, o.x); o.y = fmaf(a.beta, old.y, o.y);
+                            o.z = fmaf(a.beta, old.z, o.z); o.w = fmaf(a.beta, old.w, o.w);
                         }
-                    } else {
+                        *p = o;
+                    }
+                } else {
 #pragma unroll
-                        for (int v = 0; v < 32; ++v) {
-                            if (j + v < a.NJ) {
-                                float o = a.alpha * __uint_as_float(r[v]);
-                                if (a.beta != 0.f) o = fmaf(a.beta, crow[j + v], o);
-                                crow[j + v] = o;
-                            }
+                    for (int v = 0; v < 128; ++v) {
+                        if (j0 + v < a.NJ) {
+                            float o = a.alpha * acc[v];
+                            if (a.beta != 0.f) o = fmaf(a.beta, crow[j0 + v], o);
+                            crow[j0 + v] = o;
                         }
                     }
                 }
             }
-            tcgen05_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[buf]);
-            if (++buf == 2) { buf = 0; buf_phase ^= 1; }
         }
     }
 

@@ -432,6 +432,7 @@ int sd_hog_batch(sd_ctx* ctx, const sd_image_batch* images, const int32_t* d_ima
                  const sd_hog_param* p, float* d_A, int64_t ld)
 {
     if (!ctx) return SD_ERR_INVALID;
+    if (num_samples == 0) return SD_OK;
     SD_REQUIRE(ctx, d_A, "null output");
     return launch_hog(ctx, images, d_image_index, d_x, ldx, num_samples, num_landmarks, eyes, p, d_A, ld,
                       nullptr, nullptr, nullptr);

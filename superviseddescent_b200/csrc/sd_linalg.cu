@@ -132,7 +132,9 @@ __global__ void __launch_bounds__(256) gemm_nn_kernel(const float* __restrict__ 
         }
         s_scale[tid] = inv_n;
     }
-    float acc[4][4] = {};
+    // cv::gemm accumulates float products in double (the reference's predict, regressors.hpp:379).
+    // Here: fp32 FMA inside a 16-deep k chunk, chunk sums added into double accumulators.
+    double acc[4][4] = {};
     const int la_r = tid >> 2;           // 0..63 row
     const int la_k = (tid & 3) * 4;      // 0..12 k offset
     const int lb_k = tid >> 4;           // 0..15
@@ -146,6 +148,7 @@ __global__ void __launch_bounds__(256) gemm_nn_kernel(const float* __restrict__ 
             Bs[lb_k][lb_c + e] = (kb < D && c < M) ? B[(long long)kb * ldb + c] : 0.f;
         }
         __syncthreads();
+        float part[4][4] = {};
 #pragma unroll
         for (int kk = 0; kk < GK; ++kk) {
             const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
@@ -154,8 +157,12 @@ __global__ void __launch_bounds__(256) gemm_nn_kernel(const float* __restrict__ 
 #pragma unroll
             for (int r = 0; r < 4; ++r)
 #pragma unroll
-                for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(av[r], bv[c], acc[r][c]);
+                for (int c = 0; c < 4; ++c) part[r][c] = fmaf(av[r], bv[c], part[r][c]);
         }
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[r][c] += (double)part[r][c];
         __syncthreads();
     }
 #pragma unroll
@@ -166,12 +173,13 @@ __global__ void __launch_bounds__(256) gemm_nn_kernel(const float* __restrict__ 
         for (int c = 0; c < 4; ++c) {
             const int j = c0 + tx * 4 + c;
             if (j >= M) continue;
+            const float accf = (float)acc[r][c];
             if (ep.mode == 1) {
-                const float upd = __fmul_rn(acc[r][c], s_scale[ty * 4 + r]);
+                const float upd = __fmul_rn(accf, s_scale[ty * 4 + r]);
                 ep.x_next[(long long)i * M + j] = __fsub_rn(ep.x[(long long)i * M + j], upd);
             } else {
                 float* p = C + (long long)i * ldc + j;
-                *p = (beta == 0.f) ? alpha * acc[r][c] : fmaf(alpha, acc[r][c], beta * (*p));
+                *p = (beta == 0.f) ? alpha * accf : fmaf(alpha, accf, beta * (*p));
             }
         }
     }

@@ -1,0 +1,92 @@
+"""GPU parity of the batched HOG projection (sd_hog_batch) against the CPU oracle, through the C ABI.
+
+Integer results (patch centre, half size, resized 8-bit patch, orientation bin) must be EXACT; the float
+descriptors must agree to 1e-4 relative (max-norm / max-abs), the tolerance BASELINE.json states.
+"""
+import numpy as np
+import pytest
+
+import synth
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _oracle_params(O, p):
+    return O.HogParam(p.variant, p.num_cells, p.cell_size, p.num_bins, p.relative_patch_size)
+
+
+def _check_level(sd, O, images, x, hog_param, ids, right, left, image_index=None):
+    import torch
+    ht = sd.HogTransform(images, [hog_param], ids, right, left)
+    ridx = [ids.index(s) for s in right]
+    lidx = [ids.index(s) for s in left]
+    op = _oracle_params(O, hog_param)
+    A = ht(x, 0, image_index).cpu().numpy()
+    geo, patches, bins = [t.cpu().numpy() for t in ht.debug(x, 0, image_index)]
+    fs = hog_param.num_cells * hog_param.cell_size
+    worst = 0.0
+    for i in range(x.shape[0]):
+        img = images[i if image_index is None else image_index[i]]
+        cx, cy, half = O.patch_geometry(x[i], op, ridx, lidx)
+        assert np.array_equal(geo[i, :, 0], cx) and np.array_equal(geo[i, :, 1], cy) and np.array_equal(geo[i, :, 2], half), f"geometry sample {i}"
+        for l in range(len(ids)):
+            patch = O.resize_linear_u8(O.crop_patch_u8(img, int(cx[l]), int(cy[l]), int(half[l])), fs, fs)
+            assert np.array_equal(patches[i, l], patch), f"resized patch sample {i} landmark {l}"
+            ob = O.hog_orientation_bins(patch.astype(np.float32), hog_param.num_bins)
+            assert np.array_equal(bins[i, l].astype(np.int32), ob), f"orientation bins sample {i} landmark {l}"
+        ref = O.hog_transform(img, x[i], op, ridx, lidx)
+        assert A[i, -1] == 1.0
+        worst = max(worst, rel_err(A[i], ref))
+    assert worst <= TOL, worst
+    return worst
+
+
+def test_hog_rcr22_schedule_on_example_frames(sd, oracle, golden):
+    """The shipped rcr_22 schedule (K=4, 5x5 cells of 11/10/8/6 px) on the reference's annotated frames."""
+    m = oracle.Model(golden.model_path)
+    worst = 0.0
+    for i in (0, 2):
+        gray = golden.examples[f"gray{i}"]
+        x0 = oracle.align_mean(m.mean, golden.examples["boxes"][i]).reshape(1, -1)
+        for level in range(4):
+            p = m.hog_params[level]
+            hp = sd.HoGParam(p.variant, p.num_cells, p.cell_size, p.num_bins, p.relative_patch_size)
+            worst = max(worst, _check_level(sd, oracle, gray[None], x0, hp, m.landmark_ids, m.right_ids, m.left_ids))
+        feats = sd.HogTransform(gray[None], [sd.HoGParam(1, 5, 11, 4, 1.0)], m.landmark_ids, m.right_ids, m.left_ids)(x0[0], 0)
+        assert rel_err(feats.cpu().numpy(), golden.detect[f"features_l0_{i}"]) <= TOL     # committed hog.c golden
+    print("hog rcr22 worst rel err", worst)
+
+
+@pytest.mark.parametrize("K,variant", [(9, 1), (4, 0), (6, 1)])
+def test_hog_synthetic_batch_with_border_patches(sd, oracle, golden, K, variant):
+    """Seeded synthetic frames, boxes hanging over the border (zero padding), K=9 (31-dim cells),
+    Dalal-Triggs, and a generic K that takes the non-templated kernel."""
+    m = oracle.Model(golden.model_path)
+    images = synth.smooth_images(6, 120, 160, seed=11)
+    boxes = synth.face_boxes(6, 120, 160, seed=11, border_fraction=0.5)
+    boxes[0] = (-30, -20, 90, 90)
+    boxes[1] = (110, 70, 80, 80)
+    x = np.stack([oracle.align_mean(m.mean, b) for b in boxes])
+    idx = np.array([5, 4, 3, 2, 1, 0], dtype=np.int32)
+    for cs, rel in ((11, 1.0), (6, 0.25)):
+        hp = sd.HoGParam(variant, 5, cs, K, rel)
+        w = _check_level(sd, oracle, images, x, hp, m.landmark_ids, m.right_ids, m.left_ids, image_index=idx)
+        print(f"K={K} variant={variant} cs={cs} worst rel err {w:.2e}")
+
+
+def test_hog_ragged_and_empty_inputs(sd, oracle, golden):
+    import torch
+    m = oracle.Model(golden.model_path)
+    images = synth.smooth_images(2, 64, 64, seed=5)
+    ht = sd.HogTransform(images, [sd.HoGParam(1, 5, 6, 4, 0.25)], m.landmark_ids, m.right_ids, m.left_ids)
+    empty = torch.empty((0, 44), dtype=torch.float32, device="cuda")
+    assert ht(empty, 0).shape == (0, 8801)
+    # landmarks far outside the frame -> all-zero patches -> features are exactly the bias-only row
+    far = np.full((1, 44), 5000.0, dtype=np.float32)
+    far[0, :22] += np.arange(22) * 7
+    A = ht(far, 0).cpu().numpy()
+    assert A[0, -1] == 1.0 and np.all(A[0, :-1] == 0.0)
+    with pytest.raises(RuntimeError):
+        sd.HogTransform(images, [sd.HoGParam(1, 5, 6, 4, 0.25)], m.landmark_ids, ["nope"], m.left_ids)(far, 0)

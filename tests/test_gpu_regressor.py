@@ -1,0 +1,151 @@
+"""GPU parity of LinearRegressor / SupervisedDescentOptimiser (C ABI) against the reference's literals
+and the CPU oracle."""
+import numpy as np
+import pytest
+
+import known_answers as K
+from conftest import rel_err
+from test_oracle import run_lr_cases, run_sdo_cases
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+class GpuBackend:
+    def __init__(self, sd):
+        self.sd = sd
+
+    def learn(self, data, labels, reg):
+        lr = self.sd.LinearRegressor(self.sd.Regulariser(self.sd.RegularisationType(reg[0]), reg[1], reg[2]))
+        assert lr.learn(np.asarray(data, np.float32), np.asarray(labels, np.float32)) is True   # regressors.hpp:349
+        return lr.x.cpu().numpy()
+
+    def _lr(self, X):
+        import torch
+        lr = self.sd.LinearRegressor()
+        lr._ctx()
+        lr.x = torch.from_numpy(np.ascontiguousarray(X, dtype=np.float32)).cuda()
+        return lr
+
+    def predict(self, values, X):
+        return self._lr(X).predict(np.asarray(values, np.float32)).cpu().numpy()
+
+    def residual(self, data, labels, X):
+        return self._lr(X).test(np.asarray(data, np.float32), np.asarray(labels, np.float32))
+
+    def train(self, x_gt, x0, y, h, n_reg, callback=None):
+        sdo = self.sd.SupervisedDescentOptimiser([self.sd.LinearRegressor() for _ in range(n_reg)])
+        cb = (lambda cur: callback(cur.cpu().numpy())) if callback else None
+        xf = sdo.train(x_gt, x0, y, h, cb)
+        return sdo, xf.cpu().numpy()
+
+    def test(self, sdo, x0, y, h):
+        return sdo.test(x0, y, h).cpu().numpy()
+
+
+def test_linear_regressor_reference_literals(sd):
+    rep = run_lr_cases(GpuBackend(sd))
+    print("gpu", [(n, f"{e:.2e}") for n, e in rep])
+
+
+def test_optimiser_reference_literals(sd):
+    rep = run_sdo_cases(GpuBackend(sd))
+    print("gpu", [(r[0], f"{r[1]:.2e}", f"{r[2]:.2e}") for r in rep])
+
+
+def _features_like(rng, n, d):
+    """HOG-like design matrix: non-negative, bounded by 0.4, correlated columns, bias column of ones."""
+    base = rng.random((n, 8)).astype(np.float32)
+    mix = rng.random((8, d)).astype(np.float32)
+    A = np.clip(0.05 * (base @ mix) + 0.1 * rng.random((n, d)).astype(np.float32), 0, 0.4).astype(np.float32)
+    A[:, -1] = 1.0
+    return A
+
+
+@pytest.mark.parametrize("mode", [2, 0, 1])
+def test_gram_and_solve_vs_oracle(sd, oracle, mode):
+    """[AtA | Atb] and the regularised solve at a size that takes the tensor-core SYRK and the blocked
+    Cholesky.  mode 2 = fp32 SIMT, 0 = 3xTF32 tcgen05, 1 = single-pass TF32 (looser: 10-bit mantissa)."""
+    import ctypes as C
+    import torch
+    from superviseddescent_b200 import _capi
+    rng = np.random.default_rng(123)
+    n, d, m = 1500, 700, 44
+    A = _features_like(rng, n, d)
+    B = (0.05 * rng.standard_normal((n, m))).astype(np.float32)
+    ctx = sd.default_context()
+    ctx.set_gram_mode(mode)
+    try:
+        dA, dB = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda()
+        ldg = d + m
+        G = torch.zeros((d, ldg), dtype=torch.float32, device="cuda")
+        rc = _capi.lib().sd_gram(ctx.h, _capi.ptr(dA), C.c_int64(d), _capi.ptr(dB), C.c_int64(m), n, d, m, _capi.ptr(G), C.c_int64(ldg))
+        assert rc == 0, _capi.lib().sd_last_error(ctx.h)
+        Gh = G.cpu().numpy()
+        A64 = A.astype(np.float64)
+        Gd = A64.T @ A64
+        Rd = A64.T @ B.astype(np.float64)
+        iu = np.triu_indices(d)
+        e_g = np.max(np.abs(Gh[:, :d][iu] - Gd[iu])) / np.max(np.abs(Gd))
+        e_r = rel_err(Gh[:, d:], Rd)
+        print(f"mode {mode}: gram rel err {e_g:.2e}, Atb rel err {e_r:.2e}")
+        tol = 2e-3 if mode == 1 else 2e-6
+        assert e_g <= tol and e_r <= tol * 5
+        reg = sd.Regulariser(sd.RegularisationType.MatrixNorm, 1.5, False)
+        lr = sd.LinearRegressor(reg)
+        lr.learn(dA, dB)
+        X = lr.x.cpu().numpy()
+        Xo, lam = oracle.solve(A, B, oracle.Regulariser(1, 1.5, 0), 1)      # float64 truth
+        Xf, lamf = oracle.solve(A, B, oracle.Regulariser(1, 1.5, 0), 0)     # float32 restatement (Eigen-like)
+        print(f"mode {mode}: lambda gpu {lr.last_lambda:.6g} oracle {lam:.6g}; X rel err vs f64 {rel_err(X, Xo):.2e}; f32 oracle vs f64 {rel_err(Xf, Xo):.2e}")
+        assert abs(lr.last_lambda - lam) <= 1e-5 * lam * (100 if mode == 1 else 1)
+        assert rel_err(X, Xo) <= (5e-2 if mode == 1 else TOL)
+        pred = lr.predict(dA[:64]).cpu().numpy()
+        assert rel_err(pred, oracle.predict(A[:64], X)) <= TOL
+        print("timings", ctx.solver_timings())
+    finally:
+        ctx.set_gram_mode(0)
+
+
+def test_small_lu_path_is_bit_faithful_to_the_oracle_solver(sd, oracle):
+    """D <= 256 uses the partial-pivot LU that restates the oracle's operation order."""
+    rng = np.random.default_rng(9)
+    A = rng.standard_normal((300, 20)).astype(np.float32)
+    B = rng.standard_normal((300, 6)).astype(np.float32)
+    for reg in [(0, 0.0, True), (1, 2.0, True), (1, 0.5, False)]:
+        lr = sd.LinearRegressor(sd.Regulariser(sd.RegularisationType(reg[0]), reg[1], reg[2]))
+        lr.learn(A, B)
+        Xo, lam = oracle.solve(A, B, oracle.Regulariser(reg[0], reg[1], int(reg[2])), 0)
+        assert rel_err(lr.x.cpu().numpy(), Xo) <= 1e-5
+        assert abs(lr.last_lambda - lam) <= 1e-6 * max(lam, 1e-6)
+
+
+def test_singular_system_is_reported(sd):
+    with pytest.raises(RuntimeError):
+        sd.LinearRegressor().learn(np.zeros((1, 1), np.float32), np.ones((1, 1), np.float32))   # test_LinearRegressor1D.cpp:29-38
+
+
+def test_cascade_with_ied_normalisation_vs_oracle(sd, oracle, golden):
+    """train() with InterEyeDistanceNormalisation and a host projection functor, against the oracle cascade."""
+    rng = np.random.default_rng(17)
+    L, n = 6, 80
+    ids = [str(i) for i in range(L)]
+    x_gt = (rng.random((n, 2 * L)) * 50 + 20).astype(np.float32)
+    x0 = (x_gt + rng.standard_normal((n, 2 * L)) * 3).astype(np.float32)
+    W = rng.standard_normal((2 * L, 9)).astype(np.float32) * 0.01
+
+    def h(row, level, idx):
+        f = np.tanh(row @ W)
+        return np.concatenate([f, [1.0]]).astype(np.float32)
+
+    regs = [sd.Regulariser(sd.RegularisationType.MatrixNorm, 0.5, False) for _ in range(3)]
+    norm = sd.InterEyeDistanceNormalisation(ids, ["0", "1"], ["4"])
+    sdo = sd.SupervisedDescentOptimiser([sd.LinearRegressor(r) for r in regs], norm)
+    xf = sdo.train(x_gt, x0, None, h).cpu().numpy()
+    oregs = [oracle.Regulariser(1, 0.5, 0) for _ in range(3)]
+    w, xo, rc = oracle.cascade_train(x_gt, x0, None, oregs, [10] * 3, h, norm=([0, 1], [4]), precision=0)
+    assert rel_err(xf, xo) <= TOL
+    for k in range(3):
+        assert rel_err(sdo.regressors[k].x.cpu().numpy(), w[k]) <= 2e-3     # ill-conditioned toy system: weights looser than outputs
+    xt = sdo.test(x0[:10], None, h).cpu().numpy()
+    assert rel_err(xt, oracle.cascade_apply(x0[:10], None, w, h, norm=([0, 1], [4]))) <= TOL
