@@ -1,0 +1,134 @@
+// B200 drop-in for the reference's include/superviseddescent/regressors.hpp.
+//
+// Same names and call signatures: Regressor (regressors.hpp:43-77), Regulariser (:87-169),
+// PartialPivLUSolver (:180-235), ColPivHouseholderQRSolver (:245-306), LinearRegressor<Solver>
+// (:318-400, public member `x`).  The arithmetic is NOT here: Solver::solve forwards to sd_learn and
+// predict/test to sd_predict / sd_test_residual of libsd_b200.so (hand-written sm_100a kernels);
+// there is no CPU path.
+#pragma once
+
+#include <iostream>
+#include <string>
+
+#include "sd_b200/device.hpp"
+
+namespace superviseddescent {
+
+class Regressor {
+public:
+    virtual ~Regressor() {}
+    virtual bool learn(cv::Mat data, cv::Mat labels) = 0;
+    virtual double test(cv::Mat data, cv::Mat labels) = 0;
+    virtual cv::Mat predict(cv::Mat values) = 0;
+};
+
+class Regulariser {
+public:
+    enum class RegularisationType { Manual, MatrixNorm };
+
+    Regulariser(RegularisationType regularisation_type = RegularisationType::Manual, float param = 0.0f, bool regularise_last_row = true)
+        : regularisation_type(regularisation_type), lambda(param), regularise_last_row(regularise_last_row) {}
+
+    // The C-ABI view of this regulariser; the lambda rule itself (regressors.hpp:126-148) runs on the device.
+    sd_regulariser c() const
+    {
+        sd_regulariser r;
+        r.type = regularisation_type == RegularisationType::MatrixNorm ? 1 : 0;
+        r.param = lambda;
+        r.regularise_last_row = regularise_last_row ? 1 : 0;
+        return r;
+    }
+    static Regulariser from_c(const sd_regulariser& r)
+    {
+        return Regulariser(r.type == 1 ? RegularisationType::MatrixNorm : RegularisationType::Manual, r.param, r.regularise_last_row != 0);
+    }
+
+private:
+    RegularisationType regularisation_type;
+    float lambda;
+    bool regularise_last_row;
+};
+
+// The solver behind every Solver name of the reference: Gram on tensor cores + LU / Cholesky on the device.
+class B200Solver {
+public:
+    cv::Mat solve(cv::Mat data, cv::Mat labels, Regulariser regulariser)
+    {
+        if (data.empty() || labels.empty() || data.rows != labels.rows) throw std::runtime_error("solve: data/labels shape mismatch");
+        sd_ctx* ctx = sd_b200::context();
+        const int N = data.rows, D = data.cols, M = labels.cols;
+        // one extended operand [A | B] so that A^T B rides along in the same SYRK
+        const int64_t ld = (static_cast<int64_t>(D) + M + 3) / 4 * 4;
+        sd_b200::DeviceBuffer ext(static_cast<size_t>(N) * ld * sizeof(float)), dX(static_cast<size_t>(D) * M * sizeof(float));
+        for (int r = 0; r < N; ++r) {
+            sd_b200::check(ctx, sd_memcpy_h2d(ctx, ext.as<float>() + r * ld, data.ptr<float>(r), sizeof(float) * D), "solve");
+            sd_b200::check(ctx, sd_memcpy_h2d(ctx, ext.as<float>() + r * ld + D, labels.ptr<float>(r), sizeof(float) * M), "solve");
+        }
+        const sd_regulariser reg = regulariser.c();
+        sd_b200::check(ctx, sd_learn(ctx, ext.as<float>(), ld, ext.as<float>() + D, ld, N, D, M, &reg, dX.as<float>(), &last_lambda), "sd_learn");
+        return sd_b200::download(dX.as<float>(), D, M, M);
+    }
+    float last_lambda = 0.0f;
+};
+
+using PartialPivLUSolver = B200Solver;          // regressors.hpp:180-235
+using ColPivHouseholderQRSolver = B200Solver;   // regressors.hpp:245-306 (same system; rank diagnostics: SD_ERR_NUMERIC)
+
+template <class Solver = PartialPivLUSolver>
+class LinearRegressor : public Regressor {
+public:
+    LinearRegressor(Regulariser regulariser = Regulariser()) : x(), regulariser(regulariser) {}
+    // copies share the host model (cv::Mat is reference counted, as in the reference) but never the device copy
+    LinearRegressor(const LinearRegressor& o) : x(o.x), regulariser(o.regulariser), solver(o.solver), dirty(true) {}
+    LinearRegressor& operator=(const LinearRegressor& o)
+    {
+        if (this != &o) { x = o.x; regulariser = o.regulariser; solver = o.solver; dirty = true; }
+        return *this;
+    }
+
+    bool learn(cv::Mat data, cv::Mat labels) override
+    {
+        this->x = solver.solve(data, labels, regulariser);
+        dirty = true;
+        return true;   // regressors.hpp:349
+    }
+
+    double test(cv::Mat data, cv::Mat labels) override
+    {
+        sd_ctx* ctx = sd_b200::context();
+        sd_b200::DeviceBuffer dV, dL;
+        sd_b200::upload(data, dV, data.cols);
+        sd_b200::upload(labels, dL, labels.cols);
+        double residual = 0;
+        sd_b200::check(ctx, sd_test_residual(ctx, dV.as<float>(), data.cols, dL.as<float>(), labels.cols, data.rows, data.cols, device_x(), x.cols, &residual), "sd_test_residual");
+        return residual;
+    }
+
+    cv::Mat predict(cv::Mat values) override
+    {
+        sd_ctx* ctx = sd_b200::context();
+        sd_b200::DeviceBuffer dV, dO(static_cast<size_t>(values.rows) * x.cols * sizeof(float));
+        sd_b200::upload(values, dV, values.cols);
+        sd_b200::check(ctx, sd_predict(ctx, dV.as<float>(), values.cols, values.rows, values.cols, device_x(), x.cols, dO.as<float>(), x.cols), "sd_predict");
+        return sd_b200::download(dO.as<float>(), values.rows, x.cols, x.cols);
+    }
+
+    cv::Mat x;   // the learned D x M model, public as in the reference (regressors.hpp:383)
+
+    // device-resident copy of x for the cascade kernels (uploaded lazily after x changes)
+    const float* device_x()
+    {
+        if (dirty || dx.bytes() == 0) { sd_b200::upload(x, dx, x.cols); dirty = false; }
+        return dx.template as<float>();
+    }
+    void set_x(cv::Mat new_x) { x = new_x; dirty = true; }
+    const Regulariser& get_regulariser() const { return regulariser; }
+
+private:
+    Regulariser regulariser;
+    Solver solver;
+    sd_b200::DeviceBuffer dx;
+    bool dirty = true;
+};
+
+}  // namespace superviseddescent
