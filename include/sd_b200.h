@@ -164,7 +164,7 @@ SD_API int sd_set_gram_mode(sd_ctx* ctx, int mode);
 SD_API int sd_cascade_targets(sd_ctx* ctx, const float* d_x, const float* d_x_gt, int N, int P,
                               const sd_normalisation* norm, float* d_B, int64_t ldb);
 /* x_next_i = x_i - (A_i X) (.) (1 / norm(x_i))   (superviseddescent.hpp:209-215, 296-301, 336-339)
- * d_x_next may alias d_x. */
+ * d_x_next must not alias d_x. */
 SD_API int sd_cascade_update(sd_ctx* ctx, const float* d_A, int64_t lda, int N, int D,
                              const float* d_X, int P, const float* d_x, const sd_normalisation* norm,
                              float* d_x_next);

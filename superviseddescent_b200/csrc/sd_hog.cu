@@ -24,6 +24,7 @@ namespace {
 
 constexpr int kHogThreads = 256;
 constexpr int kHogWarps = kHogThreads / 32;
+constexpr int kLutDim = 511;                       // gx, gy in [-255, 255]
 
 struct HogArgs {
     const uint8_t* images;
@@ -34,10 +35,9 @@ struct HogArgs {
     const float* x;
     long long ldx;
     int N, L;
-    sd_eyes_dev eyes;
     int variant, nc, cs, K, fs, dd;
-    float rel;
-    float ox[SD_MAX_BINS], oy[SD_MAX_BINS];
+    const int* half;            // per sample: half patch size (hog_geometry_kernel)
+    const int8_t* lut;          // (gy+255)*511 + (gx+255) -> directed orientation bin, -1 for a zero gradient
     float* A;
     long long ld;
     int* geometry;
@@ -46,9 +46,57 @@ struct HogArgs {
     int* status;
 };
 
+// ---- per-sample geometry: IED -> half patch size (adaptive_vlhog.hpp:123), once per sample instead of
+//      once per thread of every patch ---------------------------------------------------------------
+__global__ void hog_geometry_kernel(const float* __restrict__ x, long long ldx, int N, int L, const sd_eyes_dev eyes, float rel,
+                                    int* __restrict__ half_out, int* __restrict__ status)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const double ied = sd_device_ied(x + (long long)i * ldx, L, eyes);
+    int half = (int)round(__dmul_rn(__dmul_rn((double)rel, ied), 0.5));   // std::round(float rel * double ied / 2)
+    if (half < 1) {          // cv::resize would throw on the empty ROI; flag it and keep going
+        half = 1;
+        atomicOr(status, 1);
+    }
+    half_out[i] = half;
+}
+
+// ---- (gx, gy) -> orientation bin table, generated ON THE DEVICE with the reference's float expression
+//      (hog.c:645-672): gradients of an 8-bit patch are integers in [-255, 255], so the arg-max is a pure
+//      function of the pair and can be tabulated exactly. ---------------------------------------------
+struct LutArgs {
+    int K;
+    float ox[SD_MAX_BINS], oy[SD_MAX_BINS];
+};
+
+__global__ void hog_lut_kernel(const LutArgs t, int8_t* __restrict__ lut)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= kLutDim * kLutDim) return;
+    const float gx = (float)(idx % kLutDim - 255), gy = (float)(idx / kLutDim - 255);
+    const float g2 = __fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy));
+    int bin = -1;
+    if (g2 > 0.f) {
+        const float g = __fsqrt_rn(g2);
+        // (float)((double)gx / max((double)g, 1e-10)) == gx / g in float: double rounding is innocuous for
+        // division when the wide format has >= 2p+2 bits (53 >= 50).
+        const float ux = __fdiv_rn(gx, g);
+        const float uy = __fdiv_rn(gy, g);
+        float best = 0.f;
+        for (int k = 0; k < t.K; ++k) {
+            float s = __fadd_rn(__fmul_rn(ux, t.ox[k]), __fmul_rn(uy, t.oy[k]));
+            int b = k;
+            if (s < 0.f) { s = -s; b += t.K; }
+            if (s > best) { best = s; bin = b; }   // strict >, ascending k
+        }
+    }
+    lut[idx] = (int8_t)bin;
+}
+
 // shared-memory carve-up (same function on host and device)
 struct HogSmem {
-    int patch, bin, r1, xofs, yofs0, yofs1, xa, yb, sbin, sw1, sw2, lo, hi, hist, energy, fac, priv, feat, total;
+    int patch, bin, r1, xofs, yofs0, yofs1, xa, yb, sbin, sw1, sw2, wcell, lo, hi, hist, energy, fac, priv, feat, total;
 };
 
 __host__ __device__ inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
@@ -71,6 +119,7 @@ __host__ __device__ inline HogSmem hog_smem_layout(int fs, int nc, int K, int dd
     s.sbin = o;   o += fs * 4;
     s.sw1 = o;    o += fs * 4;
     s.sw2 = o;    o += fs * 4;
+    s.wcell = o;  o += nc * fs * 4;                         // weight of pixel t for cell index c (0 if it does not vote)
     s.lo = o;     o += nc * 4;
     s.hi = o;     o += nc * 4;
     s.hist = o;   o += cells * 2 * K * 4;
@@ -106,6 +155,7 @@ __global__ void __launch_bounds__(kHogThreads) hog_patch_kernel(const HogArgs a)
     int* s_sbin = reinterpret_cast<int*>(smem + lay.sbin);
     float* s_sw1 = reinterpret_cast<float*>(smem + lay.sw1);
     float* s_sw2 = reinterpret_cast<float*>(smem + lay.sw2);
+    float* s_wcell = reinterpret_cast<float*>(smem + lay.wcell);
     int* s_lo = reinterpret_cast<int*>(smem + lay.lo);
     int* s_hi = reinterpret_cast<int*>(smem + lay.hi);
     float* s_hist = reinterpret_cast<float*>(smem + lay.hist);
@@ -120,18 +170,12 @@ __global__ void __launch_bounds__(kHogThreads) hog_patch_kernel(const HogArgs a)
     const int sample = (int)(patch_id / a.L);
     const int lm = (int)(patch_id - (long long)sample * a.L);
 
-    // ---- S0: geometry (every thread, redundantly) -----------------------------------------
+    // ---- S0: geometry: half size from the per-sample pre-pass, centre = cvRound (adaptive_vlhog.hpp:132-133)
     const float* __restrict__ row = a.x + (long long)sample * a.ldx;
-    const double ied = sd_device_ied(row, a.L, a.eyes);
-    // adaptive_vlhog.hpp:123  int half = std::round(float rel * double ied / 2)
-    int half = (int)round(__dmul_rn(__dmul_rn((double)a.rel, ied), 0.5));
-    if (half < 1) {   // cv::resize would throw on the empty ROI; flag it and keep going
-        half = 1;
-        if (tid == 0 && a.status) atomicOr(a.status, 1);
-    }
+    const int half = __ldg(a.half + sample);
     const int P = 2 * half;
-    const int cx = __float2int_rn(row[lm]);            // cvRound, :132
-    const int cy = __float2int_rn(row[lm + a.L]);      // :133
+    const int cx = __float2int_rn(row[lm]);
+    const int cy = __float2int_rn(row[lm + a.L]);
     int img_idx = a.image_index ? a.image_index[sample] : sample;
     if (img_idx < 0 || img_idx >= a.image_count) {
         img_idx = 0;
@@ -168,36 +212,51 @@ __global__ void __launch_bounds__(kHogThreads) hog_patch_kernel(const HogArgs a)
         int b = (int)h;                                   // vl_floor_f, hog.h:52-58
         if (!(h >= 0.f || (float)b == h)) b -= 1;
         const float w2 = __fsub_rn(h, (float)b);
+        const float w1 = (float)__dadd_rn(1.0, -(double)w2);
         s_sbin[t] = b;
         s_sw2[t] = w2;
-        s_sw1[t] = (float)__dadd_rn(1.0, -(double)w2);
+        s_sw1[t] = w1;
+        // weight with which pixel t votes into cell index c: w1 for its own bin, w2 for the next one
+        for (int c = 0; c < nc; ++c) s_wcell[c * fs + t] = (b == c) ? w1 : ((b == c - 1) ? w2 : 0.f);
     }
     for (int i = tid; i < kHogWarps * 2 * K * 32; i += kHogThreads) s_priv[i] = 0.f;
     __syncthreads();
 
-    // ---- S1: zero-padded crop + fixed-point bilinear resize straight from the frame ----------
-    const int x0 = cx - half, y0 = cy - half;
-    const int W = a.width, H = a.height, stride = a.row_stride;
-    for (int idx = tid; idx < fs * fs; idx += kHogThreads) {
-        const int dy = idx / fs, dx = idx - dy * fs;
-        const int sx = s_xofs[dx];
-        const short2 xa = s_xa[dx];
-        const short2 yb = s_yb[dy];
-        const int ix0 = x0 + sx, ix1 = ix0 + 1;
-        const int iy0 = y0 + s_yofs0[dy], iy1 = y0 + s_yofs1[dy];
-        const bool cx0 = (unsigned)ix0 < (unsigned)W, cx1 = (unsigned)ix1 < (unsigned)W && xa.y != 0;
-        const bool ry0 = (unsigned)iy0 < (unsigned)H, ry1 = (unsigned)iy1 < (unsigned)H;
-        const uint8_t* r0 = img + (long long)iy0 * stride;
-        const uint8_t* r1 = img + (long long)iy1 * stride;
-        const int p00 = (ry0 && cx0) ? __ldg(r0 + ix0) : 0;
-        const int p01 = (ry0 && cx1) ? __ldg(r0 + ix1) : 0;
-        const int p10 = (ry1 && cx0) ? __ldg(r1 + ix0) : 0;
-        const int p11 = (ry1 && cx1) ? __ldg(r1 + ix1) : 0;
-        const int t0 = p00 * xa.x + p01 * xa.y;
-        const int t1 = p10 * xa.x + p11 * xa.y;
-        const int v = ((((int)yb.x * (t0 >> 4)) >> 16) + (((int)yb.y * (t1 >> 4)) >> 16) + 2) >> 2;
-        s_patch[idx] = (uint8_t)v;
-        if (a.patches) a.patches[patch_id * fs * fs + idx] = (uint8_t)v;
+    // ---- S1: zero-padded crop + fixed-point bilinear resize straight from the frame; one output row
+    //      per warp pass, lanes along x (no integer division, row terms are warp-uniform) --------------
+    {
+        const int x0 = cx - half, y0 = cy - half;
+        const int W = a.width, H = a.height, stride = a.row_stride;
+        const bool inside = x0 >= 0 && y0 >= 0 && x0 + P <= W && y0 + P <= H;
+        for (int dy = warp; dy < fs; dy += kHogWarps) {
+            const short2 yb = s_yb[dy];
+            const int iy0 = y0 + s_yofs0[dy], iy1 = y0 + s_yofs1[dy];
+            const bool ry0 = (unsigned)iy0 < (unsigned)H, ry1 = (unsigned)iy1 < (unsigned)H;
+            const uint8_t* r0 = img + (long long)iy0 * stride + x0;
+            const uint8_t* r1 = img + (long long)iy1 * stride + x0;
+            for (int dx = lane; dx < fs; dx += 32) {
+                const int sx = s_xofs[dx];
+                const short2 xa = s_xa[dx];
+                int p00, p01, p10, p11;
+                if (inside) {
+                    const int sx1 = min(sx + 1, P - 1);              // clamped tap has zero weight
+                    p00 = __ldg(r0 + sx); p01 = __ldg(r0 + sx1);
+                    p10 = __ldg(r1 + sx); p11 = __ldg(r1 + sx1);
+                } else {
+                    const int ix0 = x0 + sx;
+                    const bool c0 = (unsigned)ix0 < (unsigned)W, c1 = (unsigned)(ix0 + 1) < (unsigned)W && xa.y != 0;
+                    p00 = (ry0 && c0) ? __ldg(r0 + sx) : 0;
+                    p01 = (ry0 && c1) ? __ldg(r0 + sx + 1) : 0;
+                    p10 = (ry1 && c0) ? __ldg(r1 + sx) : 0;
+                    p11 = (ry1 && c1) ? __ldg(r1 + sx + 1) : 0;
+                }
+                const int t0 = p00 * xa.x + p01 * xa.y;
+                const int t1 = p10 * xa.x + p11 * xa.y;
+                const int v = ((((int)yb.x * (t0 >> 4)) >> 16) + (((int)yb.y * (t1 >> 4)) >> 16) + 2) >> 2;
+                s_patch[dy * fs + dx] = (uint8_t)v;
+                if (a.patches) a.patches[patch_id * fs * fs + dy * fs + dx] = (uint8_t)v;
+            }
+        }
     }
     // per cell-column pixel ranges that vote into it (same for rows: square patch, square cells)
     if (tid < nc) {
@@ -211,39 +270,31 @@ __global__ void __launch_bounds__(kHogThreads) hog_patch_kernel(const HogArgs a)
     }
     __syncthreads();
 
-    // ---- S2: gradient + orientation arg-max per interior pixel (hog.c:631-672) ---------------
-    for (int idx = tid; idx < fs * fs; idx += kHogThreads) {
-        const int y = idx / fs, x = idx - y * fs;
-        int bin = -1;
-        float g = 0.f;
-        if (x >= 1 && x <= fs - 2 && y >= 1 && y <= fs - 2) {
-            const float gx = (float)((int)s_patch[idx + 1] - (int)s_patch[idx - 1]);
-            const float gy = (float)((int)s_patch[idx + fs] - (int)s_patch[idx - fs]);
-            const float g2 = __fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy));
-            if (g2 > 0.f) {
-                g = __fsqrt_rn(g2);
-                // (float)((double)gx / max((double)g, 1e-10)) == gx / g in float: double rounding is
-                // innocuous for division when the wide format has >= 2p+2 bits (53 >= 50).
-                const float ux = __fdiv_rn(gx, g);
-                const float uy = __fdiv_rn(gy, g);
-                float best = 0.f;
-#pragma unroll
-                for (int k = 0; k < (KT > 0 ? KT : SD_MAX_BINS); ++k) {
-                    if (KT == 0 && k >= K) break;
-                    float s = __fadd_rn(__fmul_rn(ux, a.ox[k]), __fmul_rn(uy, a.oy[k]));
-                    int b = k;
-                    if (s < 0.f) { s = -s; b += K; }
-                    if (s > best) { best = s; bin = b; }   // strict >, ascending k
-                }
-            }
+    // ---- S2: gradient + orientation arg-max per interior pixel (hog.c:631-672): the arg-max comes from the
+    //      device-generated table, the modulus is sqrtf of the exact integer g2 ---------------------------
+    for (int y = 1 + warp; y <= fs - 2; y += kHogWarps) {
+        for (int x = 1 + lane; x <= fs - 2; x += 32) {
+            const int idx = y * fs + x;
+            const int gx = (int)s_patch[idx + 1] - (int)s_patch[idx - 1];
+            const int gy = (int)s_patch[idx + fs] - (int)s_patch[idx - fs];
+            const int bin = __ldg(a.lut + (gy + 255) * kLutDim + (gx + 255));
+            s_bin[idx] = (int8_t)bin;
+            s_gmag[idx] = __fsqrt_rn((float)(gx * gx + gy * gy));
         }
-        s_bin[idx] = (int8_t)bin;
-        s_gmag[idx] = g;
-        if (a.bins) a.bins[patch_id * fs * fs + idx] = (int8_t)bin;
+    }
+    if (a.bins) {
+        __syncthreads();
+        for (int idx = tid; idx < fs * fs; idx += kHogThreads) {
+            const int y = idx / fs, x = idx - y * fs;
+            const bool interior = x >= 1 && x <= fs - 2 && y >= 1 && y <= fs - 2;
+            a.bins[patch_id * fs * fs + idx] = interior ? s_bin[idx] : (int8_t)-1;
+        }
     }
     __syncthreads();
 
-    // ---- S3: spatial vote, gathered per cell by one warp (hog.c:697-724) ---------------------
+    // ---- S3: spatial vote, gathered per cell by one warp (hog.c:697-724).  Lanes run along x inside the
+    //      cell's window (2*cs wide), 32 >> shift rows per pass; every lane owns a private column of the
+    //      histogram (bank == lane: conflict free), reduced by a skewed transposed read. --------------------
     {
         float* priv = s_priv + warp * (2 * K * 32);
         for (int c = warp; c < cells; c += kHogWarps) {
@@ -251,27 +302,77 @@ __global__ void __launch_bounds__(kHogThreads) hog_patch_kernel(const HogArgs a)
             const int xlo = s_lo[ci], xhi = s_hi[ci], ylo = s_lo[cj], yhi = s_hi[cj];
             const int ww = xhi - xlo + 1, hh = yhi - ylo + 1;
             if (ww > 0 && hh > 0) {
-                const int count = ww * hh;
-                for (int t = lane; t < count; t += 32) {
-                    const int ry = t / ww;
-                    const int px = xlo + (t - ry * ww), py = ylo + ry;
-                    const int idx = py * fs + px;
-                    const int b = s_bin[idx];
-                    if (b >= 0) {
-                        const float wx = (s_sbin[px] == ci) ? s_sw1[px] : s_sw2[px];
-                        const float wy = (s_sbin[py] == cj) ? s_sw1[py] : s_sw2[py];
-                        const float v = __fmul_rn(__fmul_rn(s_gmag[idx], wx), wy);   // grad * wx * wy
-                        priv[b * 32 + lane] = __fadd_rn(priv[b * 32 + lane], v);
+                const float* wyt = s_wcell + cj * fs;
+                if (ww <= 32) {
+                    const int shift = ww <= 8 ? 3 : (ww <= 16 ? 4 : 5);
+                    const int lx = lane & ((1 << shift) - 1), lr = lane >> shift, rpi = 32 >> shift;
+                    if (lx < ww) {
+                        const int px = xlo + lx;
+                        const float wx = s_wcell[ci * fs + px];
+                        const int8_t* bp = s_bin + (ylo + lr) * fs + px;
+                        const float* gp = s_gmag + (ylo + lr) * fs + px;
+                        const float* wp = wyt + ylo + lr;
+                        const int step = rpi * fs;
+                        float* pl = priv + lane;
+#pragma unroll 2
+                        for (int ry = lr; ry < hh; ry += rpi) {
+                            // a zero gradient has bin -1 and modulus 0: it votes +0 into bin 0 (no branch)
+                            const int b = max((int)*bp, 0);
+                            const float v = __fmul_rn(__fmul_rn(*gp, wx), *wp);   // grad * wx * wy
+                            float* q = pl + (b << 5);
+                            *q = __fadd_rn(*q, v);
+                            bp += step; gp += step; wp += rpi;
+                        }
                     }
+                } else {                                   // very wide cells: lanes stride along x
+                    for (int py = ylo; py <= yhi; ++py)
+                        for (int px = xlo + lane; px <= xhi; px += 32) {
+                            const int idx = py * fs + px;
+                            const int b = s_bin[idx];
+                            if (b >= 0) {
+                                const float v = __fmul_rn(__fmul_rn(s_gmag[idx], s_wcell[ci * fs + px]), wyt[py]);
+                                priv[b * 32 + lane] = __fadd_rn(priv[b * 32 + lane], v);
+                            }
+                        }
                 }
             }
             __syncwarp();
-            for (int b = 0; b < 2 * K; ++b) {
-                float v = priv[b * 32 + lane];
-                priv[b * 32 + lane] = 0.f;
+            if (KT > 0) {
+                // column sums of the private table by recursive halving: after log2(NB) exchange steps every
+                // lane owns one bin, the remaining butterfly steps finish the sum (fixed tree -> deterministic)
+                constexpr int NB = KT > 0 ? (2 * KT <= 8 ? 8 : (2 * KT <= 16 ? 16 : 32)) : 32;
+                float v[NB];
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
-                if (lane == 0) s_hist[b * cells + c] = v;
+                for (int b = 0; b < NB; ++b) {
+                    v[b] = b < 2 * KT ? priv[b * 32 + lane] : 0.f;
+                    if (b < 2 * KT) priv[b * 32 + lane] = 0.f;
+                }
+                int bin = 0;
+#pragma unroll
+                for (int o = 16, n = NB; n > 1; o >>= 1, n >>= 1) {
+                    const bool up = (lane & o) != 0;
+#pragma unroll
+                    for (int i = 0; i < n / 2; ++i) {
+                        const float send = up ? v[i] : v[i + n / 2];
+                        const float keep = up ? v[i + n / 2] : v[i];
+                        v[i] = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, o));
+                    }
+                    bin += up ? n / 2 : 0;
+                }
+                float tot = v[0];
+#pragma unroll
+                for (int o = 32 / NB / 2; o > 0; o >>= 1) tot = __fadd_rn(tot, __shfl_xor_sync(0xffffffffu, tot, o));
+                if ((lane & (32 / NB - 1)) == 0 && bin < 2 * KT) s_hist[bin * cells + c] = tot;
+            } else {
+                // transposed reduction: lane b sums row b of the private table, starting at column b (skew -> distinct banks)
+                for (int b = lane; b < 2 * K; b += 32) {
+                    float sacc = 0.f;
+#pragma unroll 8
+                    for (int j = 0; j < 32; ++j) sacc = __fadd_rn(sacc, priv[b * 32 + ((j + b) & 31)]);
+                    s_hist[b * cells + c] = sacc;
+                }
+                __syncwarp();
+                for (int i = lane; i < 2 * K * 32; i += 32) priv[i] = 0.f;
             }
             __syncwarp();
         }
@@ -381,7 +482,8 @@ int launch_hog(sd_ctx* ctx, const sd_image_batch* images, const int32_t* d_image
     if (!eyes || eyes->kind != 1) return sd_fail(ctx, SD_ERR_INVALID, "HogTransform needs the eye landmark indices (adaptive patch size)");
 
     HogArgs a;
-    int rc = sd_eyes_to_dev(ctx, eyes, L, &a.eyes);
+    sd_eyes_dev eyes_dev;
+    int rc = sd_eyes_to_dev(ctx, eyes, L, &eyes_dev);
     if (rc) return rc;
     a.images = images->d_data;
     a.width = images->width; a.height = images->height; a.row_stride = images->row_stride;
@@ -391,17 +493,34 @@ int launch_hog(sd_ctx* ctx, const sd_image_batch* images, const int32_t* d_image
     a.x = d_x; a.ldx = ldx; a.N = N; a.L = L;
     a.variant = p->variant; a.nc = p->num_cells; a.cs = p->cell_size; a.K = p->num_bins; a.fs = fs;
     a.dd = p->variant == 1 ? 3 * p->num_bins + 4 : 4 * p->num_bins;
-    a.rel = p->relative_patch_size;
-    for (int k = 0; k < SD_MAX_BINS; ++k) { a.ox[k] = 0.f; a.oy[k] = 0.f; }
-    for (int k = 0; k < p->num_bins; ++k) {              // hog.c:195-204 (host libm, as the reference)
-        const double angle = k * 3.141592653589793 / p->num_bins;
-        a.ox[k] = (float)cos(angle);
-        a.oy[k] = (float)sin(angle);
-    }
     a.A = d_A; a.ld = ld;
     if (d_A) SD_REQUIRE(ctx, ld >= (int64_t)L * a.nc * a.nc * a.dd + 1, "ld < feature length");
     a.geometry = d_geometry; a.patches = d_patches; a.bins = d_bins;
     a.status = reinterpret_cast<int*>(ctx->d_scratch);   // bit 0: empty patch, bit 1: bad image index
+
+    // orientation table for this K, built once per context (hog.c:195-204: host libm cos/sin, as the reference)
+    if (!ctx->hog_lut[a.K]) {
+        LutArgs t;
+        t.K = a.K;
+        for (int k = 0; k < SD_MAX_BINS; ++k) { t.ox[k] = 0.f; t.oy[k] = 0.f; }
+        for (int k = 0; k < a.K; ++k) {
+            const double angle = k * 3.141592653589793 / a.K;
+            t.ox[k] = (float)cos(angle);
+            t.oy[k] = (float)sin(angle);
+        }
+        void* lut = nullptr;
+        SD_CUDA(ctx, cudaMalloc(&lut, (size_t)kLutDim * kLutDim));
+        hog_lut_kernel<<<sd_div_up(kLutDim * kLutDim, 256), 256, 0, ctx->stream>>>(t, (int8_t*)lut);
+        SD_LAUNCH_CHECK(ctx, "hog_lut_kernel");
+        ctx->hog_lut[a.K] = lut;
+    }
+    a.lut = (const int8_t*)ctx->hog_lut[a.K];
+
+    int* d_half = (int*)sd_workspace(ctx, SD_WS_GEOM, (size_t)N * sizeof(int));
+    if (!d_half) return SD_ERR_CUDA;
+    hog_geometry_kernel<<<sd_div_up(N, 128), 128, 0, ctx->stream>>>(d_x, ldx, N, L, eyes_dev, p->relative_patch_size, d_half, a.status);
+    SD_LAUNCH_CHECK(ctx, "hog_geometry_kernel");
+    a.half = d_half;
 
     const HogSmem lay = hog_smem_layout(fs, a.nc, a.K, a.dd);
     SD_REQUIRE(ctx, lay.total <= 227 * 1024, "HOG configuration needs more than 227 KB of shared memory");

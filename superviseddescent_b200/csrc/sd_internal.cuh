@@ -16,7 +16,7 @@
 #define SD_MAX_BINS 16   // undirected orientations K supported by the HOG kernel
 
 enum { SD_WS_GRAM_EXT = 0, SD_WS_SPLIT_HI, SD_WS_SPLIT_LO, SD_WS_FEATURES, SD_WS_SCRATCH, SD_WS_DIAGINV,
-       SD_WS_PARTIAL, SD_WS_COUNT };
+       SD_WS_PARTIAL, SD_WS_GEOM, SD_WS_GEMM_PARTIAL, SD_WS_COUNT };
 
 struct sd_ctx {
     int device = 0;
@@ -29,6 +29,7 @@ struct sd_ctx {
     int gram_mode = 0;
     float timings[4] = {0, 0, 0, 0};
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    void* hog_lut[SD_MAX_BINS + 1] = {};   // per K: (gx,gy) -> orientation bin table (sd_hog.cu)
     void* ws[SD_WS_COUNT] = {};
     size_t ws_bytes[SD_WS_COUNT] = {};
     // pinned scratch for small device->host results (lambda, residual, status flags)

@@ -111,10 +111,12 @@ struct GemmEpilogue {
     sd_eyes_dev eyes;
 };
 
+// blockIdx.z = split along D; with gridDim.z > 1 every split writes its partial sums (double) to
+// `partial` [split][N][M] and gemm_finalize_kernel reduces them in a fixed order.
 __global__ void __launch_bounds__(256) gemm_nn_kernel(const float* __restrict__ A, long long lda, int N, int D,
                                                       const float* __restrict__ B, long long ldb, int M,
                                                       float* __restrict__ C, long long ldc, float alpha, float beta,
-                                                      const GemmEpilogue ep)
+                                                      const GemmEpilogue ep, double* __restrict__ partial, int k_per_split)
 {
     __shared__ __align__(16) float As[GK][GT + 4];     // transposed: As[k][row]
     __shared__ __align__(16) float Bs[GK][GT + 4];
@@ -122,7 +124,9 @@ __global__ void __launch_bounds__(256) gemm_nn_kernel(const float* __restrict__ 
     const int tid = threadIdx.x;
     const int ty = tid >> 4, tx = tid & 15;
     const int r0 = blockIdx.y * GT, c0 = blockIdx.x * GT;
-    if (ep.mode == 1 && tid < GT) {
+    const int kbeg = blockIdx.z * k_per_split;
+    const int kend = min(D, kbeg + k_per_split);
+    if (ep.mode == 1 && !partial && tid < GT) {
         const int r = r0 + tid;
         float inv_n = 1.0f;
         if (r < N && ep.eyes.kind == 1) {
@@ -139,13 +143,36 @@ __global__ void __launch_bounds__(256) gemm_nn_kernel(const float* __restrict__ 
     const int la_k = (tid & 3) * 4;      // 0..12 k offset
     const int lb_k = tid >> 4;           // 0..15
     const int lb_c = (tid & 15) * 4;     // 0..60
-    for (int k0 = 0; k0 < D; k0 += GK) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int r = r0 + la_r, k = k0 + la_k + e;
-            As[la_k + e][la_r] = (r < N && k < D) ? A[(long long)r * lda + k] : 0.f;
-            const int kb = k0 + lb_k, c = c0 + lb_c + e;
-            Bs[lb_k][lb_c + e] = (kb < D && c < M) ? B[(long long)kb * ldb + c] : 0.f;
+    const bool a_vec = (lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && (kbeg % 4 == 0);
+    const bool b_vec = (ldb % 4 == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
+    for (int k0 = kbeg; k0 < kend; k0 += GK) {
+        {
+            const int r = r0 + la_r, k = k0 + la_k;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < N) {
+                const float* src = A + (long long)r * lda + k;
+                if (a_vec && k + 3 < kend) v = *reinterpret_cast<const float4*>(src);
+                else {
+                    if (k < kend) v.x = src[0];
+                    if (k + 1 < kend) v.y = src[1];
+                    if (k + 2 < kend) v.z = src[2];
+                    if (k + 3 < kend) v.w = src[3];
+                }
+            }
+            As[la_k][la_r] = v.x; As[la_k + 1][la_r] = v.y; As[la_k + 2][la_r] = v.z; As[la_k + 3][la_r] = v.w;
+            const int kb = k0 + lb_k, c = c0 + lb_c;
+            float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (kb < kend) {
+                const float* src = B + (long long)kb * ldb + c;
+                if (b_vec && c + 3 < M) w = *reinterpret_cast<const float4*>(src);
+                else {
+                    if (c < M) w.x = src[0];
+                    if (c + 1 < M) w.y = src[1];
+                    if (c + 2 < M) w.z = src[2];
+                    if (c + 3 < M) w.w = src[3];
+                }
+            }
+            *reinterpret_cast<float4*>(&Bs[lb_k][lb_c]) = w;
         }
         __syncthreads();
         float part[4][4] = {};
@@ -173,6 +200,10 @@ __global__ void __launch_bounds__(256) gemm_nn_kernel(const float* __restrict__ 
         for (int c = 0; c < 4; ++c) {
             const int j = c0 + tx * 4 + c;
             if (j >= M) continue;
+            if (partial) {
+                partial[((long long)blockIdx.z * N + i) * M + j] = acc[r][c];
+                continue;
+            }
             const float accf = (float)acc[r][c];
             if (ep.mode == 1) {
                 const float upd = __fmul_rn(accf, s_scale[ty * 4 + r]);
@@ -185,14 +216,60 @@ __global__ void __launch_bounds__(256) gemm_nn_kernel(const float* __restrict__ 
     }
 }
 
+// sums the split partials in a fixed order (double) and applies the epilogue
+__global__ void gemm_finalize_kernel(const double* __restrict__ partial, int splits, int N, int M,
+                                     float* __restrict__ C, long long ldc, float alpha, float beta, const GemmEpilogue ep)
+{
+    const int i = blockIdx.x * blockDim.y + threadIdx.y;
+    if (i >= N) return;
+    float inv_n = 1.0f;
+    if (ep.mode == 1 && ep.eyes.kind == 1) {
+        const double ied = sd_device_ied(ep.x + (long long)i * M, M / 2, ep.eyes);
+        inv_n = __fdiv_rn(1.0f, (float)__ddiv_rn(1.0, ied));
+    }
+    for (int j = threadIdx.x; j < M; j += blockDim.x) {
+        double s = 0.0;
+        for (int z = 0; z < splits; ++z) s += partial[((long long)z * N + i) * M + j];
+        const float accf = (float)s;
+        if (ep.mode == 1) {
+            ep.x_next[(long long)i * M + j] = __fsub_rn(ep.x[(long long)i * M + j], __fmul_rn(accf, inv_n));
+        } else {
+            float* p = C + (long long)i * ldc + j;
+            *p = (beta == 0.f) ? alpha * accf : fmaf(alpha, accf, beta * (*p));
+        }
+    }
+}
+
 int launch_gemm_nn(sd_ctx* ctx, const float* A, int64_t lda, int N, int D, const float* B, int64_t ldb, int M,
                    float* C, int64_t ldc, float alpha, float beta, const GemmEpilogue& ep)
 {
     if (N <= 0 || M <= 0) return SD_OK;
-    dim3 grid(sd_div_up(M, GT), sd_div_up(N, GT));
+    dim3 grid(sd_div_up(M, GT), sd_div_up(N, GT), 1);
     SD_REQUIRE(ctx, grid.y <= 65535, "too many rows for one GEMM launch");
-    gemm_nn_kernel<<<grid, 256, 0, ctx->stream>>>(A, lda, N, D, B, ldb, M, C, ldc, alpha, beta, ep);
-    SD_LAUNCH_CHECK(ctx, "gemm_nn_kernel");
+    // skinny outputs (M = 2L columns) leave most SMs idle: split the contraction dimension
+    const long long tiles = (long long)grid.x * grid.y;
+    int splits = 1;
+    if (tiles < 3LL * ctx->sm_count && D >= 1024) {
+        splits = (int)((4LL * ctx->sm_count + tiles - 1) / tiles);
+        const int maxs = D / 512;
+        if (splits > maxs) splits = maxs;
+        if (splits > 32) splits = 32;
+        if (splits < 1) splits = 1;
+    }
+    if (splits == 1) {
+        gemm_nn_kernel<<<grid, 256, 0, ctx->stream>>>(A, lda, N, D, B, ldb, M, C, ldc, alpha, beta, ep, nullptr, D);
+        SD_LAUNCH_CHECK(ctx, "gemm_nn_kernel");
+        return SD_OK;
+    }
+    const int kps = sd_div_up(sd_div_up(D, splits), GK) * GK;
+    grid.z = sd_div_up(D, kps);
+    double* partial = (double*)sd_workspace(ctx, SD_WS_GEMM_PARTIAL, (size_t)grid.z * N * M * sizeof(double));
+    if (!partial) return SD_ERR_CUDA;
+    gemm_nn_kernel<<<grid, 256, 0, ctx->stream>>>(A, lda, N, D, B, ldb, M, C, ldc, alpha, beta, ep, partial, kps);
+    SD_LAUNCH_CHECK(ctx, "gemm_nn_kernel(split)");
+    dim3 fblock(32, 8);
+    gemm_finalize_kernel<<<sd_div_up(N, 8), fblock, 0, ctx->stream>>>(partial, (int)grid.z, N, M, C, ldc, alpha, beta, ep);
+    SD_LAUNCH_CHECK(ctx, "gemm_finalize_kernel");
     return SD_OK;
 }
 
@@ -728,7 +805,7 @@ int sd_cascade_update(sd_ctx* ctx, const float* d_A, int64_t lda, int N, int D, 
     ep.x_next = d_x_next;
     int rc = sd_eyes_to_dev(ctx, norm, P / 2, &ep.eyes);
     if (rc) return rc;
-    SD_REQUIRE(ctx, P <= GT || d_x != d_x_next, "in-place update needs P <= 64");
+    SD_REQUIRE(ctx, d_x != d_x_next, "x_next must not alias x");
     return launch_gemm_nn(ctx, d_A, lda, N, D, d_X, P, P, nullptr, 0, 1.0f, 0.0f, ep);
 }
 

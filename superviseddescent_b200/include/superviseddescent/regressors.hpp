@@ -68,6 +68,8 @@ public:
         sd_b200::check(ctx, sd_learn(ctx, ext.as<float>(), ld, ext.as<float>() + D, ld, N, D, M, &reg, dX.as<float>(), &last_lambda), "sd_learn");
         return sd_b200::download(dX.as<float>(), D, M, M);
     }
+    // called by the optimiser's device route after a level was learned (VerbosePartialPivLUSolver prints here)
+    void report() const {}
     float last_lambda = 0.0f;
 };
 
@@ -122,6 +124,7 @@ public:
         return dx.template as<float>();
     }
     void set_x(cv::Mat new_x) { x = new_x; dirty = true; }
+    void report_solver() { solver.report(); }
     const Regulariser& get_regulariser() const { return regulariser; }
 
 private:

@@ -207,6 +207,7 @@ private:
             const sd_regulariser reg = regressors[level].get_regulariser().c();
             sd_b200::check(ctx, sd_learn(ctx, A.as<float>(), ld, B, ld, n, D, Pd, &reg, X.as<float>(), nullptr), "sd_learn");
             regressors[level].set_x(sd_b200::download(X.as<float>(), D, Pd, Pd));
+            regressors[level].report_solver();
             sd_b200::check(ctx, sd_cascade_update(ctx, A.as<float>(), ld, n, D, X.as<float>(), Pd, d_cur.as<float>(), &norm, d_next.as<float>()), "sd_cascade_update");   // 4) :209-215
             std::swap(d_cur, d_next);
             if (want_callback) cb(sd_b200::download(d_cur.as<float>(), n, Pd, Pd));                          // 5) :217
