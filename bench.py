@@ -180,6 +180,86 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+TRAIN_CFG = {"n": 10000, "size": 128, "num_bins": 9, "cells": 5, "cell_sizes": [11, 10, 8, 6, 6], "rel": [1.0, 0.7, 0.4, 0.25, 0.25],
+             "lambda_factor": 1.5}
+
+
+def synth_train_set(sd, model, n_local, seed, dev):
+    """128x128 8UC1 crops, box = crop shrunk by 10 %, ground truth = mean shape in a box
+    jittered N(0, 0.04) in translation and N(1, 0.04) in scale (rcr-train.cpp:387-395), x0 = mean in the box."""
+    import torch
+    import torch.nn.functional as F
+    size = TRAIN_CFG["size"]
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    sigma, r = 3.0, 9
+    k = torch.exp(-0.5 * (torch.arange(-r, r + 1, device=dev, dtype=torch.float32) / sigma) ** 2)
+    k = k / k.sum()
+    imgs = torch.empty((n_local, size, size), dtype=torch.uint8, device=dev)
+    for i0 in range(0, n_local, 1024):
+        n = min(1024, n_local - i0)
+        x = torch.rand((n, 1, size + 2 * r, size + 2 * r), generator=g, device=dev)
+        x = F.conv2d(F.conv2d(x, k.view(1, 1, -1, 1)), k.view(1, 1, 1, -1))
+        lo, hi = x.amin(dim=(2, 3), keepdim=True), x.amax(dim=(2, 3), keepdim=True)
+        imgs[i0:i0 + n] = ((x - lo) / (hi - lo) * 255.0).round().clamp(0, 255).to(torch.uint8)[:, 0]
+    rng = np.random.Generator(np.random.PCG64(seed))
+    mean = model.get_mean()
+    m = int(round(size * 0.05))
+    box = (m, m, size - 2 * m, size - 2 * m)
+    x0 = np.tile(sd.align_mean(mean, box), (n_local, 1)).astype(np.float32)
+    x_gt = np.stack([sd.align_mean(mean, box, 1.0 + rng.normal(0, 0.04), 1.0 + rng.normal(0, 0.04), rng.normal(0, 0.04), rng.normal(0, 0.04))
+                     for _ in range(n_local)]).astype(np.float32)
+    return imgs, x0, x_gt
+
+
+def run_train(sd, ctx, model, world, rank, dev, barrier, max_over_ranks, group):
+    """Regressor-train seconds (all S levels: HOG + targets + Gram + all-reduce + solve + update), strong scaling."""
+    import torch
+    from superviseddescent_b200 import parallel
+    cfg = TRAIN_CFG
+    b, e = parallel.shard_range(cfg["n"], world, rank)
+    imgs, x0, x_gt = synth_train_set(sd, model, e - b, 2024 + rank, dev)
+    ids = model.landmark_ids
+    norm_c = sd.NormalisationC()
+    import ctypes as C
+    from superviseddescent_b200 import _capi
+    _capi.lib().sd_model_normalisation(model._m, C.byref(norm_c))
+    right = [ids[norm_c.right_idx[i]] for i in range(norm_c.n_right)]
+    left = [ids[norm_c.left_idx[i]] for i in range(norm_c.n_left)]
+    hps = [sd.HoGParam(1, cfg["cells"], cs, cfg["num_bins"], rel) for cs, rel in zip(cfg["cell_sizes"], cfg["rel"])]
+    ht = sd.HogTransform(imgs, hps, ids, right, left, ctx)
+    D = ht.feature_length(0)
+
+    def one_run():
+        regs = [sd.LinearRegressor(sd.Regulariser(sd.RegularisationType.MatrixNorm, cfg["lambda_factor"], False), ctx) for _ in hps]
+        sdo = sd.SupervisedDescentOptimiser(regs, sd.InterEyeDistanceNormalisation(ids, right, left), ctx)
+        xf = sdo.train(x_gt, x0, None, ht, None, group)
+        return sdo, xf
+
+    one_run()                                  # warm-up (workspaces, tensor maps, NCCL channels)
+    barrier()
+    l0 = ctx.launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    sdo, xf = one_run()
+    e1.record()
+    barrier()
+    secs = max_over_ranks(e0.elapsed_time(e1)) * 1e-3
+    res0 = float(torch.linalg.norm(torch.from_numpy(x0).to(dev) - torch.from_numpy(x_gt).to(dev)) / torch.linalg.norm(torch.from_numpy(x_gt).to(dev)))
+    res1 = float(torch.linalg.norm(xf - torch.from_numpy(x_gt).to(dev)) / torch.linalg.norm(torch.from_numpy(x_gt).to(dev)))
+    S = len(hps)
+    gram_flops = S * (cfg["n"] * D * (D + 1) + 2.0 * cfg["n"] * D * 44)
+    chol_flops = S * (D ** 3 / 3.0 + 2.0 * D * D * 44)
+    return {"metric": "regressor train sec (RCR, all cascade levels)", "value": secs, "unit": "s", "higher_is_better": False, "scaling": "strong",
+            "config": {"workload": "configs[3]: RCR training, 10k synthetic 128x128 crops, 22 landmarks, 31-bin HOG (K=9), 5 cascade levels",
+                       "samples_global": cfg["n"], "samples_this_rank": e - b, "feature_dim": D, "levels": S,
+                       "parallelism": f"samples sharded over {world} GPU(s), one all-reduce of [AtA|Atb] ({D * (D + 44) * 4 / 1e9:.2f} GB) per level, replicated solve"},
+            "gpu_launches": int(ctx.launches() - l0),
+            "algorithmic_tflop": {"gram_syrk": gram_flops / 1e12, "cholesky_and_solve": chol_flops / 1e12},
+            "train_residual": {"before": res0, "after": res1},
+            "last_level_solver_ms": ctx.solver_timings()}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -188,8 +268,10 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
     from superviseddescent_b200 import api as sd
     ctx = sd.Context(local)
     model = sd.load_detection_model(MODEL, ctx)
@@ -290,6 +372,12 @@ def run_ours(args):
                 "note": "HOG is fp32-ALU/shared-memory bound (SURVEY 8d: ~40 flop/B); fp32 figure reported beside the HBM one",
                 "achieved_fp32_tflops": alg_flops / (hog_ms * 1e-3) / 1e12}
 
+    train = None
+    if not args.no_train:
+        try:
+            train = run_train(sd, ctx, model, world, rank, dev, barrier, max_over_ranks, group)
+        except Exception as ex:   # the headline line must still be printed
+            train = {"error": repr(ex)[:300]}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -307,6 +395,8 @@ def run_ours(args):
         "clocks": clocks,
         "roofline": roofline,
     }
+    if train is not None:
+        line["train"] = train
     if world == 1 and not args.no_cpu:
         cores = host_cores()
         n = max(256, cores * 32)
@@ -328,6 +418,7 @@ def main():
     ap.add_argument("--batch", type=int, default=4096, help="frames per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-train", action="store_true", help="skip the extra regressor-train measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

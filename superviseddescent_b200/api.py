@@ -335,18 +335,15 @@ class SupervisedDescentOptimiser:
     def train(self, parameters, initialisations, templates, projection, on_training_epoch_callback=None, group=None):
         """superviseddescent.hpp:165-219.  `group`: optional torch.distributed process group -- each rank
         passes its own shard of rows; one all-reduce of [AtA | Atb] per level."""
-        import torch.distributed as dist
+        from . import parallel
         ctx = self._ctx()
         lib = _capi.lib()
         x_gt = _dev(parameters, ctx)
         cur = _dev(initialisations, ctx).clone()
         n, P = cur.shape
         tmpl = _dev(templates, ctx) if templates is not None and np.size(templates) > 0 else None
-        n_global = n
-        if group is not None:
-            t = torch.tensor([n], dtype=torch.int64, device=cur.device)
-            dist.all_reduce(t, group=group)
-            n_global = int(t.item())
+        distributed = group is not None
+        n_global = parallel.global_count(n, group, cur.device) if distributed else n
         for level, reg in enumerate(self.regressors):
             norm = self.normalisation_strategy.c(P // 2)
             A, D = self._project(projection, cur, level, extra=P)             # 1) features (:173-189)
@@ -357,8 +354,8 @@ class SupervisedDescentOptimiser:
             ldg = (D + P + 3) // 4 * 4                                       # 3) learn (:207)
             G = torch.empty((D, ldg), dtype=torch.float32, device=cur.device)
             _check(ctx.h, lib.sd_gram(ctx.h, ptr(A), C.c_int64(A.stride(0)), ptr(Bv), C.c_int64(A.stride(0)), n, D, P, ptr(G), C.c_int64(ldg)))
-            if group is not None:
-                dist.all_reduce(G, group=group)                              #    the one collective per level
+            if distributed:
+                parallel.allreduce_gram(G, group)                            #    the one collective per level
             X = torch.empty((D, P), dtype=torch.float32, device=cur.device)
             lam = C.c_float(0)
             rc_ = reg.regulariser.c()
@@ -368,7 +365,7 @@ class SupervisedDescentOptimiser:
             _check(ctx.h, lib.sd_cascade_update(ctx.h, ptr(A), C.c_int64(A.stride(0)), n, D, ptr(X), P, ptr(cur), C.byref(norm), ptr(nxt)))
             cur = nxt
             if on_training_epoch_callback is not None:                       # 5) callback (:217)
-                on_training_epoch_callback(cur)
+                on_training_epoch_callback(parallel.gather_rows(cur, group) if distributed else cur)
         return cur
 
     def test(self, initialisations, templates, projection, on_regressor_iteration_callback=None):

@@ -454,17 +454,18 @@ __global__ void __launch_bounds__(512) potrf_block_kernel(float* __restrict__ G,
         sU[i * ld + j] = (j >= i) ? G[(long long)i * ldg + j] : 0.f;
     }
     __syncthreads();
+    const int tx = tid & 31, ty = tid >> 5, nty = nthr >> 5;     // lanes along j, warps along i
     for (int k = 0; k < nb; ++k) {
         const float akk = sU[k * ld + k];
         if (!(akk > 0.f) && tid == 0) atomicOr(status, 8);   // not positive definite
         const float d = sqrtf(fabsf(akk) > 0.f ? fabsf(akk) : 1.f);
+        const float inv_d = 1.0f / d;
         __syncthreads();
-        for (int j = k + tid; j < nb; j += nthr) sU[k * ld + j] = (j == k) ? d : sU[k * ld + j] / d;
+        for (int j = k + tid; j < nb; j += nthr) sU[k * ld + j] = (j == k) ? d : sU[k * ld + j] * inv_d;
         __syncthreads();
-        const int rem = nb - k - 1;
-        for (int idx = tid; idx < rem * rem; idx += nthr) {
-            const int i = k + 1 + idx / rem, j = k + 1 + idx % rem;
-            if (j >= i) sU[i * ld + j] = fmaf(-sU[k * ld + i], sU[k * ld + j], sU[i * ld + j]);
+        for (int i = k + 1 + ty; i < nb; i += nty) {
+            const float uki = sU[k * ld + i];
+            for (int j = i + tx; j < nb; j += 32) sU[i * ld + j] = fmaf(-uki, sU[k * ld + j], sU[i * ld + j]);
         }
         __syncthreads();
     }
@@ -490,39 +491,65 @@ __global__ void __launch_bounds__(128) trsm_panel_kernel(const float* __restrict
     }
     __syncthreads();
     const int c = blockIdx.x * blockDim.x + tid;
-    if (c >= cols) return;
+    const bool live = c < cols;
+    for (int r = 0; r < nb; ++r) sY[r * 128 + tid] = live ? P[(long long)r * ldp + c] : 0.f;   // coalesced, independent loads
     for (int r = 0; r < nb; ++r) {
-        float v = P[(long long)r * ldp + c];
-        float s0 = 0.f, s1 = 0.f;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
         int p = 0;
-        for (; p + 1 < r; p += 2) {
+        for (; p + 3 < r; p += 4) {
             s0 = fmaf(sU[p * ld + r], sY[p * 128 + tid], s0);
             s1 = fmaf(sU[(p + 1) * ld + r], sY[(p + 1) * 128 + tid], s1);
+            s2 = fmaf(sU[(p + 2) * ld + r], sY[(p + 2) * 128 + tid], s2);
+            s3 = fmaf(sU[(p + 3) * ld + r], sY[(p + 3) * 128 + tid], s3);
         }
-        if (p < r) s0 = fmaf(sU[p * ld + r], sY[p * 128 + tid], s0);
-        v = (v - (s0 + s1)) / sU[r * ld + r];
-        sY[r * 128 + tid] = v;
-        P[(long long)r * ldp + c] = v;
+        for (; p < r; ++p) s0 = fmaf(sU[p * ld + r], sY[p * 128 + tid], s0);
+        sY[r * 128 + tid] = (sY[r * 128 + tid] - ((s0 + s1) + (s2 + s3))) / sU[r * ld + r];
     }
+    if (live)
+        for (int r = 0; r < nb; ++r) P[(long long)r * ldp + c] = sY[r * 128 + tid];
 }
 
-// X_j <- U_jj^-1 * Y_j : back substitution of one diagonal block, one thread per right-hand side
+// X_j <- U_jj^-1 * Y_j : back substitution of one diagonal block in shared memory.  Four lanes share one
+// right-hand side column (they split the dot product and combine with two shuffles); the block's U and Y
+// live in shared memory, so the 128 dependent steps cost shared-memory latency, not L2 latency.
 __global__ void __launch_bounds__(256) trsv_block_kernel(const float* __restrict__ U, long long ldu, int nb,
                                                          float* __restrict__ Y, long long ldy, int M)
 {
     extern __shared__ float sm[];
-    float* sU = sm;                    // nb x (nb+1)
+    float* sU = sm;                       // nb x (nb+1)
     const int ld = nb + 1;
+    float* sY = sm + nb * ld;             // nb x 64 (one 64-column chunk of right-hand sides at a time)
     for (int idx = threadIdx.x; idx < nb * nb; idx += blockDim.x) {
         const int i = idx / nb, j = idx - i * nb;
         sU[i * ld + j] = (j >= i) ? U[(long long)i * ldu + j] : 0.f;
     }
-    __syncthreads();
-    for (int c = threadIdx.x; c < M; c += blockDim.x) {
+    const int cl = threadIdx.x >> 2, part = threadIdx.x & 3;      // 64 columns x 4 lanes
+    for (int c0 = 0; c0 < M; c0 += 64) {
+        const int mc = min(64, M - c0);
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < nb * 64; idx += blockDim.x) {
+            const int i = idx >> 6, c = idx & 63;
+            sY[idx] = (c < mc) ? Y[(long long)i * ldy + c0 + c] : 0.f;
+        }
+        __syncthreads();
         for (int i = nb - 1; i >= 0; --i) {
-            float r = Y[(long long)i * ldy + c];
-            for (int k = i + 1; k < nb; ++k) r = fmaf(-sU[i * ld + k], Y[(long long)k * ldy + c], r);
-            Y[(long long)i * ldy + c] = r / sU[i * ld + i];
+            float s = 0.f, s2 = 0.f;
+            int k = i + 1 + part;
+            for (; k + 4 < nb; k += 8) {
+                s = fmaf(sU[i * ld + k], sY[k * 64 + cl], s);
+                s2 = fmaf(sU[i * ld + k + 4], sY[(k + 4) * 64 + cl], s2);
+            }
+            if (k < nb) s = fmaf(sU[i * ld + k], sY[k * 64 + cl], s);
+            s += s2;
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            if (part == 0) sY[i * 64 + cl] = (sY[i * 64 + cl] - s) / sU[i * ld + i];
+            __syncwarp();
+        }
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < nb * 64; idx += blockDim.x) {
+            const int i = idx >> 6, c = idx & 63;
+            if (c < mc) Y[(long long)i * ldy + c0 + c] = sY[idx];
         }
     }
 }
@@ -535,7 +562,8 @@ int cholesky_solve(sd_ctx* ctx, float* G, int64_t ldg, int D, int M, float* X)
     const size_t smem_trsm = smem_potrf + (size_t)kCholNb * 128 * 4;
     SD_CUDA(ctx, cudaFuncSetAttribute(potrf_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_potrf));
     SD_CUDA(ctx, cudaFuncSetAttribute(trsm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_trsm));
-    SD_CUDA(ctx, cudaFuncSetAttribute(trsv_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_potrf));
+    const size_t smem_trsv = smem_potrf + (size_t)kCholNb * 64 * 4;
+    SD_CUDA(ctx, cudaFuncSetAttribute(trsv_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_trsv));
     // ---- factorisation, carrying the right-hand side columns along (Y = U^-T R) ----
     for (int j = 0; j < D; j += kCholNb) {
         const int nb = (D - j < kCholNb) ? D - j : kCholNb;
@@ -564,7 +592,7 @@ int cholesky_solve(sd_ctx* ctx, float* G, int64_t ldg, int D, int M, float* X)
         const int j = b * kCholNb;
         const int nb = (D - j < kCholNb) ? D - j : kCholNb;
         float* Yj = G + (int64_t)j * ldg + D;
-        trsv_block_kernel<<<1, 256, (size_t)nb * (nb + 1) * 4, ctx->stream>>>(G + (int64_t)j * ldg + j, ldg, nb, Yj, ldg, M);
+        trsv_block_kernel<<<1, 256, (size_t)nb * (nb + 1) * 4 + (size_t)nb * 64 * 4, ctx->stream>>>(G + (int64_t)j * ldg + j, ldg, nb, Yj, ldg, M);
         SD_LAUNCH_CHECK(ctx, "trsv_block_kernel");
         if (j > 0) {
             // Y[0:j] -= U[0:j, j:j+nb] * X_j
