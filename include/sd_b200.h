@@ -77,13 +77,26 @@ typedef struct {
     int32_t left_idx[4];
 } sd_normalisation;
 
+/* Region of interest of one frame that is resident on the device (see sd_image_batch.d_roi). */
+typedef struct {
+    int32_t x, y, w, h;          /* in frame coordinates */
+    int32_t row_stride;          /* bytes between ROI rows in the packed buffer (multiple of 4) */
+    int32_t reserved;
+    int64_t offset;              /* byte offset of the ROI's first pixel from d_data */
+} sd_roi;
+
 /* A batch of equally sized 8UC1 images resident on the device. */
 typedef struct {
     const uint8_t* d_data;
-    int32_t width, height;
+    int32_t width, height;       /* frame size: defines where the zero padding of a patch starts */
     int32_t row_stride;          /* bytes */
     int64_t image_stride;        /* bytes between consecutive images */
     int32_t count;
+    /* Optional (NULL = whole frames are resident): only a region of interest of every frame was uploaded.
+     * d_roi[i] locates it inside d_data; a patch that needs frame pixels outside its ROI sets d_roi_miss[i]
+     * (sd_detect_batch_host then repeats that face from the full frame). */
+    const sd_roi* d_roi;
+    uint8_t* d_roi_miss;
 } sd_image_batch;
 
 /* ---- context --------------------------------------------------------------------------- */
@@ -98,6 +111,8 @@ SD_API int sd_sync(sd_ctx* ctx);
 SD_API const char* sd_version(void);
 /* number of kernels of THIS library launched on ctx since creation (bench.py's gpu_launches) */
 SD_API int64_t sd_launch_count(const sd_ctx* ctx);
+/* faces that sd_detect_batch_host had to repeat from their full frame (a patch left the uploaded ROI) */
+SD_API int64_t sd_roi_fallback_count(const sd_ctx* ctx);
 
 /* device / pinned-host memory for hosts that do not bring their own allocator */
 SD_API int sd_malloc(sd_ctx* ctx, size_t bytes, void** d_ptr);

@@ -35,12 +35,12 @@ class NormalisationC(C.Structure):
 
 class ImageBatchC(C.Structure):
     _fields_ = [("d_data", C.c_void_p), ("width", C.c_int32), ("height", C.c_int32), ("row_stride", C.c_int32),
-                ("image_stride", C.c_int64), ("count", C.c_int32)]
+                ("image_stride", C.c_int64), ("count", C.c_int32), ("d_roi", C.c_void_p), ("d_roi_miss", C.c_void_p)]
 
 
 # every symbol declared in include/sd_b200.h (tests/test_abi.py checks the list against the header)
 EXPORTS = [
-    "sd_ctx_create", "sd_ctx_destroy", "sd_last_error", "sd_sync", "sd_version", "sd_launch_count",
+    "sd_ctx_create", "sd_ctx_destroy", "sd_last_error", "sd_sync", "sd_version", "sd_launch_count", "sd_roi_fallback_count",
     "sd_malloc", "sd_free", "sd_host_alloc", "sd_host_free", "sd_memcpy_h2d", "sd_memcpy_d2h", "sd_memset",
     "sd_hog_feature_length", "sd_hog_batch", "sd_hog_debug",
     "sd_learn", "sd_gram", "sd_solve_gram", "sd_predict", "sd_test_residual", "sd_solver_timings", "sd_set_gram_mode",
@@ -65,6 +65,8 @@ def lib():
         l.sd_last_error.restype = C.c_char_p
         l.sd_version.restype = C.c_char_p
         l.sd_launch_count.restype = C.c_int64
+        l.sd_roi_fallback_count.restype = C.c_int64
+        l.sd_roi_fallback_count.argtypes = [C.c_void_p]
         l.sd_model_landmark_id.restype = C.c_char_p
         l.sd_last_error.argtypes = [C.c_void_p]
         l.sd_launch_count.argtypes = [C.c_void_p]

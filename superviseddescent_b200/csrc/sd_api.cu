@@ -1,6 +1,7 @@
 // Context, error handling and memory helpers of libsd_b200.so (C ABI: include/sd_b200.h).
 #include "sd_internal.cuh"
 
+#include <cstdlib>
 #include <cstring>
 
 int sd_fail(sd_ctx* ctx, int code, const char* fmt, ...)
@@ -96,7 +97,11 @@ int sd_ctx_create(int device, void* stream, sd_ctx** out)
         ctx->stream = (cudaStream_t)stream;   // NULL = the CUDA default stream (what torch calls its default stream)
         ctx->own_stream = false;
     }
-    bool ok = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+    // the staging stream outranks the compute stream: its (short) gather / copy work must slip in between
+    // the waves of the HOG kernels instead of queueing behind them
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    bool ok = cudaStreamCreateWithPriority(&ctx->copy_stream, cudaStreamNonBlocking, prio_hi) == cudaSuccess;
     for (int i = 0; i < 6 && ok; ++i) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
     for (int i = 0; i < 2 && ok; ++i) {
         ok = cudaEventCreateWithFlags(&ctx->stage_ev[i], cudaEventDisableTiming) == cudaSuccess &&
@@ -105,6 +110,8 @@ int sd_ctx_create(int device, void* stream, sd_ctx** out)
     ok = ok && cudaMallocHost(&ctx->h_scratch, 4096) == cudaSuccess && cudaMalloc(&ctx->d_scratch, 4096) == cudaSuccess &&
          cudaMemset(ctx->d_scratch, 0, 4096) == cudaSuccess;
     if (!ok) { sd_ctx_destroy(ctx); return SD_ERR_CUDA; }
+    { const char* e = getenv("SD_B200_NO_ROI"); ctx->disable_roi = e && e[0] == '1'; }
+    { const char* e = getenv("SD_B200_ROI_MODE"); ctx->roi_mode = (e && e[0] == '1') ? 1 : 0; }
     *out = ctx;
     return SD_OK;
 }
@@ -140,6 +147,7 @@ int sd_sync(sd_ctx* ctx)
 }
 
 int64_t sd_launch_count(const sd_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int64_t sd_roi_fallback_count(const sd_ctx* ctx) { return ctx ? ctx->roi_fallbacks : 0; }
 
 int sd_malloc(sd_ctx* ctx, size_t bytes, void** d_ptr)
 {

@@ -32,6 +32,8 @@ struct HogArgs {
     long long image_stride;
     int image_count;
     const int* image_index;
+    const sd_roi* roi;          // optional: only a region of every frame is resident
+    uint8_t* roi_miss;
     const float* x;
     long long ldx;
     int N, L;
@@ -135,12 +137,17 @@ __device__ __forceinline__ int clip_index(int x, int a, int b) { return x >= a ?
 
 __device__ __forceinline__ short sat_short(int v) { return (short)(v > 32767 ? 32767 : (v < -32768 ? -32768 : v)); }
 
-template <int KT>
+// KT / NCT / CST > 0 bake the bin count, cells per side and cell size into the kernel (the schedules the
+// reference ships: 5x5 cells of 11/10/8/6 px, K = 4 or 9), which lets the compiler strength-reduce every
+// index computation; 0 = taken from the arguments at run time (any other configuration).
+template <int KT, int NCT, int CST>
 __global__ void __launch_bounds__(kHogThreads) hog_patch_kernel(const HogArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const int K = KT > 0 ? KT : a.K;
-    const int fs = a.fs, nc = a.nc, cs = a.cs, dd = a.dd;
+    const int nc = NCT > 0 ? NCT : a.nc, cs = CST > 0 ? CST : a.cs;
+    const int fs = (NCT > 0 && CST > 0) ? NCT * CST : a.fs;
+    const int dd = a.dd;
     const int cells = nc * nc;
     const HogSmem lay = hog_smem_layout(fs, nc, K, dd);
     uint8_t* s_patch = smem + lay.patch;
@@ -181,7 +188,14 @@ __global__ void __launch_bounds__(kHogThreads) hog_patch_kernel(const HogArgs a)
         img_idx = 0;
         if (tid == 0 && a.status) atomicOr(a.status, 2);
     }
+    // resident region of this frame: the whole frame, or the ROI that sd_detect_batch_host uploaded
+    int rx = 0, ry = 0, rw = a.width, rh = a.height, rs = a.row_stride;
     const uint8_t* __restrict__ img = a.images + (long long)img_idx * a.image_stride;
+    if (a.roi) {
+        const sd_roi r = a.roi[img_idx];
+        rx = r.x; ry = r.y; rw = r.w; rh = r.h; rs = r.row_stride;
+        img = a.images + r.offset;
+    }
     if (tid == 0 && a.geometry) {
         a.geometry[patch_id * 3 + 0] = cx;
         a.geometry[patch_id * 3 + 1] = cy;
@@ -222,40 +236,90 @@ __global__ void __launch_bounds__(kHogThreads) hog_patch_kernel(const HogArgs a)
     for (int i = tid; i < kHogWarps * 2 * K * 32; i += kHogThreads) s_priv[i] = 0.f;
     __syncthreads();
 
-    // ---- S1: zero-padded crop + fixed-point bilinear resize straight from the frame; one output row
-    //      per warp pass, lanes along x (no integer division, row terms are warp-uniform) --------------
+    // ---- S1: zero-padded crop + fixed-point bilinear resize.  The P x P source window is first staged in
+    //      shared memory (zero padding materialised, aligned 32-bit loads when the window is resident), then
+    //      resampled from there: one output row per warp pass, lanes along x, no predicates, no division.
     {
         const int x0 = cx - half, y0 = cy - half;
-        const int W = a.width, H = a.height, stride = a.row_stride;
-        const bool inside = x0 >= 0 && y0 >= 0 && x0 + P <= W && y0 + P <= H;
-        for (int dy = warp; dy < fs; dy += kHogWarps) {
-            const short2 yb = s_yb[dy];
-            const int iy0 = y0 + s_yofs0[dy], iy1 = y0 + s_yofs1[dy];
-            const bool ry0 = (unsigned)iy0 < (unsigned)H, ry1 = (unsigned)iy1 < (unsigned)H;
-            const uint8_t* r0 = img + (long long)iy0 * stride + x0;
-            const uint8_t* r1 = img + (long long)iy1 * stride + x0;
-            for (int dx = lane; dx < fs; dx += 32) {
-                const int sx = s_xofs[dx];
-                const short2 xa = s_xa[dx];
-                int p00, p01, p10, p11;
-                if (inside) {
-                    const int sx1 = min(sx + 1, P - 1);              // clamped tap has zero weight
-                    p00 = __ldg(r0 + sx); p01 = __ldg(r0 + sx1);
-                    p10 = __ldg(r1 + sx); p11 = __ldg(r1 + sx1);
-                } else {
-                    const int ix0 = x0 + sx;
-                    const bool c0 = (unsigned)ix0 < (unsigned)W, c1 = (unsigned)(ix0 + 1) < (unsigned)W && xa.y != 0;
-                    p00 = (ry0 && c0) ? __ldg(r0 + sx) : 0;
-                    p01 = (ry0 && c1) ? __ldg(r0 + sx + 1) : 0;
-                    p10 = (ry1 && c0) ? __ldg(r1 + sx) : 0;
-                    p11 = (ry1 && c1) ? __ldg(r1 + sx + 1) : 0;
+        const int W = a.width, H = a.height;
+        const bool resident = x0 >= rx && y0 >= ry && x0 + P <= rx + rw && y0 + P <= ry + rh;
+        const bool words = resident && ((reinterpret_cast<uintptr_t>(img) | (uintptr_t)rs) & 3) == 0;
+        const int shiftb = words ? ((x0 - rx) & 3) : 0;          // column c of the window sits at byte shiftb + c
+        const int pitch = (P + 3 + 3) & ~3;
+        uint8_t* s_stage = smem + lay.bin;                         // [bin | r1] are dead until S2
+        const bool staged = pitch * P <= lay.xofs - lay.bin;
+        bool miss = false;
+        if (staged) {
+            if (words) {
+                const int nwords = (shiftb + P + 3) >> 2;
+                const uint8_t* wrow = img + (long long)(y0 - ry) * rs + (x0 - rx - shiftb);
+                for (int r = warp; r < P; r += kHogWarps) {
+                    const uint32_t* src = reinterpret_cast<const uint32_t*>(wrow + (long long)r * rs);
+                    uint32_t* dst = reinterpret_cast<uint32_t*>(s_stage + r * pitch);
+                    for (int w = lane; w < nwords; w += 32) dst[w] = __ldg(src + w);
                 }
-                const int t0 = p00 * xa.x + p01 * xa.y;
-                const int t1 = p10 * xa.x + p11 * xa.y;
-                const int v = ((((int)yb.x * (t0 >> 4)) >> 16) + (((int)yb.y * (t1 >> 4)) >> 16) + 2) >> 2;
-                s_patch[dy * fs + dx] = (uint8_t)v;
-                if (a.patches) a.patches[patch_id * fs * fs + dy * fs + dx] = (uint8_t)v;
+            } else {
+                for (int r = warp; r < P; r += kHogWarps) {
+                    const int iy = y0 + r;
+                    const bool rowin = (unsigned)iy < (unsigned)H;
+                    const bool rowres = iy >= ry && iy < ry + rh;
+                    for (int c = lane; c < P; c += 32) {
+                        const int ix = x0 + c;
+                        int v = 0;
+                        if (rowin && (unsigned)ix < (unsigned)W) {
+                            if (rowres && ix >= rx && ix < rx + rw) v = __ldg(img + (long long)(iy - ry) * rs + (ix - rx));
+                            else miss = true;                      // a frame pixel that was not uploaded
+                        }
+                        s_stage[r * pitch + c] = (uint8_t)v;
+                    }
+                }
             }
+            __syncthreads();
+            for (int dy = warp; dy < fs; dy += kHogWarps) {
+                const short2 yb = s_yb[dy];
+                const uint8_t* r0 = s_stage + s_yofs0[dy] * pitch + shiftb;
+                const uint8_t* r1 = s_stage + s_yofs1[dy] * pitch + shiftb;
+                for (int dx = lane; dx < fs; dx += 32) {
+                    const int sx = s_xofs[dx];
+                    const int sx1 = min(sx + 1, P - 1);            // clamped tap has zero weight
+                    const short2 xa = s_xa[dx];
+                    const int t0 = (int)r0[sx] * xa.x + (int)r0[sx1] * xa.y;
+                    const int t1 = (int)r1[sx] * xa.x + (int)r1[sx1] * xa.y;
+                    const int v = ((((int)yb.x * (t0 >> 4)) >> 16) + (((int)yb.y * (t1 >> 4)) >> 16) + 2) >> 2;
+                    s_patch[dy * fs + dx] = (uint8_t)v;            // s_patch precedes the staging area: no overlap
+                }
+            }
+        } else {
+            // window too large for the staging area: sample straight from global memory with full checks
+            for (int dy = warp; dy < fs; dy += kHogWarps) {
+                const short2 yb = s_yb[dy];
+                const int iy0 = y0 + s_yofs0[dy], iy1 = y0 + s_yofs1[dy];
+                for (int dx = lane; dx < fs; dx += 32) {
+                    const int sx = s_xofs[dx];
+                    const short2 xa = s_xa[dx];
+                    int p[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int ix = x0 + sx + (q & 1), iy = (q & 2) ? iy1 : iy0;
+                        int v = 0;
+                        if ((q & 1) && xa.y == 0) { p[q] = 0; continue; }
+                        if ((unsigned)ix < (unsigned)W && (unsigned)iy < (unsigned)H) {
+                            if (ix >= rx && ix < rx + rw && iy >= ry && iy < ry + rh) v = __ldg(img + (long long)(iy - ry) * rs + (ix - rx));
+                            else miss = true;
+                        }
+                        p[q] = v;
+                    }
+                    const int t0 = p[0] * xa.x + p[1] * xa.y;
+                    const int t1 = p[2] * xa.x + p[3] * xa.y;
+                    const int v = ((((int)yb.x * (t0 >> 4)) >> 16) + (((int)yb.y * (t1 >> 4)) >> 16) + 2) >> 2;
+                    s_patch[dy * fs + dx] = (uint8_t)v;
+                }
+            }
+        }
+        if (miss && a.roi_miss) a.roi_miss[img_idx] = 1;
+        if (a.patches) {
+            __syncthreads();
+            for (int i = tid; i < fs * fs; i += kHogThreads) a.patches[patch_id * fs * fs + i] = s_patch[i];
         }
     }
     // per cell-column pixel ranges that vote into it (same for rows: square patch, square cells)
@@ -489,6 +553,8 @@ int launch_hog(sd_ctx* ctx, const sd_image_batch* images, const int32_t* d_image
     a.width = images->width; a.height = images->height; a.row_stride = images->row_stride;
     a.image_stride = images->image_stride; a.image_count = images->count;
     a.image_index = d_image_index;
+    a.roi = images->d_roi;
+    a.roi_miss = images->d_roi_miss;
     if (!d_image_index) SD_REQUIRE(ctx, images->count >= N, "fewer images than samples and no image index");
     a.x = d_x; a.ldx = ldx; a.N = N; a.L = L;
     a.variant = p->variant; a.nc = p->num_cells; a.cs = p->cell_size; a.K = p->num_bins; a.fs = fs;
@@ -526,9 +592,15 @@ int launch_hog(sd_ctx* ctx, const sd_image_batch* images, const int32_t* d_image
     SD_REQUIRE(ctx, lay.total <= 227 * 1024, "HOG configuration needs more than 227 KB of shared memory");
     const long long blocks = (long long)N * L;
     SD_REQUIRE(ctx, blocks < 2147483647LL, "too many patches for one launch");
-    auto kern = hog_patch_kernel<0>;
-    if (a.K == 4) kern = hog_patch_kernel<4>;
-    else if (a.K == 9) kern = hog_patch_kernel<9>;
+    auto kern = hog_patch_kernel<0, 0, 0>;
+    if (a.K == 4) kern = hog_patch_kernel<4, 0, 0>;
+    else if (a.K == 9) kern = hog_patch_kernel<9, 0, 0>;
+    if (a.nc == 5 && (a.K == 4 || a.K == 9)) {
+#define SD_HOG_PICK(KK, CC) if (a.K == KK && a.cs == CC) kern = hog_patch_kernel<KK, 5, CC>;
+        SD_HOG_PICK(4, 11) SD_HOG_PICK(4, 10) SD_HOG_PICK(4, 8) SD_HOG_PICK(4, 6)
+        SD_HOG_PICK(9, 11) SD_HOG_PICK(9, 10) SD_HOG_PICK(9, 8) SD_HOG_PICK(9, 6)
+#undef SD_HOG_PICK
+    }
     SD_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, lay.total));
     kern<<<(unsigned)blocks, kHogThreads, lay.total, ctx->stream>>>(a);
     SD_LAUNCH_CHECK(ctx, "hog_patch_kernel");

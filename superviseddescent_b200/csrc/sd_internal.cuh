@@ -27,6 +27,9 @@ struct sd_ctx {
     int64_t launches = 0;
     int sm_count = 148;
     int gram_mode = 0;
+    bool disable_roi = false;      // sd_detect_batch_host: always upload whole frames
+    int roi_mode = 0;              // 0: zero-copy gather kernel, 1: batched strided DMA copies
+    int64_t roi_fallbacks = 0;     // faces repeated from the full frame because a patch left its ROI
     float timings[4] = {0, 0, 0, 0};
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     void* hog_lut[SD_MAX_BINS + 1] = {};   // per K: (gx,gy) -> orientation bin table (sd_hog.cu)

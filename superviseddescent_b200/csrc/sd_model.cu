@@ -6,6 +6,7 @@
 //   detect         model.hpp:132-157 -> superviseddescent.hpp:323-344 (predict: sequential over levels)
 #include "sd_internal.cuh"
 
+#include <cmath>
 #include <cstring>
 #include <fstream>
 #include <string>
@@ -163,6 +164,72 @@ int detect_device(sd_ctx* ctx, const sd_model* m, const sd_image_batch* images, 
     }
     SD_CUDA(ctx, cudaMemcpyAsync(d_landmarks, cur, (size_t)count * P * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
     return SD_OK;
+}
+
+
+// ---- region-of-interest upload (sd_detect_batch_host) ------------------------------------------------
+// The cascade only ever reads a neighbourhood of the face, so instead of copying whole 640x480 frames over
+// PCIe a small kernel pulls the ROI rows of every face straight out of the caller's PINNED host buffer
+// (zero-copy loads through the unified address space, 16-byte vectors) into a packed device buffer.  If a
+// patch later needs a frame pixel outside its ROI the HOG kernel raises d_roi_miss[face] and that face is
+// repeated from its full frame, so the result never depends on the ROI heuristic.
+__global__ void __launch_bounds__(256) roi_gather_kernel(const uint8_t* __restrict__ h_frames, long long frame_bytes, int row_stride,
+                                                         const sd_roi* __restrict__ roi, int first, int n, uint8_t* __restrict__ dst)
+{
+    for (int f = blockIdx.x; f < n; f += gridDim.x) {
+        const sd_roi r = roi[first + f];
+        const uint8_t* src = h_frames + (long long)(first + f) * frame_bytes + (long long)r.y * row_stride + r.x;
+        uint8_t* d = dst + r.offset;
+        const int vec_per_row = r.row_stride >> 4;
+        const int total = vec_per_row * r.h;
+        // four independent 16-byte reads in flight per thread before the stores: PCIe read latency is ~1 us
+        for (int i0 = threadIdx.x; i0 < total; i0 += 4 * blockDim.x) {
+            uint4 v[4];
+            int row[4], col[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * blockDim.x;
+                row[u] = i / vec_per_row;
+                col[u] = i - row[u] * vec_per_row;
+                if (i < total) v[u] = reinterpret_cast<const uint4*>(src + (long long)row[u] * row_stride)[col[u]];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (i0 + u * blockDim.x < total) reinterpret_cast<uint4*>(d + (long long)row[u] * r.row_stride)[col[u]] = v[u];
+        }
+    }
+}
+
+// conservative ROI of one face: landmark bounding box of the initialisation, grown by the largest patch
+// half size of the schedule plus a drift allowance, clipped to the frame, x aligned to 16 bytes
+sd_roi face_roi(const sd_model* m, const float* x0, int width, int height, int row_stride)
+{
+    const int L = m->num_landmarks;
+    float minx = x0[0], maxx = x0[0], miny = x0[L], maxy = x0[L];
+    for (int i = 1; i < L; ++i) {
+        minx = x0[i] < minx ? x0[i] : minx; maxx = x0[i] > maxx ? x0[i] : maxx;
+        miny = x0[i + L] < miny ? x0[i + L] : miny; maxy = x0[i + L] > maxy ? x0[i + L] : maxy;
+    }
+    float rxs = 0, rys = 0, lxs = 0, lys = 0;
+    for (int i = 0; i < m->norm.n_right; ++i) { rxs += x0[m->norm.right_idx[i]]; rys += x0[m->norm.right_idx[i] + L]; }
+    for (int i = 0; i < m->norm.n_left; ++i) { lxs += x0[m->norm.left_idx[i]]; lys += x0[m->norm.left_idx[i] + L]; }
+    rxs /= m->norm.n_right; rys /= m->norm.n_right; lxs /= m->norm.n_left; lys /= m->norm.n_left;
+    const float ied = std::sqrt((rxs - lxs) * (rxs - lxs) + (rys - lys) * (rys - lys));
+    float rel = 0.f;
+    for (const auto& hp : m->hog) rel = hp.relative_patch_size > rel ? hp.relative_patch_size : rel;
+    const float grow = 0.5f * rel * ied * 1.1f + 0.2f * ied + 4.f;        // half patch (IED may grow a little) + drift
+    int xa = (int)std::floor(minx - grow), xb = (int)std::ceil(maxx + grow);
+    int ya = (int)std::floor(miny - grow), yb = (int)std::ceil(maxy + grow);
+    xa = xa < 0 ? 0 : xa; ya = ya < 0 ? 0 : ya;
+    xb = xb > width ? width : xb; yb = yb > height ? height : yb;
+    sd_roi r{};
+    if (xb <= xa || yb <= ya) { xa = 0; ya = 0; xb = 16 < width ? 16 : width; yb = 1; }   // face entirely outside the frame
+    r.x = xa & ~15;
+    int w = ((xb - r.x) + 15) & ~15;
+    const int maxw = (row_stride - r.x) & ~15;
+    if (w > maxw) w = maxw;
+    r.w = w; r.y = ya; r.h = yb - ya; r.row_stride = w; r.reserved = 0; r.offset = 0;
+    return r;
 }
 
 }  // namespace
@@ -350,12 +417,9 @@ int sd_detect_batch_device(sd_ctx* ctx, const sd_model* m, const sd_image_batch*
     return detect_device(ctx, m, images, d_x0, count, d_landmarks);
 }
 
-int sd_detect_batch_host(sd_ctx* ctx, const sd_model* m, const uint8_t* h_images, int count, int width, int height,
-                         int row_stride, const int32_t* h_boxes, float* h_landmarks)
+static int detect_host_full(sd_ctx* ctx, const sd_model* m, const uint8_t* h_images, int count, int width, int height,
+                            int row_stride, const int32_t* h_boxes, float* h_landmarks)
 {
-    if (!ctx) return SD_ERR_INVALID;
-    SD_REQUIRE(ctx, m && h_images && h_boxes && h_landmarks && count >= 0 && width > 0 && height > 0 && row_stride >= width, "bad argument");
-    if (count == 0) return SD_OK;
     const int L = m->num_landmarks, P = 2 * L;
     const size_t frame_bytes = (size_t)height * row_stride;
     // chunking: ~128 MB of frames per staging buffer, at least 1 face
@@ -388,7 +452,7 @@ int sd_detect_batch_host(sd_ctx* ctx, const sd_model* m, const uint8_t* h_images
                                      cudaMemcpyHostToDevice, ctx->copy_stream));
         SD_CUDA(ctx, cudaEventRecord(ctx->stage_ev[buf], ctx->copy_stream));
         SD_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->stage_ev[buf], 0));
-        sd_image_batch ib;
+        sd_image_batch ib{};
         ib.d_data = (const uint8_t*)ctx->d_stage[buf];
         ib.width = width; ib.height = height; ib.row_stride = row_stride; ib.image_stride = (int64_t)frame_bytes; ib.count = n;
         int rc = detect_device(ctx, m, &ib, d_x + (size_t)first * P, n, d_out + (size_t)first * P);
@@ -398,6 +462,122 @@ int sd_detect_batch_host(sd_ctx* ctx, const sd_model* m, const uint8_t* h_images
     SD_CUDA(ctx, cudaMemcpyAsync(h_landmarks, d_out, (size_t)count * P * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return SD_OK;
+}
+
+// ROI route: needs the caller's frames in pinned (device-mapped) host memory
+static int detect_host_roi(sd_ctx* ctx, const sd_model* m, const uint8_t* h_images, const uint8_t* d_alias, int count, int width,
+                           int height, int row_stride, const int32_t* h_boxes, float* h_landmarks)
+{
+    const int L = m->num_landmarks, P = 2 * L;
+    const size_t frame_bytes = (size_t)height * row_stride;
+    const size_t chunk_cap = (size_t)48 << 20;            // packed ROI bytes per staging buffer
+    // initial landmarks and the ROI of every face; faces are grouped into chunks that fit one staging buffer
+    std::vector<float> x0((size_t)count * P);
+    std::vector<sd_roi> rois(count);
+    std::vector<int> chunk_first;
+    size_t used = 0;
+    for (int i = 0; i < count; ++i) {
+        sd_align_mean(m->mean.data(), L, h_boxes[4 * i], h_boxes[4 * i + 1], h_boxes[4 * i + 2], h_boxes[4 * i + 3], 1.f, 1.f, 0.f, 0.f, &x0[(size_t)i * P]);
+        sd_roi r = face_roi(m, &x0[(size_t)i * P], width, height, row_stride);
+        const size_t bytes = (size_t)r.row_stride * r.h;
+        if (chunk_first.empty() || used + bytes > chunk_cap) { chunk_first.push_back(i); used = 0; }
+        r.offset = (int64_t)used;
+        used += bytes;
+        rois[i] = r;
+    }
+    chunk_first.push_back(count);
+    for (int b = 0; b < 2; ++b) {
+        if (ctx->stage_bytes[b] < chunk_cap + (1u << 20)) {
+            if (ctx->d_stage[b]) { SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); SD_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream)); SD_CUDA(ctx, cudaFree(ctx->d_stage[b])); ctx->d_stage[b] = nullptr; }
+            SD_CUDA(ctx, cudaMalloc(&ctx->d_stage[b], chunk_cap + (1u << 20)));
+            ctx->stage_bytes[b] = chunk_cap + (1u << 20);
+        }
+    }
+    // device tables: landmarks (in, out), ROI records, miss flags
+    const size_t xbytes = (size_t)count * P * sizeof(float);
+    const size_t rbytes = (size_t)count * sizeof(sd_roi);
+    unsigned char* tab = (unsigned char*)sd_workspace(ctx, SD_WS_PARTIAL, 2 * xbytes + rbytes + count + 64);
+    if (!tab) return SD_ERR_CUDA;
+    float* d_x = (float*)tab;
+    float* d_out = (float*)(tab + xbytes);
+    sd_roi* d_roi = (sd_roi*)(tab + 2 * xbytes);
+    uint8_t* d_miss = tab + 2 * xbytes + rbytes;
+    SD_CUDA(ctx, cudaMemcpyAsync(d_x, x0.data(), xbytes, cudaMemcpyHostToDevice, ctx->stream));
+    SD_CUDA(ctx, cudaMemcpyAsync(d_roi, rois.data(), rbytes, cudaMemcpyHostToDevice, ctx->stream));
+    SD_CUDA(ctx, cudaMemsetAsync(d_miss, 0, count, ctx->stream));
+    SD_CUDA(ctx, cudaEventRecord(ctx->stage_done[0], ctx->stream));
+    SD_CUDA(ctx, cudaEventRecord(ctx->stage_done[1], ctx->stream));
+    int buf = 0;
+    for (size_t c = 0; c + 1 < chunk_first.size(); ++c, buf ^= 1) {
+        const int first = chunk_first[c], n = chunk_first[c + 1] - first;
+        SD_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->stage_done[buf], 0));   // also orders the table uploads before the first gather
+        if (ctx->roi_mode == 1) {
+            // DMA engines: one strided copy per face, submitted as a single batch
+            std::vector<cudaMemcpy3DBatchOp> ops(n);
+            for (int f = 0; f < n; ++f) {
+                const sd_roi& r = rois[first + f];
+                cudaMemcpy3DBatchOp op;
+                memset(&op, 0, sizeof(op));
+                op.src.type = cudaMemcpyOperandTypePointer;
+                op.src.op.ptr.ptr = const_cast<uint8_t*>(h_images) + (size_t)(first + f) * frame_bytes + (size_t)r.y * row_stride + r.x;
+                op.src.op.ptr.rowLength = (size_t)row_stride;
+                op.src.op.ptr.layerHeight = 0;
+                op.dst.type = cudaMemcpyOperandTypePointer;
+                op.dst.op.ptr.ptr = (uint8_t*)ctx->d_stage[buf] + r.offset;
+                op.dst.op.ptr.rowLength = (size_t)r.row_stride;
+                op.dst.op.ptr.layerHeight = 0;
+                op.extent = make_cudaExtent((size_t)r.row_stride, (size_t)r.h, 1);
+                op.srcAccessOrder = cudaMemcpySrcAccessOrderStream;
+                op.flags = 0;
+                ops[f] = op;
+            }
+            size_t fail = 0;
+            SD_CUDA(ctx, cudaMemcpy3DBatchAsync((size_t)n, ops.data(), &fail, 0, ctx->copy_stream));
+        } else {
+            const int blocks = n < 8 * ctx->sm_count ? n : 8 * ctx->sm_count;
+            roi_gather_kernel<<<blocks, 256, 0, ctx->copy_stream>>>(d_alias, (long long)frame_bytes, row_stride, d_roi, first, n, (uint8_t*)ctx->d_stage[buf]);
+            SD_LAUNCH_CHECK(ctx, "roi_gather_kernel");
+        }
+        SD_CUDA(ctx, cudaEventRecord(ctx->stage_ev[buf], ctx->copy_stream));
+        SD_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->stage_ev[buf], 0));
+        sd_image_batch ib{};
+        ib.d_data = (const uint8_t*)ctx->d_stage[buf];
+        ib.width = width; ib.height = height; ib.row_stride = row_stride; ib.image_stride = 0; ib.count = n;
+        ib.d_roi = d_roi + first;
+        ib.d_roi_miss = d_miss + first;
+        int rc = detect_device(ctx, m, &ib, d_x + (size_t)first * P, n, d_out + (size_t)first * P);
+        if (rc) return rc;
+        SD_CUDA(ctx, cudaEventRecord(ctx->stage_done[buf], ctx->stream));
+    }
+    std::vector<uint8_t> miss(count);
+    SD_CUDA(ctx, cudaMemcpyAsync(h_landmarks, d_out, xbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    SD_CUDA(ctx, cudaMemcpyAsync(miss.data(), d_miss, count, cudaMemcpyDeviceToHost, ctx->stream));
+    SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    // faces whose cascade wandered outside the uploaded region: repeat them from their full frames
+    for (int i = 0; i < count; ++i) {
+        if (!miss[i]) continue;
+        ctx->roi_fallbacks++;
+        int rc = detect_host_full(ctx, m, h_images + (size_t)i * frame_bytes, 1, width, height, row_stride, h_boxes + 4 * i, h_landmarks + (size_t)i * P);
+        if (rc) return rc;
+    }
+    return SD_OK;
+}
+
+int sd_detect_batch_host(sd_ctx* ctx, const sd_model* m, const uint8_t* h_images, int count, int width, int height,
+                         int row_stride, const int32_t* h_boxes, float* h_landmarks)
+{
+    if (!ctx) return SD_ERR_INVALID;
+    SD_REQUIRE(ctx, m && h_images && h_boxes && h_landmarks && count >= 0 && width > 0 && height > 0 && row_stride >= width, "bad argument");
+    if (count == 0) return SD_OK;
+    // ROI route when the frames are in pinned, device-mapped host memory with 16-byte aligned rows
+    const size_t frame_bytes = (size_t)height * row_stride;
+    cudaPointerAttributes attr;
+    const bool pinned = cudaPointerGetAttributes(&attr, h_images) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer;
+    if (!pinned) cudaGetLastError();
+    const bool aligned = pinned && ((reinterpret_cast<uintptr_t>(attr.devicePointer) | (uintptr_t)row_stride | (uintptr_t)frame_bytes) & 15) == 0;
+    if (aligned && !ctx->disable_roi)
+        return detect_host_roi(ctx, m, h_images, (const uint8_t*)attr.devicePointer, count, width, height, row_stride, h_boxes, h_landmarks);
+    return detect_host_full(ctx, m, h_images, count, width, height, row_stride, h_boxes, h_landmarks);
 }
 
 }  // extern "C"

@@ -60,6 +60,13 @@ def test_detect_batch_host_and_device_paths(sd, oracle, golden):
     assert np.array_equal(dev, got)
     # determinism: same inputs -> bit-identical landmarks
     assert np.array_equal(m.detect_batch(images, boxes), got)
+    # pinned host frames take the region-of-interest upload route (zero-copy gather of the face neighbourhood);
+    # it must give bit-identical landmarks, including for the boxes that hang over the frame border
+    pinned = torch.from_numpy(images).pin_memory()
+    fb0 = m.ctx.roi_fallbacks()
+    roi = m.detect_batch(pinned.numpy(), boxes)
+    assert np.array_equal(roi, got)
+    print("ROI route: fallbacks", m.ctx.roi_fallbacks() - fb0, "of", len(boxes))
 
 
 def test_cascade_levels_teacher_forced(sd, oracle, golden):
