@@ -103,7 +103,7 @@ struct HogSmem {
 
 __host__ __device__ inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
 
-__host__ __device__ inline HogSmem hog_smem_layout(int fs, int nc, int K, int dd)
+__host__ __device__ inline HogSmem hog_smem_layout(int fs, int nc, int K, int dd, bool pair)
 {
     HogSmem s;
     const int cells = nc * nc;
@@ -127,7 +127,7 @@ __host__ __device__ inline HogSmem hog_smem_layout(int fs, int nc, int K, int dd
     s.hist = o;   o += cells * 2 * K * 4;
     s.energy = o; o = align_up(o + cells * 4, 16);
     s.fac = o;    o += cells * 4 * 8;
-    s.priv = o;   o += kHogWarps * 2 * K * 32 * 4;
+    s.priv = o;   o += kHogWarps * (pair ? 2 : 1) * 2 * K * 32 * 4;   // private histogram columns (two cells when paired)
     s.feat = o;   o += cells * dd * 4;
     s.total = align_up(o, 16);
     return s;
@@ -136,6 +136,51 @@ __host__ __device__ inline HogSmem hog_smem_layout(int fs, int nc, int K, int dd
 __device__ __forceinline__ int clip_index(int x, int a, int b) { return x >= a ? (x < b ? x : b - 1) : a; }
 
 __device__ __forceinline__ short sat_short(int v) { return (short)(v > 32767 ? 32767 : (v < -32768 ? -32768 : v)); }
+
+
+// Column sums of one warp's private histogram table priv[bin][lane] -> s_hist[bin * cells + c]; the table is
+// cleared for the next cell.  KT > 0: recursive halving (after log2(NB) exchange steps every lane owns one
+// bin, the remaining butterfly steps finish the sum; fixed tree -> deterministic).  KT == 0: transposed read.
+template <int KT>
+__device__ __forceinline__ void hog_reduce_priv(float* priv, int lane, float* s_hist, int cells, int c, int K)
+{
+    if (KT > 0) {
+        constexpr int NB = KT > 0 ? (2 * KT <= 8 ? 8 : (2 * KT <= 16 ? 16 : 32)) : 32;
+        float v[NB];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            v[b] = b < 2 * KT ? priv[b * 32 + lane] : 0.f;
+            if (b < 2 * KT) priv[b * 32 + lane] = 0.f;
+        }
+        int bin = 0;
+#pragma unroll
+        for (int o = 16, n = NB; n > 1; o >>= 1, n >>= 1) {
+            const bool up = (lane & o) != 0;
+#pragma unroll
+            for (int i = 0; i < n / 2; ++i) {
+                const float send = up ? v[i] : v[i + n / 2];
+                const float keep = up ? v[i + n / 2] : v[i];
+                v[i] = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, o));
+            }
+            bin += up ? n / 2 : 0;
+        }
+        float tot = v[0];
+#pragma unroll
+        for (int o = 32 / NB / 2; o > 0; o >>= 1) tot = __fadd_rn(tot, __shfl_xor_sync(0xffffffffu, tot, o));
+        if ((lane & (32 / NB - 1)) == 0 && bin < 2 * KT) s_hist[bin * cells + c] = tot;
+    } else {
+        // lane b sums row b of the table, starting at column b (skew -> distinct banks)
+        for (int b = lane; b < 2 * K; b += 32) {
+            float sacc = 0.f;
+#pragma unroll 8
+            for (int j = 0; j < 32; ++j) sacc = __fadd_rn(sacc, priv[b * 32 + ((j + b) & 31)]);
+            s_hist[b * cells + c] = sacc;
+        }
+        __syncwarp();
+        for (int i = lane; i < 2 * K * 32; i += 32) priv[i] = 0.f;
+    }
+    __syncwarp();
+}
 
 // KT / NCT / CST > 0 bake the bin count, cells per side and cell size into the kernel (the schedules the
 // reference ships: 5x5 cells of 11/10/8/6 px, K = 4 or 9), which lets the compiler strength-reduce every
@@ -149,7 +194,9 @@ __global__ void __launch_bounds__(kHogThreads) hog_patch_kernel(const HogArgs a)
     const int fs = (NCT > 0 && CST > 0) ? NCT * CST : a.fs;
     const int dd = a.dd;
     const int cells = nc * nc;
-    const HogSmem lay = hog_smem_layout(fs, nc, K, dd);
+    // two horizontally adjacent cells per warp task when a single cell's window would leave lanes idle (2*cs > 16)
+    constexpr bool PAIR = (KT == 4 && NCT > 0 && CST >= 9);
+    const HogSmem lay = hog_smem_layout(fs, nc, K, dd, PAIR);
     uint8_t* s_patch = smem + lay.patch;
     int8_t* s_bin = reinterpret_cast<int8_t*>(smem + lay.bin);
     float* s_gmag = reinterpret_cast<float*>(smem + lay.r1);
@@ -233,7 +280,7 @@ __global__ void __launch_bounds__(kHogThreads) hog_patch_kernel(const HogArgs a)
         // weight with which pixel t votes into cell index c: w1 for its own bin, w2 for the next one
         for (int c = 0; c < nc; ++c) s_wcell[c * fs + t] = (b == c) ? w1 : ((b == c - 1) ? w2 : 0.f);
     }
-    for (int i = tid; i < kHogWarps * 2 * K * 32; i += kHogThreads) s_priv[i] = 0.f;
+    for (int i = tid; i < kHogWarps * (PAIR ? 2 : 1) * 2 * K * 32; i += kHogThreads) s_priv[i] = 0.f;
     __syncthreads();
 
     // ---- S1: zero-padded crop + fixed-point bilinear resize.  The P x P source window is first staged in
@@ -243,14 +290,26 @@ __global__ void __launch_bounds__(kHogThreads) hog_patch_kernel(const HogArgs a)
         const int x0 = cx - half, y0 = cy - half;
         const int W = a.width, H = a.height;
         const bool resident = x0 >= rx && y0 >= ry && x0 + P <= rx + rw && y0 + P <= ry + rh;
-        const bool words = resident && ((reinterpret_cast<uintptr_t>(img) | (uintptr_t)rs) & 3) == 0;
-        const int shiftb = words ? ((x0 - rx) & 3) : 0;          // column c of the window sits at byte shiftb + c
-        const int pitch = (P + 3 + 3) & ~3;
+        const uintptr_t align_bits = reinterpret_cast<uintptr_t>(img) | (uintptr_t)rs;
+        const bool vec16 = resident && (align_bits & 15) == 0;      // rows can be fetched as aligned 16-byte vectors
+        const bool words = resident && (align_bits & 3) == 0;
+        // column c of the staged window sits at byte shiftb + c of its row
+        const int shiftb = vec16 ? ((x0 - rx) & 15) : (words ? ((x0 - rx) & 3) : 0);
+        const int pitch = (P + 15 + 15) & ~15;
         uint8_t* s_stage = smem + lay.bin;                         // [bin | r1] are dead until S2
         const bool staged = pitch * P <= lay.xofs - lay.bin;
         bool miss = false;
         if (staged) {
-            if (words) {
+            if (vec16) {
+                // 8 / 16 / 32 lanes per source row, one aligned uint4 each: ~P * nvec / 32 warp loads in total
+                const int nvec = (shiftb + P + 15) >> 4;
+                const int gs = nvec <= 8 ? 3 : (nvec <= 16 ? 4 : 5);
+                const int lv = lane & ((1 << gs) - 1), lr = lane >> gs, rows_per_pass = 32 >> gs;
+                const uint8_t* wrow = img + (long long)(y0 - ry) * rs + (x0 - rx - shiftb);
+                for (int r = warp * rows_per_pass + lr; r < P; r += kHogWarps * rows_per_pass)
+                    for (int v = lv; v < nvec; v += (1 << gs))
+                        reinterpret_cast<uint4*>(s_stage + r * pitch)[v] = __ldg(reinterpret_cast<const uint4*>(wrow + (long long)r * rs) + v);
+            } else if (words) {
                 const int nwords = (shiftb + P + 3) >> 2;
                 const uint8_t* wrow = img + (long long)(y0 - ry) * rs + (x0 - rx - shiftb);
                 for (int r = warp; r < P; r += kHogWarps) {
@@ -357,9 +416,56 @@ __global__ void __launch_bounds__(kHogThreads) hog_patch_kernel(const HogArgs a)
     __syncthreads();
 
     // ---- S3: spatial vote, gathered per cell by one warp (hog.c:697-724).  Lanes run along x inside the
-    //      cell's window (2*cs wide), 32 >> shift rows per pass; every lane owns a private column of the
-    //      histogram (bank == lane: conflict free), reduced by a skewed transposed read. --------------------
-    {
+    //      cell's window; every lane owns a private column of the histogram (bank == lane: conflict free).
+    if (PAIR) {
+        // two adjacent cells (ci, ci+1) per task: their windows overlap by half, the union is <= 3*cs columns;
+        // bin / modulus / row weight are loaded once and voted into both cells
+        const int groups = (nc + 1) / 2;
+        float* privA = s_priv + warp * (2 * 2 * K * 32);
+        float* privB = privA + 2 * K * 32;
+        for (int task = warp; task < nc * groups; task += kHogWarps) {
+            const int cj = task / groups, g = task - cj * groups;
+            const int ciA = 2 * g, ciB = ciA + 1;
+            const bool hasB = ciB < nc;
+            const int xlo = s_lo[ciA], xhi = hasB ? s_hi[ciB] : s_hi[ciA], ylo = s_lo[cj], yhi = s_hi[cj];
+            const int hh = yhi - ylo + 1;
+            const float* wyt = s_wcell + cj * fs;
+            if (xhi >= xlo && hh > 0) {
+                const int px = xlo + lane;
+                if (px <= xhi) {
+                    const float wA = s_wcell[ciA * fs + px];
+                    const float wB = hasB ? s_wcell[ciB * fs + px] : 0.f;
+                    const int8_t* bp = s_bin + ylo * fs + px;
+                    const float* gp = s_gmag + ylo * fs + px;
+                    float* plA = privA + lane;
+                    float* plB = privB + lane;
+#pragma unroll 2
+                    for (int ry = 0; ry < hh; ++ry) {
+                        const int b = max((int)*bp, 0) << 5;          // zero gradient: bin -1, modulus 0 -> votes +0 into bin 0
+                        const float gm = *gp, wy = wyt[ylo + ry];
+                        plA[b] = __fadd_rn(plA[b], __fmul_rn(__fmul_rn(gm, wA), wy));     // grad * wx * wy
+                        plB[b] = __fadd_rn(plB[b], __fmul_rn(__fmul_rn(gm, wB), wy));
+                        bp += fs; gp += fs;
+                    }
+                }
+                // columns beyond the 32nd of the union (3*cs = 33 for cs = 11): lanes run along y instead
+                for (int px2 = xlo + 32; px2 <= xhi; ++px2) {
+                    const float wA = s_wcell[ciA * fs + px2];
+                    const float wB = hasB ? s_wcell[ciB * fs + px2] : 0.f;
+                    for (int ry = lane; ry < hh; ry += 32) {
+                        const int idx = (ylo + ry) * fs + px2;
+                        const int b = max((int)s_bin[idx], 0) << 5;
+                        const float gm = s_gmag[idx], wy = wyt[ylo + ry];
+                        privA[b + lane] = __fadd_rn(privA[b + lane], __fmul_rn(__fmul_rn(gm, wA), wy));
+                        privB[b + lane] = __fadd_rn(privB[b + lane], __fmul_rn(__fmul_rn(gm, wB), wy));
+                    }
+                }
+            }
+            __syncwarp();
+            hog_reduce_priv<KT>(privA, lane, s_hist, cells, cj * nc + ciA, K);
+            if (hasB) hog_reduce_priv<KT>(privB, lane, s_hist, cells, cj * nc + ciB, K);
+        }
+    } else {
         float* priv = s_priv + warp * (2 * K * 32);
         for (int c = warp; c < cells; c += kHogWarps) {
             const int cj = c / nc, ci = c - cj * nc;      // cell row (y), cell column (x)
@@ -368,6 +474,7 @@ __global__ void __launch_bounds__(kHogThreads) hog_patch_kernel(const HogArgs a)
             if (ww > 0 && hh > 0) {
                 const float* wyt = s_wcell + cj * fs;
                 if (ww <= 32) {
+                    // 8 / 16 / 32 lanes per row, 32 >> shift rows per pass
                     const int shift = ww <= 8 ? 3 : (ww <= 16 ? 4 : 5);
                     const int lx = lane & ((1 << shift) - 1), lr = lane >> shift, rpi = 32 >> shift;
                     if (lx < ww) {
@@ -401,44 +508,7 @@ __global__ void __launch_bounds__(kHogThreads) hog_patch_kernel(const HogArgs a)
                 }
             }
             __syncwarp();
-            if (KT > 0) {
-                // column sums of the private table by recursive halving: after log2(NB) exchange steps every
-                // lane owns one bin, the remaining butterfly steps finish the sum (fixed tree -> deterministic)
-                constexpr int NB = KT > 0 ? (2 * KT <= 8 ? 8 : (2 * KT <= 16 ? 16 : 32)) : 32;
-                float v[NB];
-#pragma unroll
-                for (int b = 0; b < NB; ++b) {
-                    v[b] = b < 2 * KT ? priv[b * 32 + lane] : 0.f;
-                    if (b < 2 * KT) priv[b * 32 + lane] = 0.f;
-                }
-                int bin = 0;
-#pragma unroll
-                for (int o = 16, n = NB; n > 1; o >>= 1, n >>= 1) {
-                    const bool up = (lane & o) != 0;
-#pragma unroll
-                    for (int i = 0; i < n / 2; ++i) {
-                        const float send = up ? v[i] : v[i + n / 2];
-                        const float keep = up ? v[i + n / 2] : v[i];
-                        v[i] = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, o));
-                    }
-                    bin += up ? n / 2 : 0;
-                }
-                float tot = v[0];
-#pragma unroll
-                for (int o = 32 / NB / 2; o > 0; o >>= 1) tot = __fadd_rn(tot, __shfl_xor_sync(0xffffffffu, tot, o));
-                if ((lane & (32 / NB - 1)) == 0 && bin < 2 * KT) s_hist[bin * cells + c] = tot;
-            } else {
-                // transposed reduction: lane b sums row b of the private table, starting at column b (skew -> distinct banks)
-                for (int b = lane; b < 2 * K; b += 32) {
-                    float sacc = 0.f;
-#pragma unroll 8
-                    for (int j = 0; j < 32; ++j) sacc = __fadd_rn(sacc, priv[b * 32 + ((j + b) & 31)]);
-                    s_hist[b * cells + c] = sacc;
-                }
-                __syncwarp();
-                for (int i = lane; i < 2 * K * 32; i += 32) priv[i] = 0.f;
-            }
-            __syncwarp();
+            hog_reduce_priv<KT>(priv, lane, s_hist, cells, c, K);
         }
     }
     __syncthreads();
@@ -588,7 +658,8 @@ int launch_hog(sd_ctx* ctx, const sd_image_batch* images, const int32_t* d_image
     SD_LAUNCH_CHECK(ctx, "hog_geometry_kernel");
     a.half = d_half;
 
-    const HogSmem lay = hog_smem_layout(fs, a.nc, a.K, a.dd);
+    const bool pair = a.nc == 5 && a.K == 4 && a.cs >= 9;     // must match PAIR of the kernel that gets picked below
+    const HogSmem lay = hog_smem_layout(fs, a.nc, a.K, a.dd, pair);
     SD_REQUIRE(ctx, lay.total <= 227 * 1024, "HOG configuration needs more than 227 KB of shared memory");
     const long long blocks = (long long)N * L;
     SD_REQUIRE(ctx, blocks < 2147483647LL, "too many patches for one launch");

@@ -149,3 +149,25 @@ def test_cascade_with_ied_normalisation_vs_oracle(sd, oracle, golden):
         assert rel_err(sdo.regressors[k].x.cpu().numpy(), w[k]) <= 2e-3     # ill-conditioned toy system: weights looser than outputs
     xt = sdo.test(x0[:10], None, h).cpu().numpy()
     assert rel_err(xt, oracle.cascade_apply(x0[:10], None, w, h, norm=([0, 1], [4]))) <= TOL
+
+
+def test_pose_estimation_example_config2(sd, oracle):
+    """BASELINE config 2 (examples/pose_estimation.cpp) on the GPU: host projection functor, GPU learn/predict,
+    against the oracle cascade on the same seeded training set."""
+    import pose_example as P
+    x_tr, y_tr, x0 = P.training_set()
+    regs = [sd.LinearRegressor(sd.Regulariser(sd.RegularisationType.MatrixNorm, 2.0, True)) for _ in range(3)]
+    sdo = sd.SupervisedDescentOptimiser(regs)
+    res = []
+    xf = sdo.train(x_tr, x0, y_tr, P.projection, lambda cur: res.append(K.nlsr(cur.cpu().numpy(), x_tr))).cpu().numpy()
+    oregs = [oracle.Regulariser(1, 2.0, 1) for _ in range(3)]
+    w, xo, rc = oracle.cascade_train(x_tr, x0, y_tr, oregs, [20] * 3, P.projection, None, 0)
+    print("gpu pose residuals", res, "final x rel err vs oracle", rel_err(xf, xo))
+    assert rel_err(xf, xo) <= 1e-4
+    for k in range(3):
+        assert rel_err(sdo.regressors[k].x.cpu().numpy(), w[k]) <= 1e-3
+    pred = sdo.predict(P.TEST_INIT, P.TEST_LANDMARKS, P.projection).cpu().numpy()[0]
+    ref = oracle.cascade_apply(P.TEST_INIT, P.TEST_LANDMARKS, w, P.projection, None)[0]
+    print("predicted pitch/yaw/roll", pred[:3], "oracle", ref[:3])
+    assert np.max(np.abs(pred - ref)) <= 1e-4 * np.max(np.abs(ref))
+    assert np.all(np.abs(pred[:3] - np.array([11.0, -25.0, -10.0])) < 6.0)

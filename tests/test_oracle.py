@@ -235,3 +235,18 @@ def test_matrixnorm_lambda_rule(oracle):
     Lam[-1, -1] = 0
     Xd = np.linalg.solve(G + Lam, A.astype(np.float64).T @ B.astype(np.float64))
     assert rel_err(X, Xd) < 1e-4
+
+
+def test_pose_estimation_example_config2(oracle):
+    """BASELINE config 2: examples/pose_estimation.cpp -- 500 samples x 20 features -> 6 pose parameters, three
+    regressors with MatrixNorm 2.0, known-template training (y = projected landmarks)."""
+    import pose_example as P
+    x_tr, y_tr, x0 = P.training_set()
+    regs = [oracle.Regulariser(1, 2.0, 1) for _ in range(3)]
+    residuals = []
+    w, xf, rc = oracle.cascade_train(x_tr, x0, y_tr, regs, [20] * 3, P.projection, None, 0,
+                                     lambda cur, lvl: residuals.append(K.nlsr(cur, x_tr)))
+    assert rc == 0 and len(residuals) == 3 and residuals[0] > residuals[1] > residuals[2] and residuals[2] < 0.01
+    pred = oracle.cascade_apply(P.TEST_INIT, P.TEST_LANDMARKS, w, P.projection, None)[0]
+    print("oracle pose residuals", residuals, "predicted pitch/yaw/roll", pred[:3])
+    assert np.all(np.abs(pred[:3] - np.array([11.0, -25.0, -10.0])) < 6.0)      # example's ground truth (:334)
