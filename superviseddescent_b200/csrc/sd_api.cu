@@ -111,7 +111,6 @@ int sd_ctx_create(int device, void* stream, sd_ctx** out)
          cudaMemset(ctx->d_scratch, 0, 4096) == cudaSuccess;
     if (!ok) { sd_ctx_destroy(ctx); return SD_ERR_CUDA; }
     { const char* e = getenv("SD_B200_NO_ROI"); ctx->disable_roi = e && e[0] == '1'; }
-    { const char* e = getenv("SD_B200_ROI_MODE"); ctx->roi_mode = (e && e[0] == '1') ? 1 : 0; }
     *out = ctx;
     return SD_OK;
 }

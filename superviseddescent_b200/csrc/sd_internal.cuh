@@ -16,7 +16,7 @@
 #define SD_MAX_BINS 16   // undirected orientations K supported by the HOG kernel
 
 enum { SD_WS_GRAM_EXT = 0, SD_WS_SPLIT_HI, SD_WS_SPLIT_LO, SD_WS_FEATURES, SD_WS_SCRATCH, SD_WS_DIAGINV,
-       SD_WS_PARTIAL, SD_WS_GEOM, SD_WS_GEMM_PARTIAL, SD_WS_COUNT };
+       SD_WS_PARTIAL, SD_WS_GEOM, SD_WS_GEMM_PARTIAL, SD_WS_DIAGINV2, SD_WS_PANEL, SD_WS_COUNT };
 
 struct sd_ctx {
     int device = 0;
@@ -28,7 +28,6 @@ struct sd_ctx {
     int sm_count = 148;
     int gram_mode = 0;
     bool disable_roi = false;      // sd_detect_batch_host: always upload whole frames
-    int roi_mode = 0;              // 0: zero-copy gather kernel, 1: batched strided DMA copies
     int64_t roi_fallbacks = 0;     // faces repeated from the full frame because a patch left its ROI
     float timings[4] = {0, 0, 0, 0};
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};

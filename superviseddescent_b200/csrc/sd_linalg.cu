@@ -443,165 +443,248 @@ __global__ void copy_block_kernel(const float* __restrict__ src, long long lds, 
 }
 
 // ---- blocked Cholesky G = U^T U (upper), right-looking ---------------------------------------------
-// factor one nb x nb diagonal block in shared memory
-__global__ void __launch_bounds__(512) potrf_block_kernel(float* __restrict__ G, long long ldg, int nb, int* __restrict__ status)
-{
-    extern __shared__ float sU[];   // nb x (nb+1)
-    const int tid = threadIdx.x, nthr = blockDim.x;
-    const int ld = nb + 1;
-    for (int idx = tid; idx < nb * nb; idx += nthr) {
-        const int i = idx / nb, j = idx - i * nb;
-        sU[i * ld + j] = (j >= i) ? G[(long long)i * ldg + j] : 0.f;
-    }
-    __syncthreads();
-    const int tx = tid & 31, ty = tid >> 5, nty = nthr >> 5;     // lanes along j, warps along i
-    for (int k = 0; k < nb; ++k) {
-        const float akk = sU[k * ld + k];
-        if (!(akk > 0.f) && tid == 0) atomicOr(status, 8);   // not positive definite
-        const float d = sqrtf(fabsf(akk) > 0.f ? fabsf(akk) : 1.f);
-        const float inv_d = 1.0f / d;
-        __syncthreads();
-        for (int j = k + tid; j < nb; j += nthr) sU[k * ld + j] = (j == k) ? d : sU[k * ld + j] * inv_d;
-        __syncthreads();
-        for (int i = k + 1 + ty; i < nb; i += nty) {
-            const float uki = sU[k * ld + i];
-            for (int j = i + tx; j < nb; j += 32) sU[i * ld + j] = fmaf(-uki, sU[k * ld + j], sU[i * ld + j]);
-        }
-        __syncthreads();
-    }
-    for (int idx = tid; idx < nb * nb; idx += nthr) {
-        const int i = idx / nb, j = idx - i * nb;
-        if (j >= i) G[(long long)i * ldg + j] = sU[i * ld + j];
-    }
-}
+// One CTA factors a 128 x 128 diagonal block and inverts the factor.  Inner blocking by 32: the 32 x 32
+// diagonal sub-block is factored and inverted by ONE WARP IN REGISTERS (lane j owns column j, rows are
+// exchanged with shuffles: ~500 shfl+fma each, no shared-memory round trips on the dependent chain), the
+// row panel and the trailing update inside the block are small GEMMs by all 8 warps.  Outputs: U (in place
+// in G), W = U^-1 and W^T (workspace) -- so that the panel solve U12 = U11^-T G12 and the back substitution
+// X_j = U_jj^-1 Y_j become plain GEMMs.  Blocks narrower than 128 are padded with the identity.
+constexpr int PB = 128, PS = 32, PLD = PB + 1;
 
-// U12 <- U11^-T * G12 : forward substitution, one thread per column of the row panel (in place).
-// U11 (nb x nb, upper) is staged in shared memory; the column lives in shared memory as well.
-__global__ void __launch_bounds__(128) trsm_panel_kernel(const float* __restrict__ U11, long long ldu, int nb,
-                                                         float* __restrict__ P, long long ldp, int cols)
+// Factor and invert the 32 x 32 diagonal sub-block at (k0, k0) of sA with ONE warp (lane j owns column j).
+// Rolled loops on shared memory with broadcast reads: the fully unrolled register/shuffle variant was measured
+// at 0.21 ms per 128-block -- its ~50 KB of straight-line code thrashes the instruction cache of a lone warp.
+__device__ __forceinline__ void potrf32_warp(float* sA, float* sT, int k0, int lane, bool& bad)
 {
-    extern __shared__ float sm[];
-    float* sU = sm;                       // nb x (nb+1)
-    float* sY = sm + nb * (nb + 1);       // nb x 128 (column per thread)
-    const int tid = threadIdx.x;
-    const int ld = nb + 1;
-    for (int idx = tid; idx < nb * nb; idx += blockDim.x) {
-        const int i = idx / nb, j = idx - i * nb;
-        sU[i * ld + j] = (j >= i) ? U11[(long long)i * ldu + j] : 0.f;
+    float* D = sA + k0 * PLD + k0;                 // D[i][j] at D[i * PLD + j]
+    for (int k = 0; k < PS; ++k) {
+        __syncwarp();                               // row k was last written by the previous step's update
+        const float pk = D[k * PLD + k];
+        if (!(pk > 0.f)) bad = true;
+        const float d = sqrtf(pk > 0.f ? pk : 1.f);
+        const float inv = 1.0f / d;
+        __syncwarp();
+        float ukj = 0.f;
+        if (lane >= k) {
+            ukj = (lane == k) ? d : D[k * PLD + lane] * inv;
+            D[k * PLD + lane] = ukj;
+        }
+        __syncwarp();
+        // rows k+1..31: independent read-modify-writes, unrolled so that their shared-memory latencies overlap
+#pragma unroll 8
+        for (int i = k + 1; i < PS; ++i) {
+            const float uki = D[k * PLD + i];
+            if (lane >= i) D[i * PLD + lane] = fmaf(-uki, ukj, D[i * PLD + lane]);
+        }
     }
-    __syncthreads();
-    const int c = blockIdx.x * blockDim.x + tid;
-    const bool live = c < cols;
-    for (int r = 0; r < nb; ++r) sY[r * 128 + tid] = live ? P[(long long)r * ldp + c] : 0.f;   // coalesced, independent loads
-    for (int r = 0; r < nb; ++r) {
+    __syncwarp();
+    if (lane > 0)                                   // clear the strict lower triangle of this sub-block (column `lane`... row-wise)
+        for (int j = 0; j < lane; ++j) D[lane * PLD + j] = 0.f;
+    __syncwarp();
+    // T = D^-1 (upper): lane j solves U t = e_j by back substitution; T[i][j] kept in sT[i * (PS+1) + j]
+    for (int i = PS - 1; i >= 0; --i) {
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-        int p = 0;
-        for (; p + 3 < r; p += 4) {
-            s0 = fmaf(sU[p * ld + r], sY[p * 128 + tid], s0);
-            s1 = fmaf(sU[(p + 1) * ld + r], sY[(p + 1) * 128 + tid], s1);
-            s2 = fmaf(sU[(p + 2) * ld + r], sY[(p + 2) * 128 + tid], s2);
-            s3 = fmaf(sU[(p + 3) * ld + r], sY[(p + 3) * 128 + tid], s3);
+        int k = i + 1;
+        for (; k + 3 < PS; k += 4) {
+            s0 = fmaf(D[i * PLD + k], sT[k * (PS + 1) + lane], s0);
+            s1 = fmaf(D[i * PLD + k + 1], sT[(k + 1) * (PS + 1) + lane], s1);
+            s2 = fmaf(D[i * PLD + k + 2], sT[(k + 2) * (PS + 1) + lane], s2);
+            s3 = fmaf(D[i * PLD + k + 3], sT[(k + 3) * (PS + 1) + lane], s3);
         }
-        for (; p < r; ++p) s0 = fmaf(sU[p * ld + r], sY[p * 128 + tid], s0);
-        sY[r * 128 + tid] = (sY[r * 128 + tid] - ((s0 + s1) + (s2 + s3))) / sU[r * ld + r];
+        for (; k < PS; ++k) s0 = fmaf(D[i * PLD + k], sT[k * (PS + 1) + lane], s0);
+        const float sum = (s0 + s1) + (s2 + s3);
+        __syncwarp();
+        sT[i * (PS + 1) + lane] = (lane >= i) ? ((lane == i ? 1.f : 0.f) - sum) / D[i * PLD + i] : 0.f;
+        __syncwarp();
     }
-    if (live)
-        for (int r = 0; r < nb; ++r) P[(long long)r * ldp + c] = sY[r * 128 + tid];
+    __syncwarp();
 }
 
-// X_j <- U_jj^-1 * Y_j : back substitution of one diagonal block in shared memory.  Four lanes share one
-// right-hand side column (they split the dot product and combine with two shuffles); the block's U and Y
-// live in shared memory, so the 128 dependent steps cost shared-memory latency, not L2 latency.
-__global__ void __launch_bounds__(256) trsv_block_kernel(const float* __restrict__ U, long long ldu, int nb,
-                                                         float* __restrict__ Y, long long ldy, int M)
+__global__ void __launch_bounds__(256) potrf_inv_kernel(float* __restrict__ G, long long ldg, int nb,
+                                                        float* __restrict__ W, float* __restrict__ Wt, int* __restrict__ status)
 {
     extern __shared__ float sm[];
-    float* sU = sm;                       // nb x (nb+1)
-    const int ld = nb + 1;
-    float* sY = sm + nb * ld;             // nb x 64 (one 64-column chunk of right-hand sides at a time)
-    for (int idx = threadIdx.x; idx < nb * nb; idx += blockDim.x) {
-        const int i = idx / nb, j = idx - i * nb;
-        sU[i * ld + j] = (j >= i) ? U[(long long)i * ldu + j] : 0.f;
+    float* sA = sm;                    // PB x PLD : the block, becomes U
+    float* sW = sm + PB * PLD;         // PB x PLD : U^-1
+    float* sT = sW + PB * PLD;         // PS x (PS+1) scratch (inverse of the current diagonal sub-block / partial sums)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int idx = tid; idx < PB * PB; idx += 256) {
+        const int i = idx >> 7, j = idx & (PB - 1);
+        float v = 0.f;
+        if (i < nb && j < nb) v = (j >= i) ? G[(long long)i * ldg + j] : 0.f;
+        else if (i == j) v = 1.f;                       // identity padding
+        sA[i * PLD + j] = v;
+        sW[i * PLD + j] = 0.f;
     }
-    const int cl = threadIdx.x >> 2, part = threadIdx.x & 3;      // 64 columns x 4 lanes
-    for (int c0 = 0; c0 < M; c0 += 64) {
-        const int mc = min(64, M - c0);
-        __syncthreads();
-        for (int idx = threadIdx.x; idx < nb * 64; idx += blockDim.x) {
-            const int i = idx >> 6, c = idx & 63;
-            sY[idx] = (c < mc) ? Y[(long long)i * ldy + c0 + c] : 0.f;
+    __syncthreads();
+    for (int kb = 0; kb < PB / PS; ++kb) {
+        const int k0 = kb * PS;
+        if (warp == 0) {
+            bool bad = false;
+            potrf32_warp(sA, sT, k0, lane, bad);
+            if (bad && lane == 0) atomicOr(status, 8);                  // not positive definite
+            for (int i = 0; i < PS; ++i) sW[(k0 + i) * PLD + k0 + lane] = sT[i * (PS + 1) + lane];
         }
         __syncthreads();
-        for (int i = nb - 1; i >= 0; --i) {
-            float s = 0.f, s2 = 0.f;
-            int k = i + 1 + part;
-            for (; k + 4 < nb; k += 8) {
-                s = fmaf(sU[i * ld + k], sY[k * 64 + cl], s);
-                s2 = fmaf(sU[i * ld + k + 4], sY[(k + 4) * 64 + cl], s2);
+        const int ncols = PB - k0 - PS;                                  // columns right of the diagonal sub-block
+        if (ncols > 0) {
+            // row panel: U12 = T^T * A12   (T = inverse of the diagonal sub-block)
+            float out[3][4];
+#pragma unroll
+            for (int cc = 0; cc < 3; ++cc) {
+                if (cc * 32 < ncols) {
+                    const int c = k0 + PS + cc * 32 + lane;
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) {
+                        const int r = warp + 8 * m;
+                        float acc = 0.f;
+#pragma unroll 8
+                        for (int q = 0; q <= r; ++q) acc = fmaf(sT[q * (PS + 1) + r], sA[(k0 + q) * PLD + c], acc);   // T[q][r] = 0 for q > r
+                        out[cc][m] = acc;
+                    }
+                }
             }
-            if (k < nb) s = fmaf(sU[i * ld + k], sY[k * 64 + cl], s);
-            s += s2;
-            s += __shfl_xor_sync(0xffffffffu, s, 1);
-            s += __shfl_xor_sync(0xffffffffu, s, 2);
-            if (part == 0) sY[i * 64 + cl] = (sY[i * 64 + cl] - s) / sU[i * ld + i];
-            __syncwarp();
+            __syncthreads();
+#pragma unroll
+            for (int cc = 0; cc < 3; ++cc)
+                if (cc * 32 < ncols) {
+                    const int c = k0 + PS + cc * 32 + lane;
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) sA[(k0 + warp + 8 * m) * PLD + c] = out[cc][m];
+                }
+            __syncthreads();
+            // trailing update inside the block: A22 -= U12^T U12 (upper part)
+            for (int i = k0 + PS + warp; i < PB; i += 8) {
+                for (int j0 = (i & ~31); j0 < PB; j0 += 32) {
+                    const int j = j0 + lane;
+                    float acc = 0.f;
+#pragma unroll 8
+                    for (int q = 0; q < PS; ++q) acc = fmaf(sA[(k0 + q) * PLD + i], sA[(k0 + q) * PLD + j], acc);
+                    if (j >= i) sA[i * PLD + j] -= acc;
+                }
+            }
+            __syncthreads();
         }
-        __syncthreads();
-        for (int idx = threadIdx.x; idx < nb * 64; idx += blockDim.x) {
-            const int i = idx >> 6, c = idx & 63;
-            if (c < mc) Y[(long long)i * ldy + c0 + c] = sY[idx];
+    }
+    // off-diagonal blocks of W = U^-1:  W_ij = -T_i * sum_{k=i+1..j} U_ik W_kj   (block column by block column)
+    for (int jb = 1; jb < PB / PS; ++jb) {
+        for (int ib = jb - 1; ib >= 0; --ib) {
+            float part[4];
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                const int r = warp + 8 * m;
+                float acc = 0.f;
+                for (int kbk = ib + 1; kbk <= jb; ++kbk)
+#pragma unroll 8
+                    for (int q = 0; q < PS; ++q)
+                        acc = fmaf(sA[(ib * PS + r) * PLD + kbk * PS + q], sW[(kbk * PS + q) * PLD + jb * PS + lane], acc);
+                part[m] = acc;
+            }
+#pragma unroll
+            for (int m = 0; m < 4; ++m) sT[(warp + 8 * m) * (PS + 1) + lane] = part[m];
+            __syncthreads();
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                const int r = warp + 8 * m;
+                float acc = 0.f;
+#pragma unroll 8
+                for (int q = r; q < PS; ++q) acc = fmaf(sW[(ib * PS + r) * PLD + ib * PS + q], sT[q * (PS + 1) + lane], acc);   // T_i is upper
+                part[m] = -acc;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int m = 0; m < 4; ++m) sW[(ib * PS + warp + 8 * m) * PLD + jb * PS + lane] = part[m];
+            __syncthreads();
         }
+    }
+    for (int idx = tid; idx < PB * PB; idx += 256) {
+        const int i = idx >> 7, j = idx & (PB - 1);
+        if (i < nb && j < nb && j >= i) G[(long long)i * ldg + j] = sA[i * PLD + j];
+        W[idx] = sW[i * PLD + j];
+        Wt[idx] = sW[j * PLD + i];
     }
 }
 
 int cholesky_solve(sd_ctx* ctx, float* G, int64_t ldg, int D, int M, float* X)
 {
     int* status = reinterpret_cast<int*>(ctx->d_scratch);
-    const int W = D + M;
-    const size_t smem_potrf = (size_t)kCholNb * (kCholNb + 1) * 4;
-    const size_t smem_trsm = smem_potrf + (size_t)kCholNb * 128 * 4;
-    SD_CUDA(ctx, cudaFuncSetAttribute(potrf_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_potrf));
-    SD_CUDA(ctx, cudaFuncSetAttribute(trsm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_trsm));
-    const size_t smem_trsv = smem_potrf + (size_t)kCholNb * 64 * 4;
-    SD_CUDA(ctx, cudaFuncSetAttribute(trsv_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_trsv));
+    const int W_ = D + M;
+    const int nblocks = sd_div_up(D, kCholNb);
+    const size_t smem_potrf = (size_t)(2 * PB * PLD + PS * (PS + 1)) * sizeof(float);
+    SD_CUDA(ctx, cudaFuncSetAttribute(potrf_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_potrf));
+    // per block: W = U_jj^-1 and its transpose (row-major 128 x 128 each)
+    float* inv = (float*)sd_workspace(ctx, SD_WS_DIAGINV2, (size_t)nblocks * 2 * PB * PB * sizeof(float));
+    const int64_t ldp = ((int64_t)W_ + 3) / 4 * 4;
+    float* panel = (float*)sd_workspace(ctx, SD_WS_PANEL, (size_t)2 * PB * ldp * sizeof(float));
+    if (!inv || !panel) return SD_ERR_CUDA;
+    GemmEpilogue ep;
+    memset(&ep, 0, sizeof(ep));
     // ---- factorisation, carrying the right-hand side columns along (Y = U^-T R) ----
-    for (int j = 0; j < D; j += kCholNb) {
-        const int nb = (D - j < kCholNb) ? D - j : kCholNb;
-        float* Gjj = G + (int64_t)j * ldg + j;
-        potrf_block_kernel<<<1, 512, (size_t)nb * (nb + 1) * 4, ctx->stream>>>(Gjj, ldg, nb, status);
-        SD_LAUNCH_CHECK(ctx, "potrf_block_kernel");
-        const int cols = W - j - nb;
-        if (cols > 0) {
-            float* P = Gjj + nb;
-            trsm_panel_kernel<<<sd_div_up(cols, 128), 128, (size_t)nb * (nb + 1) * 4 + (size_t)nb * 128 * 4, ctx->stream>>>(Gjj, ldg, nb, P, ldg, cols);
-            SD_LAUNCH_CHECK(ctx, "trsm_panel_kernel");
-            const int rest = D - j - nb;
-            if (rest > 0) {
-                // [G22 | R2] -= U12^T [U12 | Y1]
-                int rc = sd_syrk_update(ctx, P, ldg, nb, rest, cols, G + (int64_t)(j + nb) * ldg + (j + nb), ldg, -1.0f, 1.0f);
-                if (rc) return rc;
-            }
+    // Two 128-blocks form one 256-row panel so that the trailing SYRK (the part that streams the whole
+    // trailing matrix through HBM) runs with K = 256 and half as often:
+    //   A11 = U11^T U11 ; P1 = U11^-T [A12 | rest] ; A22 -= P1(:,A12)^T P1 ; A22 = U22^T U22 ;
+    //   P2 = U22^-T [rest of block row 2] ; trailing -= [P1;P2]^T [P1;P2]
+    auto copy_rows = [&](const float* src, int64_t lds_, int rows, int cols_, float* dst, int64_t ldd_) -> int {
+        if (rows <= 0 || cols_ <= 0) return SD_OK;
+        const int cb = sd_div_up((int64_t)rows * cols_, 256) > 2048 ? 2048 : sd_div_up((int64_t)rows * cols_, 256);
+        copy_block_kernel<<<cb, 256, 0, ctx->stream>>>(src, lds_, rows, cols_, dst, ldd_);
+        SD_LAUNCH_CHECK(ctx, "copy_block_kernel");
+        return SD_OK;
+    };
+    float* panel2 = panel + (size_t)PB * ldp;                      // second 128 rows of the panel buffer
+    for (int b = 0; b < nblocks; b += 2) {
+        const int j = b * kCholNb;
+        const int nb1 = (D - j < kCholNb) ? D - j : kCholNb;
+        const int nb2 = (b + 1 < nblocks) ? ((D - j - nb1 < kCholNb) ? D - j - nb1 : kCholNb) : 0;
+        float* G11 = G + (int64_t)j * ldg + j;
+        float* W1 = inv + (size_t)b * 2 * PB * PB;
+        potrf_inv_kernel<<<1, 256, smem_potrf, ctx->stream>>>(G11, ldg, nb1, W1, W1 + PB * PB, status);
+        SD_LAUNCH_CHECK(ctx, "potrf_inv_kernel");
+        const int cols1 = W_ - j - nb1;                            // columns right of the first diagonal block
+        if (cols1 <= 0) continue;
+        // P1 = U11^-T * G(j : j+nb1, j+nb1 : ) as a GEMM with W1^T, out of place, then copied back into G
+        int rc = launch_gemm_nn(ctx, W1 + PB * PB, PB, nb1, nb1, G11 + nb1, ldg, cols1, panel, ldp, 1.0f, 0.0f, ep);
+        if (rc) return rc;
+        rc = copy_rows(panel, ldp, nb1, cols1, G11 + nb1, ldg);
+        if (rc) return rc;
+        if (nb2 <= 0) continue;                                    // (only right-hand sides were right of the last block)
+        // block row 2 of this panel gets the rank-nb1 update:  G(j2 : j2+nb2, j2 : ) -= P1(:, 0:nb2)^T P1
+        const int j2 = j + nb1;
+        float* G22 = G + (int64_t)j2 * ldg + j2;
+        rc = sd_syrk_update(ctx, panel, ldp, nb1, nb2, cols1, G22, ldg, -1.0f, 1.0f);
+        if (rc) return rc;
+        float* W2 = inv + (size_t)(b + 1) * 2 * PB * PB;
+        potrf_inv_kernel<<<1, 256, smem_potrf, ctx->stream>>>(G22, ldg, nb2, W2, W2 + PB * PB, status);
+        SD_LAUNCH_CHECK(ctx, "potrf_inv_kernel");
+        const int cols2 = cols1 - nb2;                             // columns right of the second diagonal block
+        if (cols2 <= 0) continue;
+        // P2 = U22^-T * G(j2 : j2+nb2, j2+nb2 : ), stored under P1's matching columns in the panel buffer
+        rc = launch_gemm_nn(ctx, W2 + PB * PB, PB, nb2, nb2, G22 + nb2, ldg, cols2, panel2 + nb2, ldp, 1.0f, 0.0f, ep);
+        if (rc) return rc;
+        rc = copy_rows(panel2 + nb2, ldp, nb2, cols2, G22 + nb2, ldg);
+        if (rc) return rc;
+        const int rest = D - j2 - nb2;
+        if (rest > 0) {
+            // [G33 | R3] -= [P1;P2]^T [P1;P2]   (K = nb1 + nb2 rows of the panel buffer, columns from nb2 on)
+            rc = sd_syrk_update(ctx, panel + nb2, ldp, nb1 + nb2, rest, cols2, G + (int64_t)(j2 + nb2) * ldg + (j2 + nb2), ldg, -1.0f, 1.0f);
+            if (rc) return rc;
         }
     }
     SD_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));   // end of "Decomposition"
     // ---- back substitution U X = Y, right-looking over block columns from the last ----
-    const int nblocks = sd_div_up(D, kCholNb);
-    GemmEpilogue ep;
-    memset(&ep, 0, sizeof(ep));
     for (int b = nblocks - 1; b >= 0; --b) {
         const int j = b * kCholNb;
         const int nb = (D - j < kCholNb) ? D - j : kCholNb;
+        const float* Wb = inv + (size_t)b * 2 * PB * PB;
         float* Yj = G + (int64_t)j * ldg + D;
-        trsv_block_kernel<<<1, 256, (size_t)nb * (nb + 1) * 4 + (size_t)nb * 64 * 4, ctx->stream>>>(G + (int64_t)j * ldg + j, ldg, nb, Yj, ldg, M);
-        SD_LAUNCH_CHECK(ctx, "trsv_block_kernel");
+        float* Xj = X + (int64_t)j * M;
+        int rc = launch_gemm_nn(ctx, Wb, PB, nb, nb, Yj, ldg, M, Xj, M, 1.0f, 0.0f, ep);     // X_j = U_jj^-1 Y_j
+        if (rc) return rc;
         if (j > 0) {
-            // Y[0:j] -= U[0:j, j:j+nb] * X_j
-            int rc = launch_gemm_nn(ctx, G + j, ldg, j, nb, Yj, ldg, M, G + D, ldg, -1.0f, 1.0f, ep);
+            rc = launch_gemm_nn(ctx, G + j, ldg, j, nb, Xj, M, M, G + D, ldg, -1.0f, 1.0f, ep);   // Y[0:j] -= U[0:j, j:j+nb] X_j
             if (rc) return rc;
         }
     }
-    copy_block_kernel<<<sd_div_up((int64_t)D * M, 256) > 1024 ? 1024 : sd_div_up((int64_t)D * M, 256), 256, 0, ctx->stream>>>(G + D, ldg, D, M, X, M);
-    SD_LAUNCH_CHECK(ctx, "copy_block_kernel");
     return SD_OK;
 }
 

@@ -511,29 +511,7 @@ static int detect_host_roi(sd_ctx* ctx, const sd_model* m, const uint8_t* h_imag
     for (size_t c = 0; c + 1 < chunk_first.size(); ++c, buf ^= 1) {
         const int first = chunk_first[c], n = chunk_first[c + 1] - first;
         SD_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->stage_done[buf], 0));   // also orders the table uploads before the first gather
-        if (ctx->roi_mode == 1) {
-            // DMA engines: one strided copy per face, submitted as a single batch
-            std::vector<cudaMemcpy3DBatchOp> ops(n);
-            for (int f = 0; f < n; ++f) {
-                const sd_roi& r = rois[first + f];
-                cudaMemcpy3DBatchOp op;
-                memset(&op, 0, sizeof(op));
-                op.src.type = cudaMemcpyOperandTypePointer;
-                op.src.op.ptr.ptr = const_cast<uint8_t*>(h_images) + (size_t)(first + f) * frame_bytes + (size_t)r.y * row_stride + r.x;
-                op.src.op.ptr.rowLength = (size_t)row_stride;
-                op.src.op.ptr.layerHeight = 0;
-                op.dst.type = cudaMemcpyOperandTypePointer;
-                op.dst.op.ptr.ptr = (uint8_t*)ctx->d_stage[buf] + r.offset;
-                op.dst.op.ptr.rowLength = (size_t)r.row_stride;
-                op.dst.op.ptr.layerHeight = 0;
-                op.extent = make_cudaExtent((size_t)r.row_stride, (size_t)r.h, 1);
-                op.srcAccessOrder = cudaMemcpySrcAccessOrderStream;
-                op.flags = 0;
-                ops[f] = op;
-            }
-            size_t fail = 0;
-            SD_CUDA(ctx, cudaMemcpy3DBatchAsync((size_t)n, ops.data(), &fail, 0, ctx->copy_stream));
-        } else {
+        {
             const int blocks = n < 8 * ctx->sm_count ? n : 8 * ctx->sm_count;
             roi_gather_kernel<<<blocks, 256, 0, ctx->copy_stream>>>(d_alias, (long long)frame_bytes, row_stride, d_roi, first, n, (uint8_t*)ctx->d_stage[buf]);
             SD_LAUNCH_CHECK(ctx, "roi_gather_kernel");
