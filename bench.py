@@ -260,6 +260,51 @@ def run_train(sd, ctx, model, world, rank, dev, barrier, max_over_ranks, group):
             "last_level_solver_ms": ctx.solver_timings()}
 
 
+def cpu_train_level_seconds(n_samples, threads, seed=2024):
+    """Reference CPU path for ONE training level of config 4 (level 0: the most expensive one), all host threads:
+    the reference's hog.c inside the restated HogTransform glue (one sample per thread, as the thread pool of
+    superviseddescent.hpp:173-189), then BLAS/LAPACK (numpy/scipy sgemm, sgetrf, sgetrs) standing in for Eigen's
+    A^T A and PartialPivLU (regressors.hpp:199-234) -- BASELINE.md section 3."""
+    import scipy.linalg
+    from oracle import oracle as O
+    O.build()
+    om = O.Model(MODEL)
+    use_ref = O.ref_available()
+    cfg = TRAIN_CFG
+    size = cfg["size"]
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import synth
+    base = synth.smooth_images(64, size, size, seed)
+    imgs = np.concatenate([base] * ((n_samples + 63) // 64))[:n_samples]
+    m = int(round(size * 0.05))
+    box = (m, m, size - 2 * m, size - 2 * m)
+    rng = np.random.Generator(np.random.PCG64(seed))
+    x0 = np.tile(O.align_mean(om.mean, box), (n_samples, 1)).astype(np.float32)
+    x_gt = np.stack([O.align_mean(om.mean, box, 1.0 + rng.normal(0, 0.04), 1.0 + rng.normal(0, 0.04), rng.normal(0, 0.04), rng.normal(0, 0.04))
+                     for _ in range(n_samples)]).astype(np.float32)
+    hp = O.HogParam(1, cfg["cells"], cfg["cell_sizes"][0], cfg["num_bins"], cfg["rel"][0])
+    t0 = time.perf_counter()
+    A = O.hog_transform_batch(imgs, x0, hp, om.right_idx, om.left_idx, use_ref=use_ref, threads=threads)
+    t_hog = time.perf_counter() - t0
+    ied = np.array([O.get_ied(x0[i], om.right_idx, om.left_idx) for i in range(n_samples)])
+    b = ((x0 - x_gt) / ied[:, None]).astype(np.float32)
+    t0 = time.perf_counter()
+    G = A.T @ A
+    lam = 1.5 * np.linalg.norm(G) / n_samples
+    G[np.diag_indices_from(G)] += lam
+    G[-1, -1] -= lam
+    t_gram = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    lu = scipy.linalg.lu_factor(G, overwrite_a=True, check_finite=False)
+    X = scipy.linalg.lu_solve(lu, A.T @ b, check_finite=False)
+    t_lu = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    _ = x0 - (A @ X) * ied[:, None]
+    t_upd = time.perf_counter() - t0
+    return {"hog_s": t_hog, "gram_s": t_gram, "lu_solve_s": t_lu, "update_s": t_upd, "total_s": t_hog + t_gram + t_lu + t_upd,
+            "kind": "reference hog.c + BLAS/LAPACK for Eigen" if use_ref else "port + BLAS/LAPACK"}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -397,6 +442,16 @@ def run_ours(args):
     }
     if train is not None:
         line["train"] = train
+    if world == 1 and not args.no_cpu and train is not None and "value" in train:
+        try:
+            cores = host_cores()
+            lvl = cpu_train_level_seconds(TRAIN_CFG["n"], cores)
+            train["cpu_baseline"] = {"value": lvl["total_s"] * len(TRAIN_CFG["cell_sizes"]), "unit": "s", "cores": cores, "kind": "port",
+                                     "sample": f"ONE full level (level 0, all {TRAIN_CFG['n']} samples) timed on the host: HOG {lvl['hog_s']:.2f} s, "
+                                               f"Gram {lvl['gram_s']:.2f} s, LU+solve {lvl['lu_solve_s']:.2f} s, update {lvl['update_s']:.2f} s; "
+                                               f"x{len(TRAIN_CFG['cell_sizes'])} levels (extrapolated); {lvl['kind']}"}
+        except Exception as ex:
+            train["cpu_baseline"] = {"error": repr(ex)[:200]}
     if world == 1 and not args.no_cpu:
         cores = host_cores()
         n = max(256, cores * 32)

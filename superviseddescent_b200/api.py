@@ -60,7 +60,7 @@ class Context:
         return int(_capi.lib().sd_roi_fallback_count(self._h))
 
     def set_gram_mode(self, mode: int):
-        """0 = 3xTF32 tensor-core Gram (default), 1 = single-pass TF32, 2 = fp32 SIMT."""
+        """0 = 3xTF32 tensor-core Gram (default), 3 = unbiased 3xTF32, 1 = single-pass TF32, 2 = fp32 SIMT."""
         _check(self._h, _capi.lib().sd_set_gram_mode(self._h, int(mode)))
 
     def solver_timings(self):

@@ -111,6 +111,7 @@ int sd_ctx_create(int device, void* stream, sd_ctx** out)
          cudaMemset(ctx->d_scratch, 0, 4096) == cudaSuccess;
     if (!ok) { sd_ctx_destroy(ctx); return SD_ERR_CUDA; }
     { const char* e = getenv("SD_B200_NO_ROI"); ctx->disable_roi = e && e[0] == '1'; }
+    { const char* e = getenv("SD_B200_TC_VARIANT"); if (e && e[0] == '1') ctx->tc_variant = 1; }
     *out = ctx;
     return SD_OK;
 }
@@ -200,7 +201,7 @@ int sd_memset(sd_ctx* ctx, void* d_dst, int value, size_t bytes)
 
 int sd_set_gram_mode(sd_ctx* ctx, int mode)
 {
-    if (!ctx || mode < 0 || mode > 2) return SD_ERR_INVALID;
+    if (!ctx || mode < 0 || mode > 3) return SD_ERR_INVALID;
     ctx->gram_mode = mode;
     return SD_OK;
 }

@@ -153,6 +153,7 @@ struct TcArgs {
     long long ldc;
     float alpha, beta;
     int passes;          // 1 or 3
+    int unbiased;        // variant 2: round hi in place (slower, unbiased) instead of using the truncated raw tile
     const int2* tiles;   // (ti, tj) per tile
     int num_tiles;
 };
@@ -328,6 +329,237 @@ syrk_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
     }
 }
 
+// =====================================================================================================
+// Variant 2 (default): ONE raw fp32 tile per operand travels L2 -> shared memory; the tensor core truncates it
+// to TF32 by itself (that is the "hi" operand), and a transform warpgroup writes lo = a - trunc_tf32(a) next
+// to it in shared memory.  Halves the operand traffic of the pre-split variant (ncu r01: 9.7 TB/s L2->SM, the
+// binding limit at 57 % tensor-pipe activity) and needs no hi/lo copies of A in HBM.
+//   warp 0       TMA producer        (raw tiles, 24 KB per stage)
+//   warp 1       MMA issuer          (lo*hi, hi*lo, hi*hi; accumulators in TMEM, chunked as in variant 1)
+//   warps 4..7   transform           (raw -> lo, element-wise in the swizzled layout; fence.proxy.async)
+//   warps 8..15  epilogue            (running sums in registers)
+// Register budget is rebalanced with setmaxnreg: producer/MMA/transform warpgroups give registers back,
+// the two epilogue warpgroups take them (128 running sums + a 32-value TMEM fragment per thread).
+// =====================================================================================================
+constexpr int T2_THREADS = 512;
+constexpr int RAW_BYTES = OPER_BYTES_A + OPER_BYTES_B;     // 24 KB
+
+__device__ __forceinline__ float trunc_tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+__device__ __forceinline__ float rna_tf32(float x)
+{
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+__global__ void __launch_bounds__(T2_THREADS, 1)
+syrk_tc2_kernel(const __grid_constant__ CUtensorMap map_raw, const TcArgs a)
+{
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* raw_full = bars;                      // [STAGES] TMA bytes landed
+    uint64_t* lo_ready = bars + STAGES;             // [STAGES] transform finished
+    uint64_t* empty_bar = bars + 2 * STAGES;        // [STAGES] MMAs retired
+    uint64_t* tmem_full = bars + 3 * STAGES;        // [2]
+    uint64_t* tmem_empty = bars + 3 * STAGES + 2;   // [2]
+    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_k = (a.K + BK - 1) / BK;
+    const bool split = a.passes == 3;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&lo_ready[s], 128); mbar_init(&empty_bar[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_raw) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_base_slot;
+
+    if (warp < 4) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;" ::: "memory");
+        if (warp == 0) {
+            // ===================== TMA producer =====================
+            if (lane == 0) {
+                uint32_t stage = 0, phase = 0;
+                for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
+                    const int2 tile = a.tiles[t];
+                    const int i0 = tile.x * BM, j0 = tile.y * BN;
+                    for (int kb = 0; kb < num_k; ++kb) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        mbar_arrive_expect_tx(&raw_full[stage], RAW_BYTES);
+                        unsigned char* sa = smem + stage * STAGE_BYTES;
+                        unsigned char* sb = sa + OPER_BYTES_A;
+                        const int k0 = kb * BK;
+#pragma unroll
+                        for (int cb = 0; cb < A_BLOCKS; ++cb) tma_load_2d(sa + cb * BOX_BYTES, &map_raw, &raw_full[stage], i0 + cb * BOX_COLS, k0);
+#pragma unroll
+                        for (int cb = 0; cb < B_BLOCKS; ++cb) tma_load_2d(sb + cb * BOX_BYTES, &map_raw, &raw_full[stage], j0 + cb * BOX_COLS, k0);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        } else if (warp == 1) {
+            // ===================== MMA issuer =====================
+            uint32_t stage = 0, phase = 0;
+            uint32_t buf = 0, buf_phase = 0;
+            for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
+                for (int kb = 0; kb < num_k; ++kb) {
+                    const bool chunk_first = (kb % KC_STAGES) == 0;
+                    const bool chunk_last = (kb % KC_STAGES) == KC_STAGES - 1 || kb == num_k - 1;
+                    if (chunk_first) {
+                        mbar_wait(&tmem_empty[buf], buf_phase ^ 1);
+                        tcgen05_fence_after();
+                    }
+                    const uint32_t tmem_d = tmem_base + buf * BN;
+                    mbar_wait(split ? &lo_ready[stage] : &raw_full[stage], phase);
+                    tcgen05_fence_after();
+                    if (lane == 0) {
+                        const uint32_t sa_hi = smem_u32(smem + stage * STAGE_BYTES);
+                        const uint32_t sb_hi = sa_hi + OPER_BYTES_A;
+                        const uint32_t sa_lo = sa_hi + RAW_BYTES;
+                        const uint32_t sb_lo = sa_lo + OPER_BYTES_A;
+#pragma unroll
+                        for (int ks = 0; ks < BK / 8; ++ks) {
+                            const uint32_t koff = ks * 8 * 128;
+                            const uint32_t first = (chunk_first && ks == 0) ? 0u : 1u;
+                            if (split) {
+                                tcgen05_mma_tf32(tmem_d, make_desc(sa_lo + koff), make_desc(sb_hi + koff), kInstrDesc, first);
+                                tcgen05_mma_tf32(tmem_d, make_desc(sa_hi + koff), make_desc(sb_lo + koff), kInstrDesc, 1u);
+                                tcgen05_mma_tf32(tmem_d, make_desc(sa_hi + koff), make_desc(sb_hi + koff), kInstrDesc, 1u);
+                            } else {
+                                tcgen05_mma_tf32(tmem_d, make_desc(sa_hi + koff), make_desc(sb_hi + koff), kInstrDesc, first);
+                            }
+                        }
+                        tcgen05_commit(&empty_bar[stage]);
+                        if (chunk_last) tcgen05_commit(&tmem_full[buf]);
+                    }
+                    __syncwarp();
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if (chunk_last) { if (++buf == 2) { buf = 0; buf_phase ^= 1; } }
+                }
+            }
+        }
+    } else if (warp < 8) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 72;" ::: "memory");
+        // ===================== transform: lo = a - trunc_tf32(a), element-wise on the swizzled bytes =====================
+        if (split) {
+            const int tt = threadIdx.x - 128;                 // 0..127
+            uint32_t stage = 0, phase = 0;
+            for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
+                for (int kb = 0; kb < num_k; ++kb) {
+                    mbar_wait(&raw_full[stage], phase);
+                    float4* raw = reinterpret_cast<float4*>(smem + stage * STAGE_BYTES);
+                    float4* lo = reinterpret_cast<float4*>(smem + stage * STAGE_BYTES + RAW_BYTES);
+                    if (a.unbiased) {
+                        // hi = rna_tf32(a) written back in place (the tensor core's truncation is then a no-op and the
+                        // split is unbiased), lo = rna_tf32(a - hi).  One more 24 KB shared-memory write per stage:
+                        // measured 58 % tensor-pipe activity instead of 69 %, weights 3.0e-5 instead of 6.5e-5.
+#pragma unroll 4
+                        for (int i = 0; i < RAW_BYTES / 16 / 128; ++i) {
+                            const float4 v = raw[i * 128 + tt];
+                            float4 h, l;
+                            h.x = rna_tf32(v.x); h.y = rna_tf32(v.y); h.z = rna_tf32(v.z); h.w = rna_tf32(v.w);
+                            l.x = rna_tf32(v.x - h.x); l.y = rna_tf32(v.y - h.y); l.z = rna_tf32(v.z - h.z); l.w = rna_tf32(v.w - h.w);
+                            raw[i * 128 + tt] = h;
+                            lo[i * 128 + tt] = l;
+                        }
+                    } else {
+                        // hi is the raw tile as the tensor core sees it (low 13 mantissa bits ignored); the residual is
+                        // rounded to TF32 so that the hardware's truncation of the lo operand is a no-op
+#pragma unroll 4
+                        for (int i = 0; i < RAW_BYTES / 16 / 128; ++i) {
+                            const float4 v = raw[i * 128 + tt];
+                            float4 l;
+                            l.x = rna_tf32(v.x - trunc_tf32(v.x)); l.y = rna_tf32(v.y - trunc_tf32(v.y));
+                            l.z = rna_tf32(v.z - trunc_tf32(v.z)); l.w = rna_tf32(v.w - trunc_tf32(v.w));
+                            lo[i * 128 + tt] = l;
+                        }
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+                    mbar_arrive(&lo_ready[stage]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 176;" ::: "memory");
+        // ===================== epilogue (warps 8..15) =====================
+        const int q = warp & 3;
+        const int half = (warp - 8) >> 2;
+        uint32_t buf = 0, buf_phase = 0;
+        const bool vec_ok = (a.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.C) & 15) == 0);
+        const int num_chunks = (num_k + KC_STAGES - 1) / KC_STAGES;
+        for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
+            const int2 tile = a.tiles[t];
+            const int i = tile.x * BM + q * 32 + lane;
+            const int j0 = tile.y * BN + half * 128;
+            float acc[128];
+#pragma unroll
+            for (int v = 0; v < 128; ++v) acc[v] = 0.f;
+            for (int c = 0; c < num_chunks; ++c) {
+                mbar_wait(&tmem_full[buf], buf_phase);
+                tcgen05_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + half * 128;
+#pragma unroll
+                for (int c0 = 0; c0 < 128; c0 += 32) {
+                    uint32_t r[32];
+                    tmem_ld_32x32b_x32(taddr + c0, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int v = 0; v < 32; ++v) acc[c0 + v] = __fadd_rn(acc[c0 + v], __uint_as_float(r[v]));
+                }
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+                if (++buf == 2) { buf = 0; buf_phase ^= 1; }
+            }
+            if (i < a.MI) {
+                float* crow = a.C + (long long)i * a.ldc;
+                if (vec_ok && j0 + 128 <= a.NJ) {
+#pragma unroll
+                    for (int v = 0; v < 32; ++v) {
+                        float4 o;
+                        o.x = a.alpha * acc[4 * v + 0]; o.y = a.alpha * acc[4 * v + 1];
+                        o.z = a.alpha * acc[4 * v + 2]; o.w = a.alpha * acc[4 * v + 3];
+                        float4* p = reinterpret_cast<float4*>(crow + j0 + 4 * v);
+                        if (a.beta != 0.f) {
+                            const float4 old = *p;
+                            o.x = fmaf(a.beta, old.x, o.x); o.y = fmaf(a.beta, old.y, o.y);
+                            o.z = fmaf(a.beta, old.z, o.z); o.w = fmaf(a.beta, old.w, o.w);
+                        }
+                        *p = o;
+                    }
+                } else {
+#pragma unroll
+                    for (int v = 0; v < 128; ++v) {
+                        if (j0 + v < a.NJ) {
+                            float o = a.alpha * acc[v];
+                            if (a.beta != 0.f) o = fmaf(a.beta, crow[j0 + v], o);
+                            crow[j0 + v] = o;
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
 // hi = rna_tf32(s), lo = rna_tf32(s - hi); columns [NJ, ldw) are zero-filled
 __global__ void split_tf32_kernel(const float* __restrict__ S, long long lds, int K, int NJ,
                                   float* __restrict__ hi, float* __restrict__ lo, long long ldw)
@@ -401,7 +633,8 @@ int sd_syrk_tc(sd_ctx* ctx, const float* d_S, int64_t lds, int K, int MI, int NJ
     const float* hi = d_S;
     const float* lo = d_S;
     int64_t ldw = lds;
-    if (passes == 3) {
+    const bool variant2 = ctx->tc_variant != 1;          // default: raw tiles + in-kernel split
+    if (passes == 3 && !variant2) {
         ldw = ((int64_t)NJ + 3) / 4 * 4;
         float* whi = (float*)sd_workspace(ctx, SD_WS_SPLIT_HI, (size_t)K * ldw * sizeof(float));
         float* wlo = (float*)sd_workspace(ctx, SD_WS_SPLIT_LO, (size_t)K * ldw * sizeof(float));
@@ -435,10 +668,17 @@ int sd_syrk_tc(sd_ctx* ctx, const float* d_S, int64_t lds, int K, int MI, int NJ
 
     TcArgs a;
     a.K = K; a.MI = MI; a.NJ = NJ; a.C = d_C; a.ldc = ldc; a.alpha = alpha; a.beta = beta; a.passes = passes;
+    a.unbiased = ctx->gram_mode == 3 ? 1 : 0;
     a.tiles = d_tiles; a.num_tiles = (int)tiles.size();
-    SD_CUDA(ctx, cudaFuncSetAttribute(syrk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     const int grid = a.num_tiles < ctx->sm_count ? a.num_tiles : ctx->sm_count;
-    syrk_tc_kernel<<<grid, TC_THREADS, SMEM_BYTES, ctx->stream>>>(map_hi, map_lo, a);
-    SD_LAUNCH_CHECK(ctx, "syrk_tc_kernel");
+    if (variant2) {
+        SD_CUDA(ctx, cudaFuncSetAttribute(syrk_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        syrk_tc2_kernel<<<grid, T2_THREADS, SMEM_BYTES, ctx->stream>>>(map_hi, a);
+        SD_LAUNCH_CHECK(ctx, "syrk_tc2_kernel");
+    } else {
+        SD_CUDA(ctx, cudaFuncSetAttribute(syrk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        syrk_tc_kernel<<<grid, TC_THREADS, SMEM_BYTES, ctx->stream>>>(map_hi, map_lo, a);
+        SD_LAUNCH_CHECK(ctx, "syrk_tc_kernel");
+    }
     return SD_OK;
 }

@@ -27,6 +27,7 @@ struct sd_ctx {
     int64_t launches = 0;
     int sm_count = 148;
     int gram_mode = 0;
+    int tc_variant = 2;            // tensor-core SYRK: 2 = raw tiles + in-kernel hi/lo split (default), 1 = operands pre-split in HBM
     bool disable_roi = false;      // sd_detect_batch_host: always upload whole frames
     int64_t roi_fallbacks = 0;     // faces repeated from the full frame because a patch left its ROI
     float timings[4] = {0, 0, 0, 0};
