@@ -444,60 +444,57 @@ __global__ void copy_block_kernel(const float* __restrict__ src, long long lds, 
 
 // ---- blocked Cholesky G = U^T U (upper), right-looking ---------------------------------------------
 // One CTA factors a 128 x 128 diagonal block and inverts the factor.  Inner blocking by 32: the 32 x 32
-// diagonal sub-block is factored and inverted by ONE WARP IN REGISTERS (lane j owns column j, rows are
-// exchanged with shuffles: ~500 shfl+fma each, no shared-memory round trips on the dependent chain), the
-// row panel and the trailing update inside the block are small GEMMs by all 8 warps.  Outputs: U (in place
-// in G), W = U^-1 and W^T (workspace) -- so that the panel solve U12 = U11^-T G12 and the back substitution
-// X_j = U_jj^-1 Y_j become plain GEMMs.  Blocks narrower than 128 are padded with the identity.
+// diagonal sub-block is factored AND inverted by one warp in the same 32 left-looking steps (potrf32_warp), the
+// row panel and the trailing update inside the block are small register-tiled GEMMs by all 8 warps.  Outputs:
+// U (in place in G), W = U^-1 and W^T (workspace) -- so that the panel solve U12 = U11^-T G12 and the back
+// substitution X_j = U_jj^-1 Y_j become plain GEMMs.  Blocks narrower than 128 are padded with the identity.
+// Phase timings (clock64, -DSD_PROFILE_POTRF + tools_potrf_prof.py): 369k cycles before the restructuring
+// (4 x 65k in the single-warp phases), 146k after (load 10k, 4 x 21k potrf32, panels 8k, trailing 10k, W 28k, store 5k).
 constexpr int PB = 128, PS = 32, PLD = PB + 1;
+#ifdef SD_PROFILE_POTRF
+__device__ long long sd_dbg_clk[64];
+#define SD_CLK(i) do { __syncthreads(); if (threadIdx.x == 0) sd_dbg_clk[i] = clock64(); } while (0)
+#else
+#define SD_CLK(i) do {} while (0)
+#endif
 
 // Factor and invert the 32 x 32 diagonal sub-block at (k0, k0) of sA with ONE warp (lane j owns column j).
-// Rolled loops on shared memory with broadcast reads: the fully unrolled register/shuffle variant was measured
-// at 0.21 ms per 128-block -- its ~50 KB of straight-line code thrashes the instruction cache of a lone warp.
+// Rolled loops on shared memory with broadcast reads: a fully unrolled register/shuffle variant was measured no
+// faster -- its ~50 KB of straight-line code thrashes the instruction cache of a lone warp.
 __device__ __forceinline__ void potrf32_warp(float* sA, float* sT, int k0, int lane, bool& bad)
 {
+    // One warp factors the 32 x 32 diagonal sub-block D = U^T U in place (upper) and, in the same 32 steps, builds
+    // T = U^-1 by carrying the identity along: the row operations that turn A into U turn I into U^-T.
+    //   row k of U    = (row k of A - sum_{q<k} U[q][k] * U[q][:])    / U[k][k]
+    //   row k of U^-T = (e_k        - sum_{q<k} U[q][k] * U^-T[q][:]) / U[k][k]
+    // Left-looking, so the dot products have no read-modify-write through shared memory and their loads overlap.
+    // Lane j owns column j; U^-T[k][j] = T[j][k] is kept at sT[j * (PS+1) + k] (conflict-free for both accesses).
     float* D = sA + k0 * PLD + k0;                 // D[i][j] at D[i * PLD + j]
+    float* E = sT + lane * (PS + 1);               // E[q] = U^-T[q][lane]
     for (int k = 0; k < PS; ++k) {
-        __syncwarp();                               // row k was last written by the previous step's update
-        const float pk = D[k * PLD + k];
+        float s[4] = {0.f, 0.f, 0.f, 0.f}, e[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int q = 0; q < k; q += 4) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const bool in = q + u < k;
+                const float c = in ? D[(q + u) * PLD + k] : 0.f;
+                const float dv = in ? D[(q + u) * PLD + lane] : 0.f;
+                const float ev = in ? E[q + u] : 0.f;
+                s[u] = fmaf(c, dv, s[u]);
+                e[u] = fmaf(c, ev, e[u]);
+            }
+        }
+        const float a = D[k * PLD + lane] - ((s[0] + s[1]) + (s[2] + s[3]));
+        const float w = (lane == k ? 1.f : 0.f) - ((e[0] + e[1]) + (e[2] + e[3]));
+        const float pk = __shfl_sync(0xffffffffu, a, k);
         if (!(pk > 0.f)) bad = true;
-        const float d = sqrtf(pk > 0.f ? pk : 1.f);
-        const float inv = 1.0f / d;
-        __syncwarp();
-        float ukj = 0.f;
-        if (lane >= k) {
-            ukj = (lane == k) ? d : D[k * PLD + lane] * inv;
-            D[k * PLD + lane] = ukj;
-        }
-        __syncwarp();
-        // rows k+1..31: independent read-modify-writes, unrolled so that their shared-memory latencies overlap
-#pragma unroll 8
-        for (int i = k + 1; i < PS; ++i) {
-            const float uki = D[k * PLD + i];
-            if (lane >= i) D[i * PLD + lane] = fmaf(-uki, ukj, D[i * PLD + lane]);
-        }
-    }
-    __syncwarp();
-    if (lane > 0)                                   // clear the strict lower triangle of this sub-block (column `lane`... row-wise)
-        for (int j = 0; j < lane; ++j) D[lane * PLD + j] = 0.f;
-    __syncwarp();
-    // T = D^-1 (upper): lane j solves U t = e_j by back substitution; T[i][j] kept in sT[i * (PS+1) + j]
-    for (int i = PS - 1; i >= 0; --i) {
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-        int k = i + 1;
-        for (; k + 3 < PS; k += 4) {
-            s0 = fmaf(D[i * PLD + k], sT[k * (PS + 1) + lane], s0);
-            s1 = fmaf(D[i * PLD + k + 1], sT[(k + 1) * (PS + 1) + lane], s1);
-            s2 = fmaf(D[i * PLD + k + 2], sT[(k + 2) * (PS + 1) + lane], s2);
-            s3 = fmaf(D[i * PLD + k + 3], sT[(k + 3) * (PS + 1) + lane], s3);
-        }
-        for (; k < PS; ++k) s0 = fmaf(D[i * PLD + k], sT[k * (PS + 1) + lane], s0);
-        const float sum = (s0 + s1) + (s2 + s3);
-        __syncwarp();
-        sT[i * (PS + 1) + lane] = (lane >= i) ? ((lane == i ? 1.f : 0.f) - sum) / D[i * PLD + i] : 0.f;
+        const float pks = pk > 0.f ? pk : 1.f;
+        float inv = rsqrtf(pks);                                  // MUFU + one Newton step instead of sqrt and divide
+        inv = inv * fmaf(-0.5f * pks * inv, inv, 1.5f);
+        if (lane >= k) D[k * PLD + lane] = (lane == k) ? pks * inv : a * inv;
+        E[k] = w * inv;                                           // exactly 0 for lane > k
         __syncwarp();
     }
-    __syncwarp();
 }
 
 __global__ void __launch_bounds__(256) potrf_inv_kernel(float* __restrict__ G, long long ldg, int nb,
@@ -508,15 +505,27 @@ __global__ void __launch_bounds__(256) potrf_inv_kernel(float* __restrict__ G, l
     float* sW = sm + PB * PLD;         // PB x PLD : U^-1
     float* sT = sW + PB * PLD;         // PS x (PS+1) scratch (inverse of the current diagonal sub-block / partial sums)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int idx = tid; idx < PB * PB; idx += 256) {
-        const int i = idx >> 7, j = idx & (PB - 1);
-        float v = 0.f;
-        if (i < nb && j < nb) v = (j >= i) ? G[(long long)i * ldg + j] : 0.f;
-        else if (i == j) v = 1.f;                       // identity padding
-        sA[i * PLD + j] = v;
-        sW[i * PLD + j] = 0.f;
+    SD_CLK(0);
+#pragma unroll 1
+    for (int base = 0; base < PB * PB; base += 256 * 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {                             // 8 independent global loads in flight per thread
+            const int idx = base + u * 256 + tid;
+            const int i = idx >> 7, j = idx & (PB - 1);
+            v[u] = (i == j) ? 1.f : 0.f;                          // identity padding outside nb
+            if (i < nb && j < nb) v[u] = (j >= i) ? G[(long long)i * ldg + j] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int idx = base + u * 256 + tid;
+            const int i = idx >> 7, j = idx & (PB - 1);
+            sA[i * PLD + j] = v[u];
+            sW[i * PLD + j] = 0.f;
+        }
     }
     __syncthreads();
+    SD_CLK(1);
     for (int kb = 0; kb < PB / PS; ++kb) {
         const int k0 = kb * PS;
         if (warp == 0) {
@@ -526,23 +535,27 @@ __global__ void __launch_bounds__(256) potrf_inv_kernel(float* __restrict__ G, l
             for (int i = 0; i < PS; ++i) sW[(k0 + i) * PLD + k0 + lane] = sT[i * (PS + 1) + lane];
         }
         __syncthreads();
+        SD_CLK(2 + kb * 3);
         const int ncols = PB - k0 - PS;                                  // columns right of the diagonal sub-block
         if (ncols > 0) {
             // row panel: U12 = T^T * A12   (T = inverse of the diagonal sub-block)
             float out[3][4];
 #pragma unroll
-            for (int cc = 0; cc < 3; ++cc) {
-                if (cc * 32 < ncols) {
-                    const int c = k0 + PS + cc * 32 + lane;
+            for (int cc = 0; cc < 3; ++cc)
 #pragma unroll
-                    for (int m = 0; m < 4; ++m) {
-                        const int r = warp + 8 * m;
-                        float acc = 0.f;
-#pragma unroll 8
-                        for (int q = 0; q <= r; ++q) acc = fmaf(sT[q * (PS + 1) + r], sA[(k0 + q) * PLD + c], acc);   // T[q][r] = 0 for q > r
-                        out[cc][m] = acc;
-                    }
-                }
+                for (int m = 0; m < 4; ++m) out[cc][m] = 0.f;
+            const int ncc = ncols >> 5;
+#pragma unroll 4
+            for (int q = 0; q < PS; ++q) {                        // T[q][r] = 0 for q > r, so the full range is exact
+                float t[4], av[3];
+#pragma unroll
+                for (int m = 0; m < 4; ++m) t[m] = sT[q * (PS + 1) + warp + 8 * m];
+#pragma unroll
+                for (int cc = 0; cc < 3; ++cc) av[cc] = (cc < ncc) ? sA[(k0 + q) * PLD + k0 + PS + cc * 32 + lane] : 0.f;
+#pragma unroll
+                for (int cc = 0; cc < 3; ++cc)
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) out[cc][m] = fmaf(t[m], av[cc], out[cc][m]);
             }
             __syncthreads();
 #pragma unroll
@@ -553,32 +566,42 @@ __global__ void __launch_bounds__(256) potrf_inv_kernel(float* __restrict__ G, l
                     for (int m = 0; m < 4; ++m) sA[(k0 + warp + 8 * m) * PLD + c] = out[cc][m];
                 }
             __syncthreads();
+            SD_CLK(3 + kb * 3);
             // trailing update inside the block: A22 -= U12^T U12 (upper part)
-            for (int i = k0 + PS + warp; i < PB; i += 8) {
-                for (int j0 = (i & ~31); j0 < PB; j0 += 32) {
-                    const int j = j0 + lane;
-                    float acc = 0.f;
-#pragma unroll 8
-                    for (int q = 0; q < PS; ++q) acc = fmaf(sA[(k0 + q) * PLD + i], sA[(k0 + q) * PLD + j], acc);
-                    if (j >= i) sA[i * PLD + j] -= acc;
+            // work unit = 8 rows x 32 columns of one 32 x 32 tile (ti <= tj); 9 shared loads per 8 FMAs
+            const int nt = ncols >> 5, npairs = nt * (nt + 1) / 2;
+            for (int u = warp; u < npairs * 4; u += 8) {
+                int p = u >> 2, ti = 0;
+                while (p >= nt - ti) { p -= nt - ti; ++ti; }
+                const int tj = ti + p;
+                const int i0 = k0 + PS + ti * 32 + (u & 3) * 8, j = k0 + PS + tj * 32 + lane;
+                float acc[8];
+#pragma unroll
+                for (int m = 0; m < 8; ++m) acc[m] = 0.f;
+#pragma unroll 4
+                for (int q = 0; q < PS; ++q) {
+                    const float uj = sA[(k0 + q) * PLD + j];
+#pragma unroll
+                    for (int m = 0; m < 8; ++m) acc[m] = fmaf(sA[(k0 + q) * PLD + i0 + m], uj, acc[m]);
                 }
+#pragma unroll
+                for (int m = 0; m < 8; ++m)
+                    if (j >= i0 + m) sA[(i0 + m) * PLD + j] -= acc[m];
             }
             __syncthreads();
+            SD_CLK(4 + kb * 3);
         }
     }
+    SD_CLK(14);
     // off-diagonal blocks of W = U^-1:  W_ij = -T_i * sum_{k=i+1..j} U_ik W_kj   (block column by block column)
     for (int jb = 1; jb < PB / PS; ++jb) {
         for (int ib = jb - 1; ib >= 0; --ib) {
-            float part[4];
+            float part[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+            for (int kq = (ib + 1) * PS; kq < (jb + 1) * PS; ++kq) {         // 5 shared loads per 4 FMAs
+                const float w = sW[kq * PLD + jb * PS + lane];
 #pragma unroll
-            for (int m = 0; m < 4; ++m) {
-                const int r = warp + 8 * m;
-                float acc = 0.f;
-                for (int kbk = ib + 1; kbk <= jb; ++kbk)
-#pragma unroll 8
-                    for (int q = 0; q < PS; ++q)
-                        acc = fmaf(sA[(ib * PS + r) * PLD + kbk * PS + q], sW[(kbk * PS + q) * PLD + jb * PS + lane], acc);
-                part[m] = acc;
+                for (int m = 0; m < 4; ++m) part[m] = fmaf(sA[(ib * PS + warp + 8 * m) * PLD + kq], w, part[m]);
             }
 #pragma unroll
             for (int m = 0; m < 4; ++m) sT[(warp + 8 * m) * (PS + 1) + lane] = part[m];
@@ -597,13 +620,18 @@ __global__ void __launch_bounds__(256) potrf_inv_kernel(float* __restrict__ G, l
             __syncthreads();
         }
     }
+    SD_CLK(15);
     for (int idx = tid; idx < PB * PB; idx += 256) {
         const int i = idx >> 7, j = idx & (PB - 1);
         if (i < nb && j < nb && j >= i) G[(long long)i * ldg + j] = sA[i * PLD + j];
         W[idx] = sW[i * PLD + j];
         Wt[idx] = sW[j * PLD + i];
     }
+    SD_CLK(16);
 }
+#ifdef SD_PROFILE_POTRF
+extern "C" __attribute__((visibility("default"))) void sd_debug_read_clk(long long* out) { cudaMemcpyFromSymbol(out, sd_dbg_clk, sizeof(long long) * 64); }
+#endif
 
 int cholesky_solve(sd_ctx* ctx, float* G, int64_t ldg, int D, int M, float* X)
 {
