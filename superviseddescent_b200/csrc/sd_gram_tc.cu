@@ -156,6 +156,7 @@ struct TcArgs {
     int unbiased;        // variant 2: round hi in place (slower, unbiased) instead of using the truncated raw tile
     const int2* tiles;   // (ti, tj) per tile
     int num_tiles;
+    int tma_c;           // variant 2: 0 = register epilogue, 1 = TMA store (beta == 0), 2 = TMA reduce-add (beta == 1)
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -343,6 +344,8 @@ syrk_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
 // =====================================================================================================
 constexpr int T2_THREADS = 512;
 constexpr int RAW_BYTES = OPER_BYTES_A + OPER_BYTES_B;     // 24 KB
+constexpr int CBOX_BYTES = 32 * 32 * 4;                     // one 32 x 32 fp32 box of C per epilogue warp (128B-swizzled)
+constexpr int SMEM2_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 1024 /*barriers*/ + EPI_WARPS * CBOX_BYTES;
 
 __device__ __forceinline__ float trunc_tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 __device__ __forceinline__ float rna_tf32(float x)
@@ -353,7 +356,7 @@ __device__ __forceinline__ float rna_tf32(float x)
 }
 
 __global__ void __launch_bounds__(T2_THREADS, 1)
-syrk_tc2_kernel(const __grid_constant__ CUtensorMap map_raw, const TcArgs a)
+syrk_tc2_kernel(const __grid_constant__ CUtensorMap map_raw, const __grid_constant__ CUtensorMap map_c, const TcArgs a)
 {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -374,6 +377,7 @@ syrk_tc2_kernel(const __grid_constant__ CUtensorMap map_raw, const TcArgs a)
         for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_raw) : "memory");
+        if (a.tma_c) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c) : "memory");
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "r"(TMEM_COLS) : "memory");
@@ -522,9 +526,50 @@ syrk_tc2_kernel(const __grid_constant__ CUtensorMap map_raw, const TcArgs a)
                 if (lane == 0) mbar_arrive(&tmem_empty[buf]);
                 if (++buf == 2) { buf = 0; buf_phase ^= 1; }
             }
-            if (i < a.MI) {
+            if (a.tma_c) {
+                // Coalesced write-back through the TMA: the thread-per-row TMEM fragment would touch 32 different
+                // lines per store instruction (measured: the epilogue, not the MMAs, set the pace of K = 256 updates).
+                // Each warp stages 32 x 32 boxes in 128B-swizzled shared memory and one lane issues a bulk tensor
+                // store (beta == 0) or reduce-add (beta == 1, done in L2: C is never read by the SM).  Every element
+                // is touched once per launch, so the result is the single rounding of old + alpha * sum; rows and
+                // columns outside C are clipped by the tensor map.
+                unsigned char* box = smem + STAGES * STAGE_BYTES + 1024 + (warp - 8) * CBOX_BYTES;
+                const uint32_t box_u32 = smem_u32(box);
+#pragma unroll
+                for (int c0 = 0; c0 < 128; c0 += 32) {
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // box buffer free again
+                    __syncwarp();
+#pragma unroll
+                    for (int v = 0; v < 8; ++v) {
+                        const float4 o = make_float4(a.alpha * acc[c0 + 4 * v + 0], a.alpha * acc[c0 + 4 * v + 1],
+                                                     a.alpha * acc[c0 + 4 * v + 2], a.alpha * acc[c0 + 4 * v + 3]);
+                        *reinterpret_cast<float4*>(box + lane * 128 + ((v ^ (lane & 7)) << 4)) = o;
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        const int cx = j0 + c0, cy = tile.x * BM + q * 32;
+                        if (a.tma_c == 2)
+                            asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2}], [%3];"
+                                         ::"l"(&map_c), "r"(cx), "r"(cy), "r"(box_u32) : "memory");
+                        else
+                            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];"
+                                         ::"l"(&map_c), "r"(cx), "r"(cy), "r"(box_u32) : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                }
+            } else if (i < a.MI) {
                 float* crow = a.C + (long long)i * a.ldc;
-                if (vec_ok && j0 + 128 <= a.NJ) {
+                if (vec_ok && j0 + 128 <= a.NJ && a.beta == 1.f) {
+                    // C += alpha * sum as fire-and-forget vector reductions: no load of C, no round trip on the
+                    // epilogue's critical path.  Each element is touched once per launch, so the result is the
+                    // same single rounding as fmaf(1, old, alpha * sum) and is reproducible.
+#pragma unroll
+                    for (int v = 0; v < 32; ++v)
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(crow + j0 + 4 * v),
+                                     "f"(a.alpha * acc[4 * v + 0]), "f"(a.alpha * acc[4 * v + 1]),
+                                     "f"(a.alpha * acc[4 * v + 2]), "f"(a.alpha * acc[4 * v + 3]) : "memory");
+                } else if (vec_ok && j0 + 128 <= a.NJ) {
 #pragma unroll
                     for (int v = 0; v < 32; ++v) {
                         float4 o;
@@ -552,6 +597,7 @@ syrk_tc2_kernel(const __grid_constant__ CUtensorMap map_raw, const TcArgs a)
         }
     }
 
+    if (warp >= 8 && lane == 0 && a.tma_c) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // writes complete
     tcgen05_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -616,6 +662,21 @@ int make_map(sd_ctx* ctx, CUtensorMap* map, const float* base, int64_t ld, int r
     return SD_OK;
 }
 
+// C (rows x cols, pitch ld) as 32 x 32 boxes, 128B-swizzled in shared memory
+int make_map_c(sd_ctx* ctx, CUtensorMap* map, float* base, int64_t ld, int rows, int cols)
+{
+    PFN_encodeTiled enc = get_encode_fn();
+    if (!enc) return sd_fail(ctx, SD_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(float)};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return sd_fail(ctx, SD_ERR_CUDA, "cuTensorMapEncodeTiled (C) failed (%d)", (int)r);
+    return SD_OK;
+}
+
 }  // namespace
 
 bool sd_syrk_tc_supported(const float* d_S, int64_t lds, int K, int MI, int NJ, const float* d_C, int64_t ldc)
@@ -669,11 +730,20 @@ int sd_syrk_tc(sd_ctx* ctx, const float* d_S, int64_t lds, int K, int MI, int NJ
     TcArgs a;
     a.K = K; a.MI = MI; a.NJ = NJ; a.C = d_C; a.ldc = ldc; a.alpha = alpha; a.beta = beta; a.passes = passes;
     a.unbiased = ctx->gram_mode == 3 ? 1 : 0;
+    a.tma_c = 0;
     a.tiles = d_tiles; a.num_tiles = (int)tiles.size();
     const int grid = a.num_tiles < ctx->sm_count ? a.num_tiles : ctx->sm_count;
     if (variant2) {
-        SD_CUDA(ctx, cudaFuncSetAttribute(syrk_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        syrk_tc2_kernel<<<grid, T2_THREADS, SMEM_BYTES, ctx->stream>>>(map_hi, a);
+        // C goes back through the TMA when it can be described by a tensor map (16-byte aligned base and pitch)
+        CUtensorMap map_c = map_hi;
+        a.tma_c = 0;
+        if ((beta == 0.f || beta == 1.f) && (ldc % 4) == 0 && (reinterpret_cast<uintptr_t>(d_C) & 15) == 0 && !getenv("SD_B200_NO_TMA_C")) {
+            rc = make_map_c(ctx, &map_c, d_C, ldc, MI, NJ);
+            if (rc) return rc;
+            a.tma_c = beta == 1.f ? 2 : 1;
+        }
+        SD_CUDA(ctx, cudaFuncSetAttribute(syrk_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+        syrk_tc2_kernel<<<grid, T2_THREADS, SMEM2_BYTES, ctx->stream>>>(map_hi, map_c, a);
         SD_LAUNCH_CHECK(ctx, "syrk_tc2_kernel");
     } else {
         SD_CUDA(ctx, cudaFuncSetAttribute(syrk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));

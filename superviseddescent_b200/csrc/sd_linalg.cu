@@ -313,20 +313,25 @@ __global__ void subtract_kernel(float* __restrict__ A, long long lda, const floa
 
 // ---- regulariser (regressors.hpp:126-148) ---------------------------------------------------------
 // sum of squares of the full symmetric D x D matrix from its upper triangle, in double (cv::norm)
-__global__ void frob_upper_kernel(const float* __restrict__ G, long long ldg, int D, double* __restrict__ out)
+// Rows are dealt round-robin to the blocks (balanced triangle), a block's 1024 threads stride along the row with
+// four independent loads in flight each; fixed grid and fixed order, so the sum is reproducible.
+__global__ void __launch_bounds__(1024) frob_upper_kernel(const float* __restrict__ G, long long ldg, int D, double* __restrict__ out)
 {
-    double s = 0.0;
-    const long long total = (long long)D * D;
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-        const int i = (int)(idx / D), j = (int)(idx - (long long)i * D);
-        if (j < i) continue;
-        const double v = (double)G[(long long)i * ldg + j];
-        s += (j == i) ? v * v : 2.0 * v * v;
+    double s0 = 0.0, s1 = 0.0;
+    for (int i = blockIdx.x; i < D; i += gridDim.x) {
+        const float* row = G + (long long)i * ldg;
+        if (threadIdx.x == 0) { const double v = (double)row[i]; s0 -= 0.5 * v * v; }  // the diagonal counts once, everything is doubled below
+        int j = i + threadIdx.x;
+        for (; j + 3 * 1024 < D; j += 4 * 1024) {
+            const float a = row[j], b = row[j + 1024], c = row[j + 2048], d = row[j + 3072];
+            s0 += (double)a * a; s1 += (double)b * b; s0 += (double)c * c; s1 += (double)d * d;
+        }
+        for (; j < D; j += 1024) { const float a = row[j]; s0 += (double)a * a; }
     }
-    __shared__ double red[256];
-    red[threadIdx.x] = s;
+    __shared__ double red[1024];
+    red[threadIdx.x] = 2.0 * (s0 + s1);
     __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
+    for (int o = 512; o > 0; o >>= 1) {
         if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
         __syncthreads();
     }
@@ -812,14 +817,12 @@ int sd_solve_gram(sd_ctx* ctx, float* d_G, int64_t ldg, int D, int M, const sd_r
     SD_REQUIRE(ctx, reg->type == 0 || reg->type == 1, "unknown regularisation type");
     SD_REQUIRE(ctx, n_train_global >= 1, "n_train_global must be >= 1");
     float* scal = reinterpret_cast<float*>(ctx->d_scratch) + 16;
-    double* partial = reinterpret_cast<double*>(reinterpret_cast<char*>(ctx->d_scratch) + 1024);   // up to 256 doubles
+    double* partial = reinterpret_cast<double*>(reinterpret_cast<char*>(ctx->d_scratch) + 1024);   // up to 384 doubles
     SD_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
     int nparts = 0;
     if (reg->type == 1) {
-        nparts = sd_div_up((int64_t)D * D, 256 * 64);
-        if (nparts > 256) nparts = 256;
-        if (nparts < 1) nparts = 1;
-        frob_upper_kernel<<<nparts, 256, 0, ctx->stream>>>(d_G, ldg, D, partial);
+        nparts = D < 296 ? D : 296;                                   // 2 x 148 SMs; at most 384 partials fit the scratch
+        frob_upper_kernel<<<nparts, 1024, 0, ctx->stream>>>(d_G, ldg, D, partial);
         SD_LAUNCH_CHECK(ctx, "frob_upper_kernel");
     }
     lambda_kernel<<<1, 32, 0, ctx->stream>>>(partial, nparts, reg->type, reg->param, n_train_global, scal);
