@@ -111,6 +111,19 @@ __device__ __forceinline__ void tcgen05_mma_tf32(uint32_t tmem_d, uint64_t desc_
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// One lane of a converged warp (cute::elect_one_sync).  Unlike `lane == 0`, the compiler knows the guarded region is
+// executed by a single thread, so tcgen05 / TMA instructions inside it take their uniform-register operands directly
+// instead of being wrapped in an ELECT / BRA.U.ANY waterfall loop each (measured: the MMA warp was issue-bound).
+__device__ __forceinline__ bool elect_one_sync()
+{
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32])
 {
     asm volatile(
@@ -193,7 +206,7 @@ syrk_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        if (elect_one_sync()) {
             uint32_t stage = 0, phase = 0;
             const uint32_t tx_bytes = (a.passes == 3) ? STAGE_BYTES : (OPER_BYTES_A + OPER_BYTES_B);
             for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
@@ -236,7 +249,7 @@ syrk_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
                 const uint32_t tmem_d = tmem_base + buf * BN;
                 mbar_wait(&full_bar[stage], phase);
                 tcgen05_fence_after();
-                if (lane == 0) {
+                if (elect_one_sync()) {
                     const uint32_t sa_hi = smem_u32(smem + stage * STAGE_BYTES);
                     const uint32_t sb_hi = sa_hi + OPER_BYTES_A;
                     const uint32_t sa_lo = sb_hi + OPER_BYTES_B;
@@ -347,6 +360,19 @@ constexpr int RAW_BYTES = OPER_BYTES_A + OPER_BYTES_B;     // 24 KB
 constexpr int CBOX_BYTES = 32 * 32 * 4;                     // one 32 x 32 fp32 box of C per epilogue warp (128B-swizzled)
 constexpr int SMEM2_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 1024 /*barriers*/ + EPI_WARPS * CBOX_BYTES;
 
+// explicit shared-space accesses: the tile pointers come from integer arithmetic on the dynamic shared-memory base, so
+// the compiler would otherwise emit generic LD/ST (ncu: 8 wavefronts per 128-bit request instead of 4)
+__device__ __forceinline__ float4 lds128(uint32_t addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const float4& v)
+{
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 __device__ __forceinline__ float trunc_tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 __device__ __forceinline__ float rna_tf32(float x)
 {
@@ -392,7 +418,7 @@ syrk_tc2_kernel(const __grid_constant__ CUtensorMap map_raw, const __grid_consta
         asm volatile("setmaxnreg.dec.sync.aligned.u32 56;" ::: "memory");
         if (warp == 0) {
             // ===================== TMA producer =====================
-            if (lane == 0) {
+            if (elect_one_sync()) {
                 uint32_t stage = 0, phase = 0;
                 for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
                     const int2 tile = a.tiles[t];
@@ -426,7 +452,7 @@ syrk_tc2_kernel(const __grid_constant__ CUtensorMap map_raw, const __grid_consta
                     const uint32_t tmem_d = tmem_base + buf * BN;
                     mbar_wait(split ? &lo_ready[stage] : &raw_full[stage], phase);
                     tcgen05_fence_after();
-                    if (lane == 0) {
+                    if (elect_one_sync()) {
                         const uint32_t sa_hi = smem_u32(smem + stage * STAGE_BYTES);
                         const uint32_t sb_hi = sa_hi + OPER_BYTES_A;
                         const uint32_t sa_lo = sa_hi + RAW_BYTES;
@@ -461,31 +487,31 @@ syrk_tc2_kernel(const __grid_constant__ CUtensorMap map_raw, const __grid_consta
             for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
                 for (int kb = 0; kb < num_k; ++kb) {
                     mbar_wait(&raw_full[stage], phase);
-                    float4* raw = reinterpret_cast<float4*>(smem + stage * STAGE_BYTES);
-                    float4* lo = reinterpret_cast<float4*>(smem + stage * STAGE_BYTES + RAW_BYTES);
+                    const uint32_t raw = smem_u32(smem + stage * STAGE_BYTES) + tt * 16;
+                    const uint32_t lo = raw + RAW_BYTES;
                     if (a.unbiased) {
                         // hi = rna_tf32(a) written back in place (the tensor core's truncation is then a no-op and the
                         // split is unbiased), lo = rna_tf32(a - hi).  One more 24 KB shared-memory write per stage:
                         // measured 58 % tensor-pipe activity instead of 69 %, weights 3.0e-5 instead of 6.5e-5.
 #pragma unroll 4
                         for (int i = 0; i < RAW_BYTES / 16 / 128; ++i) {
-                            const float4 v = raw[i * 128 + tt];
+                            const float4 v = lds128(raw + i * 2048);
                             float4 h, l;
                             h.x = rna_tf32(v.x); h.y = rna_tf32(v.y); h.z = rna_tf32(v.z); h.w = rna_tf32(v.w);
                             l.x = rna_tf32(v.x - h.x); l.y = rna_tf32(v.y - h.y); l.z = rna_tf32(v.z - h.z); l.w = rna_tf32(v.w - h.w);
-                            raw[i * 128 + tt] = h;
-                            lo[i * 128 + tt] = l;
+                            sts128(raw + i * 2048, h);
+                            sts128(lo + i * 2048, l);
                         }
                     } else {
                         // hi is the raw tile as the tensor core sees it (low 13 mantissa bits ignored); the residual is
                         // rounded to TF32 so that the hardware's truncation of the lo operand is a no-op
 #pragma unroll 4
                         for (int i = 0; i < RAW_BYTES / 16 / 128; ++i) {
-                            const float4 v = raw[i * 128 + tt];
+                            const float4 v = lds128(raw + i * 2048);
                             float4 l;
                             l.x = rna_tf32(v.x - trunc_tf32(v.x)); l.y = rna_tf32(v.y - trunc_tf32(v.y));
                             l.z = rna_tf32(v.z - trunc_tf32(v.z)); l.w = rna_tf32(v.w - trunc_tf32(v.w));
-                            lo[i * 128 + tt] = l;
+                            sts128(lo + i * 2048, l);
                         }
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
@@ -543,7 +569,7 @@ syrk_tc2_kernel(const __grid_constant__ CUtensorMap map_raw, const __grid_consta
                     for (int v = 0; v < 8; ++v) {
                         const float4 o = make_float4(a.alpha * acc[c0 + 4 * v + 0], a.alpha * acc[c0 + 4 * v + 1],
                                                      a.alpha * acc[c0 + 4 * v + 2], a.alpha * acc[c0 + 4 * v + 3]);
-                        *reinterpret_cast<float4*>(box + lane * 128 + ((v ^ (lane & 7)) << 4)) = o;
+                        sts128(box_u32 + lane * 128 + ((v ^ (lane & 7)) << 4), o);
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
