@@ -133,6 +133,8 @@ void sd_ctx_destroy(sd_ctx* ctx)
     if (ctx->h_scratch) cudaFreeHost(ctx->h_scratch);
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->chain_stream) { cudaStreamSynchronize(ctx->chain_stream); cudaStreamDestroy(ctx->chain_stream); }
+    for (int i = 0; i < 2; ++i) if (ctx->chain_ev[i]) cudaEventDestroy(ctx->chain_ev[i]);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

@@ -713,7 +713,7 @@ bool sd_syrk_tc_supported(const float* d_S, int64_t lds, int K, int MI, int NJ, 
 }
 
 int sd_syrk_tc(sd_ctx* ctx, const float* d_S, int64_t lds, int K, int MI, int NJ, float* d_C, int64_t ldc,
-               float alpha, float beta, int passes)
+               float alpha, float beta, int passes, bool unbiased_split)
 {
     if (MI <= 0 || NJ <= 0 || K <= 0) return SD_OK;
     SD_REQUIRE(ctx, passes == 1 || passes == 3, "passes must be 1 or 3");
@@ -755,10 +755,11 @@ int sd_syrk_tc(sd_ctx* ctx, const float* d_S, int64_t lds, int K, int MI, int NJ
 
     TcArgs a;
     a.K = K; a.MI = MI; a.NJ = NJ; a.C = d_C; a.ldc = ldc; a.alpha = alpha; a.beta = beta; a.passes = passes;
-    a.unbiased = ctx->gram_mode == 3 ? 1 : 0;
+    a.unbiased = (ctx->gram_mode == 3 || unbiased_split) ? 1 : 0;
     a.tma_c = 0;
     a.tiles = d_tiles; a.num_tiles = (int)tiles.size();
-    const int grid = a.num_tiles < ctx->sm_count ? a.num_tiles : ctx->sm_count;
+    const int sms = ctx->sm_count - ctx->syrk_sm_reserve > 0 ? ctx->sm_count - ctx->syrk_sm_reserve : 1;
+    const int grid = a.num_tiles < sms ? a.num_tiles : sms;
     if (variant2) {
         // C goes back through the TMA when it can be described by a tensor map (16-byte aligned base and pitch)
         CUtensorMap map_c = map_hi;

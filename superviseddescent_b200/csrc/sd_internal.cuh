@@ -23,6 +23,9 @@ struct sd_ctx {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     cudaStream_t copy_stream = nullptr;   // host<->device staging for sd_detect_batch_host
+    cudaStream_t chain_stream = nullptr;  // Cholesky look-ahead: next panel's diagonal blocks while the trailing update runs
+    cudaEvent_t chain_ev[2] = {nullptr, nullptr};
+    int syrk_sm_reserve = 0;              // SMs the persistent SYRK leaves free (1 while a look-ahead chain runs beside it)
     std::string err;
     int64_t launches = 0;
     int sm_count = 148;
@@ -75,12 +78,15 @@ static inline int sd_div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b
 // C[i,j] = beta*C[i,j] + alpha * sum_{k<K} S[k,i] * S[k,j]   for i < MI, j < NJ, restricted to the
 // tiles that intersect j >= i (upper triangle).  S: K x NJ row-major (lds), C: MI x NJ (ldc).
 // Used for the Gram matrix [A^T A | A^T B] and for the Cholesky trailing update.
+// path: 0 = choose by size, 1 = tensor cores whenever the operands allow it, 2 = fp32 SIMT.  A factorisation step
+// passes the same choice for every piece of one rank-k update (mixing the two kernels inside one update was measured
+// to double the error of the solved weights).  unbiased_split: round the hi operand (gram mode 3) for this call.
 int sd_syrk_update(sd_ctx* ctx, const float* d_S, int64_t lds, int K, int MI, int NJ,
-                   float* d_C, int64_t ldc, float alpha, float beta);
+                   float* d_C, int64_t ldc, float alpha, float beta, int path = 0, bool unbiased_split = false);
 int sd_syrk_simt(sd_ctx* ctx, const float* d_S, int64_t lds, int K, int MI, int NJ,
                  float* d_C, int64_t ldc, float alpha, float beta);
 int sd_syrk_tc(sd_ctx* ctx, const float* d_S, int64_t lds, int K, int MI, int NJ,
-               float* d_C, int64_t ldc, float alpha, float beta, int passes);
+               float* d_C, int64_t ldc, float alpha, float beta, int passes, bool unbiased_split = false);
 bool sd_syrk_tc_supported(const float* d_S, int64_t lds, int K, int MI, int NJ, const float* d_C, int64_t ldc);
 
 // device-side normalisation factors, shared by the HOG and cascade kernels

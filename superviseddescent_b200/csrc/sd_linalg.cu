@@ -502,8 +502,11 @@ __device__ __forceinline__ void potrf32_warp(float* sA, float* sT, int k0, int l
     }
 }
 
+// Optional fused update (look-ahead path): the block is first reduced by A^T A, A = nk x nb rows of the panel that
+// was just solved (the part of the trailing update this diagonal block still misses).
 __global__ void __launch_bounds__(256) potrf_inv_kernel(float* __restrict__ G, long long ldg, int nb,
-                                                        float* __restrict__ W, float* __restrict__ Wt, int* __restrict__ status)
+                                                        float* __restrict__ W, float* __restrict__ Wt, int* __restrict__ status,
+                                                        const float* __restrict__ A, long long lda, int nk)
 {
     extern __shared__ float sm[];
     float* sA = sm;                    // PB x PLD : the block, becomes U
@@ -528,6 +531,41 @@ __global__ void __launch_bounds__(256) potrf_inv_kernel(float* __restrict__ G, l
             sA[i * PLD + j] = v[u];
             sW[i * PLD + j] = 0.f;
         }
+    }
+    if (A) {
+        // stage A in the (still unused) W area, subtract A^T A from the upper triangle, clear the area again
+        for (int idx = tid; idx < PB * PB; idx += 256) {
+            const int q = idx >> 7, i = idx & (PB - 1);
+            sW[q * PLD + i] = (q < nk && i < nb) ? A[(long long)q * lda + i] : 0.f;
+        }
+        __syncthreads();
+        const int tx = tid & 15, ty = tid >> 4;                   // rows ty*8 + m, columns tx + 16*n (conflict-free)
+        float acc[8][8];
+#pragma unroll
+        for (int m = 0; m < 8; ++m)
+#pragma unroll
+            for (int n = 0; n < 8; ++n) acc[m][n] = 0.f;
+#pragma unroll 4
+        for (int q = 0; q < PB; ++q) {
+            float ar[8], ac[8];
+#pragma unroll
+            for (int m = 0; m < 8; ++m) ar[m] = sW[q * PLD + ty * 8 + m];
+#pragma unroll
+            for (int n = 0; n < 8; ++n) ac[n] = sW[q * PLD + tx + 16 * n];
+#pragma unroll
+            for (int m = 0; m < 8; ++m)
+#pragma unroll
+                for (int n = 0; n < 8; ++n) acc[m][n] = fmaf(ar[m], ac[n], acc[m][n]);
+        }
+#pragma unroll
+        for (int m = 0; m < 8; ++m)
+#pragma unroll
+            for (int n = 0; n < 8; ++n) {
+                const int i = ty * 8 + m, j = tx + 16 * n;
+                if (j >= i && j < nb) sA[i * PLD + j] -= acc[m][n];
+            }
+        __syncthreads();
+        for (int idx = tid; idx < PB * PB; idx += 256) sW[(idx >> 7) * PLD + (idx & (PB - 1))] = 0.f;
     }
     __syncthreads();
     SD_CLK(1);
@@ -638,6 +676,144 @@ __global__ void __launch_bounds__(256) potrf_inv_kernel(float* __restrict__ G, l
 extern "C" __attribute__((visibility("default"))) void sd_debug_read_clk(long long* out) { cudaMemcpyFromSymbol(out, sd_dbg_clk, sizeof(long long) * 64); }
 #endif
 
+// Block-row solve as a GEMM with the explicit inverse, in place:
+//     B <- W^T (B - A^T P)            B: nb x cols block row of G,  W = U_jj^-1 (PB x PB, identity padded)
+// The optional A^T P term (A = nk x nb, P = nk x cols) is the rank-nk update the block row still misses (second
+// block row of a 256-row panel).  One CTA owns 64 columns over all rows, so the update is safe in place; thread
+// tile 8 x 4 with 3 shared 128-bit loads per 32 FMAs.
+constexpr int TA_COLS = 64;
+struct TrsmArgs {
+    float* B; long long ldb; int nb; int cols;
+    const float* W;
+    const float* A; long long lda; int nk;
+    const float* P; long long ldp;
+};
+
+__global__ void __launch_bounds__(256) trsm_apply_kernel(const TrsmArgs a)
+{
+    extern __shared__ __align__(16) float sm_ta[];
+    float* sW = sm_ta;                       // [PB][PB]      W[k][i]
+    float* sT = sW + PB * PB;                // [PB][TA_COLS] B tile, then T = B - A^T P
+    float* sA = sT + PB * TA_COLS;           // fused only: [PB][PB] A[q][k]
+    float* sP = sA + PB * PB;                // fused only: [PB][TA_COLS]
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int c0 = blockIdx.x * TA_COLS;
+    for (int idx = tid; idx < PB * PB / 4; idx += 256)
+        reinterpret_cast<float4*>(sW)[idx] = reinterpret_cast<const float4*>(a.W)[idx];
+    const bool full = c0 + TA_COLS <= a.cols;
+    const bool vecB = full && (a.ldb & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.B) & 15) == 0);
+    if (vecB) {
+#pragma unroll 4
+        for (int idx = tid; idx < PB * TA_COLS / 4; idx += 256) {
+            const int k = idx >> 4, c = (idx & 15) * 4;
+            reinterpret_cast<float4*>(sT)[idx] = (k < a.nb) ? *reinterpret_cast<const float4*>(a.B + (long long)k * a.ldb + c0 + c)
+                                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    } else {
+        for (int idx = tid; idx < PB * TA_COLS; idx += 256) {
+            const int k = idx >> 6, c = idx & (TA_COLS - 1);
+            sT[idx] = (k < a.nb && c0 + c < a.cols) ? a.B[(long long)k * a.ldb + c0 + c] : 0.f;
+        }
+    }
+    if (a.A) {
+        const bool vecA = (a.lda & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.A) & 15) == 0) && (a.nb & 3) == 0;
+        if (vecA) {
+#pragma unroll 4
+            for (int idx = tid; idx < PB * PB / 4; idx += 256) {
+                const int q = idx >> 5, k = (idx & 31) * 4;
+                reinterpret_cast<float4*>(sA)[idx] = (q < a.nk && k < a.nb) ? *reinterpret_cast<const float4*>(a.A + (long long)q * a.lda + k)
+                                                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        } else {
+            for (int idx = tid; idx < PB * PB; idx += 256) {
+                const int q = idx >> 7, k = idx & (PB - 1);
+                sA[idx] = (q < a.nk && k < a.nb) ? a.A[(long long)q * a.lda + k] : 0.f;
+            }
+        }
+        const bool vecP = full && (a.ldp & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.P) & 15) == 0);
+        if (vecP) {
+#pragma unroll 4
+            for (int idx = tid; idx < PB * TA_COLS / 4; idx += 256) {
+                const int q = idx >> 4, c = (idx & 15) * 4;
+                reinterpret_cast<float4*>(sP)[idx] = (q < a.nk) ? *reinterpret_cast<const float4*>(a.P + (long long)q * a.ldp + c0 + c)
+                                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        } else {
+            for (int idx = tid; idx < PB * TA_COLS; idx += 256) {
+                const int q = idx >> 6, c = idx & (TA_COLS - 1);
+                sP[idx] = (q < a.nk && c0 + c < a.cols) ? a.P[(long long)q * a.ldp + c0 + c] : 0.f;
+            }
+        }
+    }
+    __syncthreads();
+    float acc[8][4];
+    if (a.A) {
+#pragma unroll
+        for (int m = 0; m < 8; ++m) { acc[m][0] = acc[m][1] = acc[m][2] = acc[m][3] = 0.f; }
+#pragma unroll 4
+        for (int q = 0; q < PB; ++q) {
+            const float4 a0 = *reinterpret_cast<const float4*>(sA + q * PB + ty * 8);
+            const float4 a1 = *reinterpret_cast<const float4*>(sA + q * PB + ty * 8 + 4);
+            const float4 pv = *reinterpret_cast<const float4*>(sP + q * TA_COLS + tx * 4);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                acc[m][0] = fmaf(av[m], pv.x, acc[m][0]); acc[m][1] = fmaf(av[m], pv.y, acc[m][1]);
+                acc[m][2] = fmaf(av[m], pv.z, acc[m][2]); acc[m][3] = fmaf(av[m], pv.w, acc[m][3]);
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {                               // every thread updates only its own entries of T
+            float4* t = reinterpret_cast<float4*>(sT + (ty * 8 + m) * TA_COLS + tx * 4);
+            float4 v = *t;
+            v.x -= acc[m][0]; v.y -= acc[m][1]; v.z -= acc[m][2]; v.w -= acc[m][3];
+            *t = v;
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int m = 0; m < 8; ++m) { acc[m][0] = acc[m][1] = acc[m][2] = acc[m][3] = 0.f; }
+#pragma unroll 4
+    for (int k = 0; k < PB; ++k) {
+        const float4 w0 = *reinterpret_cast<const float4*>(sW + k * PB + ty * 8);
+        const float4 w1 = *reinterpret_cast<const float4*>(sW + k * PB + ty * 8 + 4);
+        const float4 tv = *reinterpret_cast<const float4*>(sT + k * TA_COLS + tx * 4);
+        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            acc[m][0] = fmaf(wv[m], tv.x, acc[m][0]); acc[m][1] = fmaf(wv[m], tv.y, acc[m][1]);
+            acc[m][2] = fmaf(wv[m], tv.z, acc[m][2]); acc[m][3] = fmaf(wv[m], tv.w, acc[m][3]);
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+        const int i = ty * 8 + m;
+        if (i >= a.nb) continue;
+        float* row = a.B + (long long)i * a.ldb + c0 + tx * 4;
+#pragma unroll
+        for (int n = 0; n < 4; ++n)
+            if (c0 + tx * 4 + n < a.cols) row[n] = acc[m][n];
+    }
+}
+
+int launch_trsm_apply(sd_ctx* ctx, cudaStream_t stream, float* B, int64_t ldb, int nb, int cols, const float* W,
+                      const float* A, int64_t lda, int nk, const float* P, int64_t ldp)
+{
+    if (nb <= 0 || cols <= 0) return SD_OK;
+    TrsmArgs a;
+    a.B = B; a.ldb = ldb; a.nb = nb; a.cols = cols; a.W = W; a.A = A; a.lda = lda; a.nk = nk; a.P = P; a.ldp = ldp;
+    const size_t smem = (size_t)(PB * PB + PB * TA_COLS) * sizeof(float) * (A ? 2 : 1);
+    trsm_apply_kernel<<<sd_div_up(cols, TA_COLS), 256, smem, stream>>>(a);
+    SD_LAUNCH_CHECK(ctx, "trsm_apply_kernel");
+    return SD_OK;
+}
+
+bool sd_syrk_is_big(int K, int64_t MI, int64_t NJ)
+{
+    static const long long tc_min = getenv("SD_B200_TC_MIN") ? atoll(getenv("SD_B200_TC_MIN")) : 256LL * 256LL;
+    return MI * NJ >= tc_min && K >= 64;
+}
+
 int cholesky_solve(sd_ctx* ctx, float* G, int64_t ldg, int D, int M, float* X)
 {
     int* status = reinterpret_cast<int*>(ctx->d_scratch);
@@ -645,64 +821,100 @@ int cholesky_solve(sd_ctx* ctx, float* G, int64_t ldg, int D, int M, float* X)
     const int nblocks = sd_div_up(D, kCholNb);
     const size_t smem_potrf = (size_t)(2 * PB * PLD + PS * (PS + 1)) * sizeof(float);
     SD_CUDA(ctx, cudaFuncSetAttribute(potrf_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_potrf));
+    SD_CUDA(ctx, cudaFuncSetAttribute(trsm_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)((PB * PB + PB * TA_COLS) * sizeof(float) * 2)));
     // per block: W = U_jj^-1 and its transpose (row-major 128 x 128 each)
     float* inv = (float*)sd_workspace(ctx, SD_WS_DIAGINV2, (size_t)nblocks * 2 * PB * PB * sizeof(float));
-    const int64_t ldp = ((int64_t)W_ + 3) / 4 * 4;
-    float* panel = (float*)sd_workspace(ctx, SD_WS_PANEL, (size_t)2 * PB * ldp * sizeof(float));
-    if (!inv || !panel) return SD_ERR_CUDA;
+    if (!inv) return SD_ERR_CUDA;
+    if (!ctx->chain_stream) {
+        int prio_lo = 0, prio_hi = 0;
+        SD_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        SD_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->chain_stream, cudaStreamNonBlocking, prio_hi));
+        for (int i = 0; i < 2; ++i) SD_CUDA(ctx, cudaEventCreateWithFlags(&ctx->chain_ev[i], cudaEventDisableTiming));
+    }
+    const bool lookahead = getenv("SD_B200_NO_LOOKAHEAD") == nullptr;      // debugging knob: run the chain in line
+    cudaStream_t main_s = ctx->stream, chain_s = lookahead ? ctx->chain_stream : ctx->stream;
+    cudaEvent_t ev_head = ctx->chain_ev[0], ev_chain = ctx->chain_ev[1];
     GemmEpilogue ep;
     memset(&ep, 0, sizeof(ep));
-    // ---- factorisation, carrying the right-hand side columns along (Y = U^-T R) ----
-    // Two 128-blocks form one 256-row panel so that the trailing SYRK (the part that streams the whole
-    // trailing matrix through HBM) runs with K = 256 and half as often:
-    //   A11 = U11^T U11 ; P1 = U11^-T [A12 | rest] ; A22 -= P1(:,A12)^T P1 ; A22 = U22^T U22 ;
-    //   P2 = U22^-T [rest of block row 2] ; trailing -= [P1;P2]^T [P1;P2]
-    auto copy_rows = [&](const float* src, int64_t lds_, int rows, int cols_, float* dst, int64_t ldd_) -> int {
-        if (rows <= 0 || cols_ <= 0) return SD_OK;
-        const int cb = sd_div_up((int64_t)rows * cols_, 256) > 2048 ? 2048 : sd_div_up((int64_t)rows * cols_, 256);
-        copy_block_kernel<<<cb, 256, 0, ctx->stream>>>(src, lds_, rows, cols_, dst, ldd_);
-        SD_LAUNCH_CHECK(ctx, "copy_block_kernel");
-        return SD_OK;
+    // ---- factorisation G = U^T U in 256-row panels (two 128-blocks), carrying the right-hand sides along (Y = U^-T R) ----
+    //   chain(p)  [one SM]  : A11 = U11^T U11 ; P1a = U11^-T A12 ; A22 - P1a^T P1a = U22^T U22           (diagonal blocks)
+    //   bulk(p)             : P1 = U11^-T [rest of block row 1] ; P2 = U22^-T ([rest of block row 2] - P1a^T P1)
+    //   head(p)             : rows of panel p+1      -= [P1;P2]^T [P1;P2]     (K = 256, tensor cores)
+    //   tail(p)             : everything below them  -= [P1;P2]^T [P1;P2]
+    // Look-ahead: chain(p+1) only needs head(p), so it runs on a second stream on the one SM that tail(p) leaves free;
+    // the 134 dependent single-CTA factorisations are hidden behind the trailing updates while those are long enough.
+    // Every element still receives its updates in panel order (events), so the result does not depend on timing.
+    auto panel_dims = [&](int b, int& j, int& nb1, int& nb2) {
+        j = b * kCholNb;
+        nb1 = (D - j < kCholNb) ? D - j : kCholNb;
+        nb2 = (b + 1 < nblocks) ? ((D - j - nb1 < kCholNb) ? D - j - nb1 : kCholNb) : 0;
     };
-    float* panel2 = panel + (size_t)PB * ldp;                      // second 128 rows of the panel buffer
-    for (int b = 0; b < nblocks; b += 2) {
-        const int j = b * kCholNb;
-        const int nb1 = (D - j < kCholNb) ? D - j : kCholNb;
-        const int nb2 = (b + 1 < nblocks) ? ((D - j - nb1 < kCholNb) ? D - j - nb1 : kCholNb) : 0;
+    auto launch_chain = [&](int b) -> int {
+        int j, nb1, nb2;
+        panel_dims(b, j, nb1, nb2);
         float* G11 = G + (int64_t)j * ldg + j;
         float* W1 = inv + (size_t)b * 2 * PB * PB;
-        potrf_inv_kernel<<<1, 256, smem_potrf, ctx->stream>>>(G11, ldg, nb1, W1, W1 + PB * PB, status);
+        potrf_inv_kernel<<<1, 256, smem_potrf, chain_s>>>(G11, ldg, nb1, W1, W1 + PB * PB, status, nullptr, 0, 0);
         SD_LAUNCH_CHECK(ctx, "potrf_inv_kernel");
-        const int cols1 = W_ - j - nb1;                            // columns right of the first diagonal block
-        if (cols1 <= 0) continue;
-        // P1 = U11^-T * G(j : j+nb1, j+nb1 : ) as a GEMM with W1^T, out of place, then copied back into G
-        int rc = launch_gemm_nn(ctx, W1 + PB * PB, PB, nb1, nb1, G11 + nb1, ldg, cols1, panel, ldp, 1.0f, 0.0f, ep);
+        if (nb2 > 0) {
+            int rc = launch_trsm_apply(ctx, chain_s, G11 + nb1, ldg, nb1, nb2, W1, nullptr, 0, 0, nullptr, 0);   // P1a
+            if (rc) return rc;
+            float* G22 = G + (int64_t)(j + nb1) * ldg + (j + nb1);
+            float* W2 = inv + (size_t)(b + 1) * 2 * PB * PB;
+            potrf_inv_kernel<<<1, 256, smem_potrf, chain_s>>>(G22, ldg, nb2, W2, W2 + PB * PB, status, G11 + nb1, ldg, nb1);
+            SD_LAUNCH_CHECK(ctx, "potrf_inv_kernel");
+        }
+        return SD_OK;
+    };
+    SD_CUDA(ctx, cudaEventRecord(ev_head, main_s));                   // G is ready (regulariser applied) for chain(0)
+    SD_CUDA(ctx, cudaStreamWaitEvent(chain_s, ev_head, 0));
+    int rc = launch_chain(0);
+    if (rc) return rc;
+    SD_CUDA(ctx, cudaEventRecord(ev_chain, chain_s));
+    for (int b = 0; b < nblocks; b += 2) {
+        int j, nb1, nb2;
+        panel_dims(b, j, nb1, nb2);
+        SD_CUDA(ctx, cudaStreamWaitEvent(main_s, ev_chain, 0));       // chain(p) done
+        const int j3 = j + nb1 + nb2;                                 // first column right of the panel
+        const int cols3 = W_ - j3;
+        if (cols3 <= 0) continue;
+        float* W1 = inv + (size_t)b * 2 * PB * PB;
+        float* row1 = G + (int64_t)j * ldg + j3;
+        rc = launch_trsm_apply(ctx, main_s, row1, ldg, nb1, cols3, W1, nullptr, 0, 0, nullptr, 0);                 // P1
         if (rc) return rc;
-        rc = copy_rows(panel, ldp, nb1, cols1, G11 + nb1, ldg);
+        if (nb2 > 0) {
+            float* W2 = inv + (size_t)(b + 1) * 2 * PB * PB;
+            float* row2 = G + (int64_t)(j + nb1) * ldg + j3;
+            const float* P1a = G + (int64_t)j * ldg + (j + nb1);
+            rc = launch_trsm_apply(ctx, main_s, row2, ldg, nb2, cols3, W2, P1a, ldg, nb1, row1, ldg);               // P2
+            if (rc) return rc;
+        }
+        const int rest = D - j3;                                      // rows (= diagonal columns) below the panel
+        if (rest <= 0) continue;
+        const int kp = nb1 + nb2;                                     // rows of [P1;P2], contiguous in G
+        const int head = rest < 2 * kCholNb ? rest : 2 * kCholNb;
+        float* C3 = G + (int64_t)j3 * ldg + j3;
+        // one kernel family per rank-kp update, chosen from the size of the whole trailing matrix; the updates use the
+        // unbiased hi/lo split: a truncated hi leaves a one-signed lo*lo term behind, which is harmless in the Gram (it
+        // scales [AtA|Atb] almost uniformly) but is amplified by the cancellation inside Schur complements
+        static const bool upd_unbiased = getenv("SD_B200_UPDATE_BIASED") == nullptr;
+        const int path = sd_syrk_is_big(kp, rest, cols3) ? 1 : 2;
+        rc = sd_syrk_update(ctx, row1, ldg, kp, head, cols3, C3, ldg, -1.0f, 1.0f, path, upd_unbiased);
         if (rc) return rc;
-        if (nb2 <= 0) continue;                                    // (only right-hand sides were right of the last block)
-        // block row 2 of this panel gets the rank-nb1 update:  G(j2 : j2+nb2, j2 : ) -= P1(:, 0:nb2)^T P1
-        const int j2 = j + nb1;
-        float* G22 = G + (int64_t)j2 * ldg + j2;
-        rc = sd_syrk_update(ctx, panel, ldp, nb1, nb2, cols1, G22, ldg, -1.0f, 1.0f);
+        SD_CUDA(ctx, cudaEventRecord(ev_head, main_s));
+        SD_CUDA(ctx, cudaStreamWaitEvent(chain_s, ev_head, 0));
+        rc = launch_chain(b + 2);
         if (rc) return rc;
-        float* W2 = inv + (size_t)(b + 1) * 2 * PB * PB;
-        potrf_inv_kernel<<<1, 256, smem_potrf, ctx->stream>>>(G22, ldg, nb2, W2, W2 + PB * PB, status);
-        SD_LAUNCH_CHECK(ctx, "potrf_inv_kernel");
-        const int cols2 = cols1 - nb2;                             // columns right of the second diagonal block
-        if (cols2 <= 0) continue;
-        // P2 = U22^-T * G(j2 : j2+nb2, j2+nb2 : ), stored under P1's matching columns in the panel buffer
-        rc = launch_gemm_nn(ctx, W2 + PB * PB, PB, nb2, nb2, G22 + nb2, ldg, cols2, panel2 + nb2, ldp, 1.0f, 0.0f, ep);
-        if (rc) return rc;
-        rc = copy_rows(panel2 + nb2, ldp, nb2, cols2, G22 + nb2, ldg);
-        if (rc) return rc;
-        const int rest = D - j2 - nb2;
-        if (rest > 0) {
-            // [G33 | R3] -= [P1;P2]^T [P1;P2]   (K = nb1 + nb2 rows of the panel buffer, columns from nb2 on)
-            rc = sd_syrk_update(ctx, panel + nb2, ldp, nb1 + nb2, rest, cols2, G + (int64_t)(j2 + nb2) * ldg + (j2 + nb2), ldg, -1.0f, 1.0f);
+        SD_CUDA(ctx, cudaEventRecord(ev_chain, chain_s));
+        if (rest > head) {
+            ctx->syrk_sm_reserve = lookahead ? 1 : 0;                 // leave one SM to the chain running beside it
+            rc = sd_syrk_update(ctx, row1 + head, ldg, kp, rest - head, cols3 - head, C3 + (int64_t)head * ldg + head, ldg, -1.0f, 1.0f, path, upd_unbiased);
+            ctx->syrk_sm_reserve = 0;
             if (rc) return rc;
         }
     }
+    SD_CUDA(ctx, cudaStreamWaitEvent(main_s, ev_chain, 0));
     SD_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));   // end of "Decomposition"
     // ---- back substitution U X = Y, right-looking over block columns from the last ----
     for (int b = nblocks - 1; b >= 0; --b) {
@@ -775,11 +987,11 @@ int sd_syrk_simt(sd_ctx* ctx, const float* d_S, int64_t lds, int K, int MI, int 
 }
 
 int sd_syrk_update(sd_ctx* ctx, const float* d_S, int64_t lds, int K, int MI, int NJ, float* d_C, int64_t ldc,
-                   float alpha, float beta)
+                   float alpha, float beta, int path, bool unbiased_split)
 {
-    const bool big = (int64_t)MI * NJ >= 256LL * 256LL && K >= 64;
-    if (ctx->gram_mode != 2 && big && sd_syrk_tc_supported(d_S, lds, K, MI, NJ, d_C, ldc))
-        return sd_syrk_tc(ctx, d_S, lds, K, MI, NJ, d_C, ldc, alpha, beta, ctx->gram_mode == 1 ? 1 : 3);
+    const bool want_tc = path == 1 || (path == 0 && sd_syrk_is_big(K, MI, NJ));
+    if (ctx->gram_mode != 2 && path != 2 && want_tc && sd_syrk_tc_supported(d_S, lds, K, MI, NJ, d_C, ldc))
+        return sd_syrk_tc(ctx, d_S, lds, K, MI, NJ, d_C, ldc, alpha, beta, ctx->gram_mode == 1 ? 1 : 3, unbiased_split);
     return sd_syrk_simt(ctx, d_S, lds, K, MI, NJ, d_C, ldc, alpha, beta);
 }
 
