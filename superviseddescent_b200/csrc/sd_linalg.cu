@@ -463,6 +463,26 @@ __device__ long long sd_dbg_clk[64];
 #define SD_CLK(i) do {} while (0)
 #endif
 
+// cp.async staging: all of a CTA's global->shared copies are put in flight at once (the block kernels of the
+// factorisation are latency-bound: measured 37 us per back-substitution step with plain load/store loops).
+// valid == false zero-fills the destination (src-size 0; the source pointer is then only required to be mapped).
+__device__ __forceinline__ void cp_async16(float* dst_smem, const float* src, bool valid)
+{
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
+    const int n = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async4(float* dst_smem, const float* src, bool valid)
+{
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
+    const int n = valid ? 4 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
 // Factor and invert the 32 x 32 diagonal sub-block at (k0, k0) of sA with ONE warp (lane j owns column j).
 // Rolled loops on shared memory with broadcast reads: a fully unrolled register/shuffle variant was measured no
 // faster -- its ~50 KB of straight-line code thrashes the instruction cache of a lone warp.
@@ -514,30 +534,22 @@ __global__ void __launch_bounds__(256) potrf_inv_kernel(float* __restrict__ G, l
     float* sT = sW + PB * PLD;         // PS x (PS+1) scratch (inverse of the current diagonal sub-block / partial sums)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     SD_CLK(0);
-#pragma unroll 1
-    for (int base = 0; base < PB * PB; base += 256 * 8) {
-        float v[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {                             // 8 independent global loads in flight per thread
-            const int idx = base + u * 256 + tid;
-            const int i = idx >> 7, j = idx & (PB - 1);
-            v[u] = (i == j) ? 1.f : 0.f;                          // identity padding outside nb
-            if (i < nb && j < nb) v[u] = (j >= i) ? G[(long long)i * ldg + j] : 0.f;
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int idx = base + u * 256 + tid;
-            const int i = idx >> 7, j = idx & (PB - 1);
-            sA[i * PLD + j] = v[u];
+    // the block (upper triangle, identity padding outside nb) and, for the fused update, the panel rows A go to shared
+    // memory as one batch of asynchronous copies; W's area doubles as the staging buffer for A
+    for (int idx = tid; idx < PB * PB; idx += 256) {
+        const int i = idx >> 7, j = idx & (PB - 1);
+        const bool ok = i < nb && j < nb && j >= i;
+        if (ok) cp_async4(sA + i * PLD + j, G + (long long)i * ldg + j, true);
+        else sA[i * PLD + j] = (i == j && i >= nb) ? 1.f : 0.f;
+        if (A) {
+            const bool oka = i < nk && j < nb;                      // here i = panel row q, j = column of the block
+            cp_async4(sW + i * PLD + j, oka ? A + (long long)i * lda + j : A, oka);
+        } else {
             sW[i * PLD + j] = 0.f;
         }
     }
+    cp_async_wait_all();
     if (A) {
-        // stage A in the (still unused) W area, subtract A^T A from the upper triangle, clear the area again
-        for (int idx = tid; idx < PB * PB; idx += 256) {
-            const int q = idx >> 7, i = idx & (PB - 1);
-            sW[q * PLD + i] = (q < nk && i < nb) ? A[(long long)q * lda + i] : 0.f;
-        }
         __syncthreads();
         const int tx = tid & 15, ty = tid >> 4;                   // rows ty*8 + m, columns tx + 16*n (conflict-free)
         float acc[8][8];
@@ -698,53 +710,48 @@ __global__ void __launch_bounds__(256) trsm_apply_kernel(const TrsmArgs a)
     float* sP = sA + PB * PB;                // fused only: [PB][TA_COLS]
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int c0 = blockIdx.x * TA_COLS;
-    for (int idx = tid; idx < PB * PB / 4; idx += 256)
-        reinterpret_cast<float4*>(sW)[idx] = reinterpret_cast<const float4*>(a.W)[idx];
+    for (int idx = tid; idx < PB * PB / 4; idx += 256) cp_async16(sW + idx * 4, a.W + idx * 4, true);
     const bool full = c0 + TA_COLS <= a.cols;
-    const bool vecB = full && (a.ldb & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.B) & 15) == 0);
-    if (vecB) {
-#pragma unroll 4
+    if (full && (a.ldb & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.B) & 15) == 0)) {
         for (int idx = tid; idx < PB * TA_COLS / 4; idx += 256) {
             const int k = idx >> 4, c = (idx & 15) * 4;
-            reinterpret_cast<float4*>(sT)[idx] = (k < a.nb) ? *reinterpret_cast<const float4*>(a.B + (long long)k * a.ldb + c0 + c)
-                                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+            cp_async16(sT + idx * 4, a.B + (long long)(k < a.nb ? k : 0) * a.ldb + c0 + c, k < a.nb);
         }
     } else {
         for (int idx = tid; idx < PB * TA_COLS; idx += 256) {
             const int k = idx >> 6, c = idx & (TA_COLS - 1);
-            sT[idx] = (k < a.nb && c0 + c < a.cols) ? a.B[(long long)k * a.ldb + c0 + c] : 0.f;
+            const bool ok = k < a.nb && c0 + c < a.cols;
+            cp_async4(sT + idx, ok ? a.B + (long long)k * a.ldb + c0 + c : a.B, ok);
         }
     }
     if (a.A) {
-        const bool vecA = (a.lda & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.A) & 15) == 0) && (a.nb & 3) == 0;
-        if (vecA) {
-#pragma unroll 4
+        if ((a.lda & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.A) & 15) == 0) && (a.nb & 3) == 0) {
             for (int idx = tid; idx < PB * PB / 4; idx += 256) {
                 const int q = idx >> 5, k = (idx & 31) * 4;
-                reinterpret_cast<float4*>(sA)[idx] = (q < a.nk && k < a.nb) ? *reinterpret_cast<const float4*>(a.A + (long long)q * a.lda + k)
-                                                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+                const bool ok = q < a.nk && k < a.nb;
+                cp_async16(sA + idx * 4, ok ? a.A + (long long)q * a.lda + k : a.A, ok);
             }
         } else {
             for (int idx = tid; idx < PB * PB; idx += 256) {
                 const int q = idx >> 7, k = idx & (PB - 1);
-                sA[idx] = (q < a.nk && k < a.nb) ? a.A[(long long)q * a.lda + k] : 0.f;
+                const bool ok = q < a.nk && k < a.nb;
+                cp_async4(sA + idx, ok ? a.A + (long long)q * a.lda + k : a.A, ok);
             }
         }
-        const bool vecP = full && (a.ldp & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.P) & 15) == 0);
-        if (vecP) {
-#pragma unroll 4
+        if (full && (a.ldp & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.P) & 15) == 0)) {
             for (int idx = tid; idx < PB * TA_COLS / 4; idx += 256) {
                 const int q = idx >> 4, c = (idx & 15) * 4;
-                reinterpret_cast<float4*>(sP)[idx] = (q < a.nk) ? *reinterpret_cast<const float4*>(a.P + (long long)q * a.ldp + c0 + c)
-                                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+                cp_async16(sP + idx * 4, a.P + (long long)(q < a.nk ? q : 0) * a.ldp + c0 + c, q < a.nk);
             }
         } else {
             for (int idx = tid; idx < PB * TA_COLS; idx += 256) {
                 const int q = idx >> 6, c = idx & (TA_COLS - 1);
-                sP[idx] = (q < a.nk && c0 + c < a.cols) ? a.P[(long long)q * a.ldp + c0 + c] : 0.f;
+                const bool ok = q < a.nk && c0 + c < a.cols;
+                cp_async4(sP + idx, ok ? a.P + (long long)q * a.ldp + c0 + c : a.P, ok);
             }
         }
     }
+    cp_async_wait_all();
     __syncthreads();
     float acc[8][4];
     if (a.A) {
@@ -793,6 +800,98 @@ __global__ void __launch_bounds__(256) trsm_apply_kernel(const TrsmArgs a)
 #pragma unroll
         for (int n = 0; n < 4; ++n)
             if (c0 + tx * 4 + n < a.cols) row[n] = acc[m][n];
+    }
+}
+
+// One step of the back substitution U X = Y (right-looking over block columns, from the last):
+//     X_j = U_jj^-1 Y_j            (every CTA, redundantly: 128 x 128 x 64 -- cheaper than a second dependent launch)
+//     Y[rows of chunk r] -= U[chunk r, block j] X_j
+// grid.x = 128-row chunks above block j (at least 1; CTA 0 also stores X_j), grid.y = 64-column tiles of the right-hand sides.
+constexpr int BS_COLS = 64, BS_ULD = PB + 4;      // 16-byte aligned rows for cp.async
+struct BackArgs {
+    float* G; long long ldg; int D; int M; int j; int nb; int nchunks;
+    const float* Wt;        // (U_jj^-1)^T, PB x PB row-major, identity padded
+    float* X;               // D x M
+};
+
+__global__ void __launch_bounds__(256) backsub_step_kernel(const BackArgs a)
+{
+    extern __shared__ __align__(16) float sm_bs[];
+    float* sWt = sm_bs;                      // [PB][PB]        Wt[k][i] = W[i][k]
+    float* sY = sWt + PB * PB;               // [PB][BS_COLS]   Y_j tile
+    float* sX = sY + PB * BS_COLS;           // [PB][BS_COLS]   X_j tile
+    float* sU = sX + PB * BS_COLS;           // [PB][BS_ULD]    U[chunk rows][block columns]
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int c0 = blockIdx.y * BS_COLS;
+    const int r0 = blockIdx.x * PB;
+    const bool update = (int)blockIdx.x < a.nchunks;
+    for (int idx = tid; idx < PB * PB / 4; idx += 256) cp_async16(sWt + idx * 4, a.Wt + idx * 4, true);
+    for (int idx = tid; idx < PB * BS_COLS; idx += 256) {
+        const int k = idx >> 6, c = idx & (BS_COLS - 1);
+        const bool ok = k < a.nb && c0 + c < a.M;
+        cp_async4(sY + idx, ok ? a.G + (long long)(a.j + k) * a.ldg + a.D + c0 + c : a.G, ok);
+    }
+    if (update) {
+        const float* Ub = a.G + (long long)r0 * a.ldg + a.j;
+        if ((a.ldg & 3) == 0 && (reinterpret_cast<uintptr_t>(Ub) & 15) == 0 && (a.nb & 3) == 0) {
+            for (int idx = tid; idx < PB * PB / 4; idx += 256) {
+                const int i = idx >> 5, k = (idx & 31) * 4;
+                cp_async16(sU + i * BS_ULD + k, Ub + (long long)i * a.ldg + k, k < a.nb);
+            }
+        } else {
+            for (int idx = tid; idx < PB * PB; idx += 256) {
+                const int i = idx >> 7, k = idx & (PB - 1);
+                cp_async4(sU + i * BS_ULD + k, Ub + (long long)i * a.ldg + k, k < a.nb);
+            }
+        }
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    float acc[8][4];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) { acc[m][0] = acc[m][1] = acc[m][2] = acc[m][3] = 0.f; }
+#pragma unroll 4
+    for (int k = 0; k < PB; ++k) {
+        const float4 w0 = *reinterpret_cast<const float4*>(sWt + k * PB + ty * 8);
+        const float4 w1 = *reinterpret_cast<const float4*>(sWt + k * PB + ty * 8 + 4);
+        const float4 yv = *reinterpret_cast<const float4*>(sY + k * BS_COLS + tx * 4);
+        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            acc[m][0] = fmaf(wv[m], yv.x, acc[m][0]); acc[m][1] = fmaf(wv[m], yv.y, acc[m][1]);
+            acc[m][2] = fmaf(wv[m], yv.z, acc[m][2]); acc[m][3] = fmaf(wv[m], yv.w, acc[m][3]);
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+        const int i = ty * 8 + m;
+        *reinterpret_cast<float4*>(sX + i * BS_COLS + tx * 4) = make_float4(acc[m][0], acc[m][1], acc[m][2], acc[m][3]);
+        if (blockIdx.x == 0 && i < a.nb) {
+#pragma unroll
+            for (int n = 0; n < 4; ++n)
+                if (c0 + tx * 4 + n < a.M) a.X[(long long)(a.j + i) * a.M + c0 + tx * 4 + n] = acc[m][n];
+        }
+    }
+    if (!update) return;
+    __syncthreads();
+#pragma unroll
+    for (int m = 0; m < 8; ++m) { acc[m][0] = acc[m][1] = acc[m][2] = acc[m][3] = 0.f; }
+#pragma unroll 4
+    for (int k = 0; k < PB; ++k) {
+        const float4 xv = *reinterpret_cast<const float4*>(sX + k * BS_COLS + tx * 4);
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            const float u = sU[(ty * 8 + m) * BS_ULD + k];
+            acc[m][0] = fmaf(u, xv.x, acc[m][0]); acc[m][1] = fmaf(u, xv.y, acc[m][1]);
+            acc[m][2] = fmaf(u, xv.z, acc[m][2]); acc[m][3] = fmaf(u, xv.w, acc[m][3]);
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+        float* row = a.G + (long long)(r0 + ty * 8 + m) * a.ldg + a.D + c0 + tx * 4;
+#pragma unroll
+        for (int n = 0; n < 4; ++n)
+            if (c0 + tx * 4 + n < a.M) row[n] -= acc[m][n];
     }
 }
 
@@ -916,19 +1015,19 @@ int cholesky_solve(sd_ctx* ctx, float* G, int64_t ldg, int D, int M, float* X)
     }
     SD_CUDA(ctx, cudaStreamWaitEvent(main_s, ev_chain, 0));
     SD_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));   // end of "Decomposition"
-    // ---- back substitution U X = Y, right-looking over block columns from the last ----
+    // ---- back substitution U X = Y, right-looking over block columns from the last: one launch per block ----
+    const size_t smem_bs = (size_t)(PB * PB + 2 * PB * BS_COLS + PB * BS_ULD) * sizeof(float);
+    SD_CUDA(ctx, cudaFuncSetAttribute(backsub_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bs));
     for (int b = nblocks - 1; b >= 0; --b) {
-        const int j = b * kCholNb;
-        const int nb = (D - j < kCholNb) ? D - j : kCholNb;
-        const float* Wb = inv + (size_t)b * 2 * PB * PB;
-        float* Yj = G + (int64_t)j * ldg + D;
-        float* Xj = X + (int64_t)j * M;
-        int rc = launch_gemm_nn(ctx, Wb, PB, nb, nb, Yj, ldg, M, Xj, M, 1.0f, 0.0f, ep);     // X_j = U_jj^-1 Y_j
-        if (rc) return rc;
-        if (j > 0) {
-            rc = launch_gemm_nn(ctx, G + j, ldg, j, nb, Xj, M, M, G + D, ldg, -1.0f, 1.0f, ep);   // Y[0:j] -= U[0:j, j:j+nb] X_j
-            if (rc) return rc;
-        }
+        BackArgs ba;
+        ba.G = G; ba.ldg = ldg; ba.D = D; ba.M = M; ba.j = b * kCholNb;
+        ba.nb = (D - ba.j < kCholNb) ? D - ba.j : kCholNb;
+        ba.nchunks = b;                                              // full 128-row chunks above block b
+        ba.Wt = inv + (size_t)b * 2 * PB * PB + PB * PB;
+        ba.X = X;
+        const dim3 grid(b > 0 ? b : 1, sd_div_up(M, BS_COLS));
+        backsub_step_kernel<<<grid, 256, smem_bs, main_s>>>(ba);
+        SD_LAUNCH_CHECK(ctx, "backsub_step_kernel");
     }
     return SD_OK;
 }
