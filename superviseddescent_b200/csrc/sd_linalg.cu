@@ -449,12 +449,13 @@ __global__ void copy_block_kernel(const float* __restrict__ src, long long lds, 
 
 // ---- blocked Cholesky G = U^T U (upper), right-looking ---------------------------------------------
 // One CTA factors a 128 x 128 diagonal block and inverts the factor.  Inner blocking by 32: the 32 x 32
-// diagonal sub-block is factored AND inverted by one warp in the same 32 left-looking steps (potrf32_warp), the
+// diagonal sub-block is factored AND inverted in the same 32 right-looking steps on [A | I] (potrf32_block), the
 // row panel and the trailing update inside the block are small register-tiled GEMMs by all 8 warps.  Outputs:
 // U (in place in G), W = U^-1 and W^T (workspace) -- so that the panel solve U12 = U11^-T G12 and the back
 // substitution X_j = U_jj^-1 Y_j become plain GEMMs.  Blocks narrower than 128 are padded with the identity.
 // Phase timings (clock64, -DSD_PROFILE_POTRF + tools_potrf_prof.py): 369k cycles before the restructuring
-// (4 x 65k in the single-warp phases), 146k after (load 10k, 4 x 21k potrf32, panels 8k, trailing 10k, W 28k, store 5k).
+// (4 x 65k in the single-warp phases), ~120k now (load 5k, 4 x 14.6k potrf32, panels 8k, trailing 10k, W 28k, store 7k;
+// the fused rank-128 update of the look-ahead path adds ~30k).
 constexpr int PB = 128, PS = 32, PLD = PB + 1;
 #ifdef SD_PROFILE_POTRF
 __device__ long long sd_dbg_clk[64];
@@ -483,42 +484,52 @@ __device__ __forceinline__ void cp_async_wait_all()
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
-// Factor and invert the 32 x 32 diagonal sub-block at (k0, k0) of sA with ONE warp (lane j owns column j).
-// Rolled loops on shared memory with broadcast reads: a fully unrolled register/shuffle variant was measured no
-// faster -- its ~50 KB of straight-line code thrashes the instruction cache of a lone warp.
-__device__ __forceinline__ void potrf32_warp(float* sA, float* sT, int k0, int lane, bool& bad)
+// Factor and invert the 32 x 32 diagonal sub-block at (k0, k0) of sA.  History (clock64 per sub-block): single warp,
+// right-looking + separate back substitution 65k cycles; single warp, left-looking with the inverse carried along 21k;
+// whole CTA, right-looking on the augmented block (below) 14.6k.  A fully unrolled register/shuffle version was no
+// faster than the first one: ~50 KB of straight-line code thrashes the instruction cache of a lone warp.
+//
+// Whole CTA, right-looking on the augmented block M = [A | I]
+// (32 x 64, work copy in sM): per pivot k every thread reads the pivot row, rows k+1.. get their rank-1 update
+// (4 rows x 64 columns per pass), the scaled pivot row goes straight to its destination (U -> sA, U^-T -> sT as T).
+// One __syncthreads per pivot; ~190 cycles per pivot instead of ~660 for the single-warp left-looking version.
+constexpr int MLD = 2 * PS + 1;
+constexpr int ULD = PB + 4;          // row pitch of the panel rows staged for the fused update (float4-aligned)
+__device__ __forceinline__ void potrf32_block(float* sA, float* sT, float* sM, int k0, int tid, bool& bad)
 {
-    // One warp factors the 32 x 32 diagonal sub-block D = U^T U in place (upper) and, in the same 32 steps, builds
-    // T = U^-1 by carrying the identity along: the row operations that turn A into U turn I into U^-T.
-    //   row k of U    = (row k of A - sum_{q<k} U[q][k] * U[q][:])    / U[k][k]
-    //   row k of U^-T = (e_k        - sum_{q<k} U[q][k] * U^-T[q][:]) / U[k][k]
-    // Left-looking, so the dot products have no read-modify-write through shared memory and their loads overlap.
-    // Lane j owns column j; U^-T[k][j] = T[j][k] is kept at sT[j * (PS+1) + k] (conflict-free for both accesses).
-    float* D = sA + k0 * PLD + k0;                 // D[i][j] at D[i * PLD + j]
-    float* E = sT + lane * (PS + 1);               // E[q] = U^-T[q][lane]
+    const int c = tid & 63, g = tid >> 6;
+    for (int idx = tid; idx < PS * 2 * PS; idx += 256) {
+        const int r = idx >> 6, cc = idx & 63;
+        sM[r * MLD + cc] = (cc < PS) ? sA[(k0 + r) * PLD + k0 + cc] : ((cc - PS == r) ? 1.f : 0.f);
+    }
+    __syncthreads();
     for (int k = 0; k < PS; ++k) {
-        float s[4] = {0.f, 0.f, 0.f, 0.f}, e[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int q = 0; q < k; q += 4) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const bool in = q + u < k;
-                const float c = in ? D[(q + u) * PLD + k] : 0.f;
-                const float dv = in ? D[(q + u) * PLD + lane] : 0.f;
-                const float ev = in ? E[q + u] : 0.f;
-                s[u] = fmaf(c, dv, s[u]);
-                e[u] = fmaf(c, ev, e[u]);
-            }
-        }
-        const float a = D[k * PLD + lane] - ((s[0] + s[1]) + (s[2] + s[3]));
-        const float w = (lane == k ? 1.f : 0.f) - ((e[0] + e[1]) + (e[2] + e[3]));
-        const float pk = __shfl_sync(0xffffffffu, a, k);
+        const float pk = sM[k * MLD + k];
         if (!(pk > 0.f)) bad = true;
         const float pks = pk > 0.f ? pk : 1.f;
-        float inv = rsqrtf(pks);                                  // MUFU + one Newton step instead of sqrt and divide
-        inv = inv * fmaf(-0.5f * pks * inv, inv, 1.5f);
-        if (lane >= k) D[k * PLD + lane] = (lane == k) ? pks * inv : a * inv;
-        E[k] = w * inv;                                           // exactly 0 for lane > k
-        __syncwarp();
+        float rinv = rsqrtf(pks);
+        rinv = rinv * fmaf(-0.5f * pks * rinv, rinv, 1.5f);        // one Newton step
+        const float pr = sM[k * MLD + c];
+        const float ps = pr * rinv;                                // scaled pivot row = row k of [U | U^-T]
+        if (g == 0) {
+            if (c < PS) { if (c >= k) sA[(k0 + k) * PLD + k0 + c] = (c == k) ? pks * rinv : ps; }
+            else sT[(c - PS) * (PS + 1) + k] = (c - PS <= k) ? ps : 0.f;      // T[e][k] = U^-T[k][e]
+        }
+        // up to 8 rows per thread: all loads first, then the stores (a rolled loop serialises on possible aliasing)
+        float f[8], o[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = k + 1 + g + 4 * u;
+            const bool ok = i < PS;
+            f[u] = ok ? sM[k * MLD + i] : 0.f;
+            o[u] = ok ? sM[i * MLD + c] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = k + 1 + g + 4 * u;
+            if (i < PS) sM[i * MLD + c] = fmaf(-(f[u] * rinv), ps, o[u]);      // f * rinv = U[k][i]
+        }
+        __syncthreads();
     }
 }
 
@@ -532,6 +543,7 @@ __global__ void __launch_bounds__(256) potrf_inv_kernel(float* __restrict__ G, l
     float* sA = sm;                    // PB x PLD : the block, becomes U
     float* sW = sm + PB * PLD;         // PB x PLD : U^-1
     float* sT = sW + PB * PLD;         // PS x (PS+1) scratch (inverse of the current diagonal sub-block / partial sums)
+    float* sM = sT + PS * (PS + 1);    // PS x MLD work copy of [A | I] for potrf32_block
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     SD_CLK(0);
     // the block (upper triangle, identity padding outside nb) and, for the fused update, the panel rows A go to shared
@@ -543,7 +555,7 @@ __global__ void __launch_bounds__(256) potrf_inv_kernel(float* __restrict__ G, l
         else sA[i * PLD + j] = (i == j && i >= nb) ? 1.f : 0.f;
         if (A) {
             const bool oka = i < nk && j < nb;                      // here i = panel row q, j = column of the block
-            cp_async4(sW + i * PLD + j, oka ? A + (long long)i * lda + j : A, oka);
+            cp_async4(sW + i * ULD + j, oka ? A + (long long)i * lda + j : A, oka);   // 16-byte aligned rows (spills into sT/sM)
         } else {
             sW[i * PLD + j] = 0.f;
         }
@@ -551,7 +563,7 @@ __global__ void __launch_bounds__(256) potrf_inv_kernel(float* __restrict__ G, l
     cp_async_wait_all();
     if (A) {
         __syncthreads();
-        const int tx = tid & 15, ty = tid >> 4;                   // rows ty*8 + m, columns tx + 16*n (conflict-free)
+        const int tx = tid & 15, ty = tid >> 4;                   // rows ty*8 + m, columns tx*4 + n and 64 + tx*4 + n
         float acc[8][8];
 #pragma unroll
         for (int m = 0; m < 8; ++m)
@@ -559,11 +571,12 @@ __global__ void __launch_bounds__(256) potrf_inv_kernel(float* __restrict__ G, l
             for (int n = 0; n < 8; ++n) acc[m][n] = 0.f;
 #pragma unroll 4
         for (int q = 0; q < PB; ++q) {
-            float ar[8], ac[8];
-#pragma unroll
-            for (int m = 0; m < 8; ++m) ar[m] = sW[q * PLD + ty * 8 + m];
-#pragma unroll
-            for (int n = 0; n < 8; ++n) ac[n] = sW[q * PLD + tx + 16 * n];
+            const float4 r0 = *reinterpret_cast<const float4*>(sW + q * ULD + ty * 8);
+            const float4 r1 = *reinterpret_cast<const float4*>(sW + q * ULD + ty * 8 + 4);
+            const float4 c0 = *reinterpret_cast<const float4*>(sW + q * ULD + tx * 4);
+            const float4 c1 = *reinterpret_cast<const float4*>(sW + q * ULD + 64 + tx * 4);
+            const float ar[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+            const float ac[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
 #pragma unroll
             for (int m = 0; m < 8; ++m)
 #pragma unroll
@@ -573,21 +586,24 @@ __global__ void __launch_bounds__(256) potrf_inv_kernel(float* __restrict__ G, l
         for (int m = 0; m < 8; ++m)
 #pragma unroll
             for (int n = 0; n < 8; ++n) {
-                const int i = ty * 8 + m, j = tx + 16 * n;
+                const int i = ty * 8 + m, j = (n < 4 ? 0 : 60) + tx * 4 + n;
                 if (j >= i && j < nb) sA[i * PLD + j] -= acc[m][n];
             }
         __syncthreads();
-        for (int idx = tid; idx < PB * PB; idx += 256) sW[(idx >> 7) * PLD + (idx & (PB - 1))] = 0.f;
+        for (int idx = tid; idx < PB * PLD; idx += 256) sW[idx] = 0.f;
     }
     __syncthreads();
     SD_CLK(1);
     for (int kb = 0; kb < PB / PS; ++kb) {
         const int k0 = kb * PS;
-        if (warp == 0) {
+        {
             bool bad = false;
-            potrf32_warp(sA, sT, k0, lane, bad);
-            if (bad && lane == 0) atomicOr(status, 8);                  // not positive definite
-            for (int i = 0; i < PS; ++i) sW[(k0 + i) * PLD + k0 + lane] = sT[i * (PS + 1) + lane];
+            potrf32_block(sA, sT, sM, k0, tid, bad);
+            if (bad && tid == 0) atomicOr(status, 8);                   // not positive definite
+            for (int idx = tid; idx < PS * PS; idx += 256) {
+                const int i = idx >> 5, jj = idx & 31;
+                sW[(k0 + i) * PLD + k0 + jj] = sT[i * (PS + 1) + jj];
+            }
         }
         __syncthreads();
         SD_CLK(2 + kb * 3);
@@ -918,7 +934,7 @@ int cholesky_solve(sd_ctx* ctx, float* G, int64_t ldg, int D, int M, float* X)
     int* status = reinterpret_cast<int*>(ctx->d_scratch);
     const int W_ = D + M;
     const int nblocks = sd_div_up(D, kCholNb);
-    const size_t smem_potrf = (size_t)(2 * PB * PLD + PS * (PS + 1)) * sizeof(float);
+    const size_t smem_potrf = (size_t)(2 * PB * PLD + PS * (PS + 1) + PS * MLD) * sizeof(float);
     SD_CUDA(ctx, cudaFuncSetAttribute(potrf_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_potrf));
     SD_CUDA(ctx, cudaFuncSetAttribute(trsm_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)((PB * PB + PB * TA_COLS) * sizeof(float) * 2)));
