@@ -171,3 +171,38 @@ def test_pose_estimation_example_config2(sd, oracle):
     print("predicted pitch/yaw/roll", pred[:3], "oracle", ref[:3])
     assert np.max(np.abs(pred - ref)) <= 1e-4 * np.max(np.abs(ref))
     assert np.all(np.abs(pred[:3] - np.array([11.0, -25.0, -10.0])) < 6.0)
+
+
+@pytest.mark.parametrize("D,M,pad", [(257, 1, 0), (300, 8, 0), (384, 44, 0), (385, 44, 1), (513, 3, 2), (640, 70, 0),
+                                     (1000, 44, 3), (1153, 136, 0)])
+def test_blocked_cholesky_shapes(sd, D, M, pad):
+    """sd_solve_gram on well-conditioned SPD systems of awkward shapes: D just above the LU limit, odd numbers of
+    128-blocks (a panel with a single block), ragged last blocks, right-hand sides wider than one column tile, and
+    leading dimensions that are not a multiple of 4 (scalar staging, SIMT trailing updates instead of TMA).  Manual
+    regularisation lambda = 0.5 is added to the diagonal as regressors.hpp:126-148 does (bias row unregularised)."""
+    import ctypes as C
+    import torch
+    from superviseddescent_b200 import _capi
+    rng = np.random.default_rng(D * 7 + M)
+    Q = rng.standard_normal((D + 40, D))
+    G64 = Q.T @ Q / (D + 40) + np.eye(D)                      # condition number of a few units
+    R64 = rng.standard_normal((D, M))
+    ldg = D + M + pad
+    Gh = np.zeros((D, ldg), np.float32)
+    Gh[:, :D] = np.triu(G64)                                  # only the upper triangle is an input
+    Gh[:, D:D + M] = R64
+    lam = 0.5
+    Greg = G64.copy()
+    Greg[np.arange(D - 1), np.arange(D - 1)] += np.float32(lam)   # regularise_last_row = false
+    Xo = np.linalg.solve(Greg.astype(np.float32).astype(np.float64), R64.astype(np.float32).astype(np.float64))
+    ctx = sd.default_context()
+    G = torch.from_numpy(Gh).cuda()
+    X = torch.zeros((D, M), dtype=torch.float32, device="cuda")
+    reg = _capi.RegulariserC(0, lam, 0)
+    lam_out = C.c_float(0)
+    rc = _capi.lib().sd_solve_gram(ctx.h, _capi.ptr(G), C.c_int64(ldg), D, M, C.byref(reg), 1, _capi.ptr(X), C.byref(lam_out))
+    assert rc == 0, _capi.lib().sd_last_error(ctx.h)
+    assert abs(lam_out.value - lam) < 1e-7
+    err = rel_err(X.cpu().numpy(), Xo)
+    print(f"D={D} M={M} ldg={ldg}: X rel err {err:.2e}")
+    assert err <= 2e-5
