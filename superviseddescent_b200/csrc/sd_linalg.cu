@@ -453,7 +453,7 @@ __global__ void copy_block_kernel(const float* __restrict__ src, long long lds, 
 // row panel and the trailing update inside the block are small register-tiled GEMMs by all 8 warps.  Outputs:
 // U (in place in G), W = U^-1 and W^T (workspace) -- so that the panel solve U12 = U11^-T G12 and the back
 // substitution X_j = U_jj^-1 Y_j become plain GEMMs.  Blocks narrower than 128 are padded with the identity.
-// Phase timings (clock64, -DSD_PROFILE_POTRF + tools_potrf_prof.py): 369k cycles before the restructuring
+// Phase timings (clock64, -DSD_PROFILE_POTRF + tools/potrf_prof.py): 369k cycles before the restructuring
 // (4 x 65k in the single-warp phases), ~120k now (load 5k, 4 x 14.6k potrf32, panels 8k, trailing 10k, W 28k, store 7k;
 // the fused rank-128 update of the look-ahead path adds ~30k).
 constexpr int PB = 128, PS = 32, PLD = PB + 1;

@@ -1,3 +1,4 @@
+"""Probes variants of the host-frame route of sd_detect_batch_host.  Development helper, not part of the product."""
 import os, sys, time, numpy as np, torch
 sys.path.insert(0, "/root/repo")
 import bench

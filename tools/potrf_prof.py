@@ -1,3 +1,5 @@
+"""Prints the clock64 phase timings of potrf_inv_kernel from the instrumented library (tools/build_prof.sh).
+Development helper, not part of the product."""
 import ctypes as C, os, sys, numpy as np, torch
 sys.path.insert(0, "/root/repo")
 from superviseddescent_b200 import _capi

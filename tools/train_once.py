@@ -1,3 +1,5 @@
+"""Times the levels of the config-4 training run once (LEVELS=n selects how many); the command the ncu launch lists and
+captures in profiles/ were taken with.  Development helper, not part of the product."""
 import sys, os, numpy as np, torch
 sys.path.insert(0, "/root/repo")
 import bench
