@@ -143,6 +143,14 @@ SD_API int sd_hog_debug(sd_ctx* ctx, const sd_image_batch* images, const int32_t
                         uint8_t* d_patches /* N*L*fs*fs or NULL */,
                         int8_t* d_bins /* N*L*fs*fs or NULL, -1 on border / zero gradient */);
 
+/* Colour frames: HogTransform::operator() converts 3-channel images with cv::cvtColor(BGR2GRAY) before anything else
+ * (adaptive_vlhog.hpp:114-120).  Same conversion on the device, once per frame instead of once per call:
+ *   gray = (3735 B + 19235 G + 9798 R + 2^14) >> 15      (OpenCV >= 3 fixed point; SURVEY.md 8c, pinned against cv2)
+ * d_bgr: count frames of height x width interleaved B,G,R bytes; strides in bytes. */
+SD_API int sd_bgr2gray(sd_ctx* ctx, const uint8_t* d_bgr, int width, int height, int64_t bgr_row_stride,
+                       int64_t bgr_image_stride, int count, uint8_t* d_gray, int64_t gray_row_stride,
+                       int64_t gray_image_stride);
+
 /* ---- regressor: LinearRegressor<Solver> (regressors.hpp:318-400) ------------------------ */
 /* Solver::solve (regressors.hpp:199-234 == verbose_solver.hpp:53-111):
  *   X = (A^T A + Lambda)^-1 A^T B ;  A: N x D, B: N x M, X: D x M (ldx_out = M).

@@ -42,7 +42,7 @@ class ImageBatchC(C.Structure):
 EXPORTS = [
     "sd_ctx_create", "sd_ctx_destroy", "sd_last_error", "sd_sync", "sd_version", "sd_launch_count", "sd_roi_fallback_count",
     "sd_malloc", "sd_free", "sd_host_alloc", "sd_host_free", "sd_memcpy_h2d", "sd_memcpy_d2h", "sd_memset",
-    "sd_hog_feature_length", "sd_hog_batch", "sd_hog_debug",
+    "sd_hog_feature_length", "sd_hog_batch", "sd_hog_debug", "sd_bgr2gray",
     "sd_learn", "sd_gram", "sd_solve_gram", "sd_predict", "sd_test_residual", "sd_solver_timings", "sd_set_gram_mode",
     "sd_cascade_targets", "sd_cascade_update", "sd_subtract_templates",
     "sd_model_load", "sd_model_save", "sd_model_create", "sd_model_destroy", "sd_model_num_levels",

@@ -214,8 +214,26 @@ class InterEyeDistanceNormalisation:
 # ------------------------------------------------------------------------------------------------
 # rcr::HogTransform (adaptive_vlhog.hpp:70-195), batched
 # ------------------------------------------------------------------------------------------------
+def bgr2gray(images, ctx: Optional["Context"] = None) -> torch.Tensor:
+    """cv::cvtColor(BGR2GRAY) on the device (adaptive_vlhog.hpp:114-120): (count, H, W, 3) uint8 -> (count, H, W) uint8.
+    Host arrays are uploaded first; the result stays in HBM."""
+    ctx = ctx or default_context()
+    t = images if isinstance(images, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(images))
+    if t.dim() == 3:
+        t = t.unsqueeze(0)
+    if t.dtype != torch.uint8 or t.dim() != 4 or t.shape[3] != 3:
+        raise ValueError("images must be (count, H, W, 3) uint8 (interleaved B, G, R)")
+    t = t.to(f"cuda:{ctx.device}").contiguous()
+    n, h, w, _ = t.shape
+    out = torch.empty((n, h, w), dtype=torch.uint8, device=t.device)
+    _check(ctx.h, _capi.lib().sd_bgr2gray(ctx.h, ptr(t), w, h, C.c_int64(t.stride(1)), C.c_int64(t.stride(0)), n,
+                                          ptr(out), C.c_int64(out.stride(1)), C.c_int64(out.stride(0))))
+    return out
+
+
 class HogTransform:
-    """Projection functor h.  images: (count, H, W) uint8 (8UC1) on host or device.
+    """Projection functor h.  images: (count, H, W) uint8 (8UC1) or (count, H, W, 3) uint8 (8UC3, B G R: converted
+    once on the device as adaptive_vlhog.hpp:114-120 does per call), on host or device.
 
     __call__(parameters, regressor_level, training_index) keeps the reference's meaning
     (adaptive_vlhog.hpp:109) but takes ALL rows at once: parameters is (N, 2L) and training_index an
@@ -229,8 +247,10 @@ class HogTransform:
         imgs = images if isinstance(images, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(images))
         if imgs.dim() == 2:
             imgs = imgs.unsqueeze(0)
+        if imgs.dtype == torch.uint8 and imgs.dim() == 4 and imgs.shape[3] == 3:
+            imgs = bgr2gray(imgs, self.ctx)
         if imgs.dtype != torch.uint8 or imgs.dim() != 3:
-            raise ValueError("images must be (count, H, W) uint8 (single channel)")
+            raise ValueError("images must be (count, H, W) uint8 or (count, H, W, 3) uint8")
         self.images = imgs.to(f"cuda:{self.ctx.device}").contiguous()
         self.hog_params = list(hog_params)
         self.norm = InterEyeDistanceNormalisation(model_landmarks_list, right_eye_identifiers, left_eye_identifiers)
@@ -470,11 +490,18 @@ class detection_model:
         return self.detect_batch_device(imgs, x0).cpu().numpy()[0]
 
     def detect_batch(self, images: np.ndarray, boxes: np.ndarray) -> np.ndarray:
-        """Batched detect(image, facebox) with HOST buffers (copies are part of the call)."""
+        """Batched detect(image, facebox) with HOST buffers (copies are part of the call).  Colour frames
+        (count, H, W, 3) are converted on the device first (model.hpp:134-145 calls cvtColor through HogTransform)."""
         if isinstance(images, torch.Tensor):
             images_np = images.numpy()
         else:
             images_np = np.ascontiguousarray(images, dtype=np.uint8)
+        if images_np.ndim == 4:
+            gray = bgr2gray(images_np, self.ctx)
+            n = gray.shape[0]
+            b = np.ascontiguousarray(boxes, dtype=np.int32).reshape(n, 4)
+            x0 = torch.from_numpy(np.stack([align_mean(self.get_mean(), tuple(int(v) for v in b[i])) for i in range(n)]).astype(np.float32))
+            return self.detect_batch_device(gray, x0.to(gray.device)).cpu().numpy()
         n, h, w = images_np.shape
         boxes = np.ascontiguousarray(boxes, dtype=np.int32).reshape(n, 4)
         out = np.empty((n, 2 * self.num_landmarks), dtype=np.float32)

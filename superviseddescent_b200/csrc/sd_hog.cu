@@ -680,6 +680,43 @@ int launch_hog(sd_ctx* ctx, const sd_image_batch* images, const int32_t* d_image
 
 }  // namespace
 
+namespace {
+// cv::cvtColor(BGR2GRAY), 8-bit, OpenCV >= 3 fixed point (15-bit coefficients): HBM-bound, 3 bytes read + 1 written per
+// pixel.  A thread converts four pixels: three aligned 32-bit loads, one 32-bit store (scalar path for the row tail or
+// unaligned rows).
+__global__ void bgr2gray_kernel(const uint8_t* __restrict__ bgr, int width, int height, long long srow, long long simg, int count,
+                                uint8_t* __restrict__ gray, long long drow, long long dimg, int vec_ok)
+{
+    const int groups = (width + 3) >> 2;
+    const long long total = (long long)count * height * groups;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int g = (int)(t % groups);
+        const long long ry = t / groups;
+        const int y = (int)(ry % height);
+        const long long im = ry / height;
+        const uint8_t* s = bgr + im * simg + (long long)y * srow + 12 * g;
+        uint8_t* d = gray + im * dimg + (long long)y * drow + 4 * g;
+        const int x0 = 4 * g;
+        if (vec_ok && x0 + 4 <= width) {
+            const uint32_t w0 = *reinterpret_cast<const uint32_t*>(s), w1 = *reinterpret_cast<const uint32_t*>(s + 4),
+                           w2 = *reinterpret_cast<const uint32_t*>(s + 8);
+            // bytes: w0 = B0 G0 R0 B1 | w1 = G1 R1 B2 G2 | w2 = R2 B3 G3 R3   (little endian)
+            const uint32_t b0 = w0 & 255, g0 = (w0 >> 8) & 255, r0 = (w0 >> 16) & 255, b1 = w0 >> 24;
+            const uint32_t g1 = w1 & 255, r1 = (w1 >> 8) & 255, b2 = (w1 >> 16) & 255, g2 = w1 >> 24;
+            const uint32_t r2 = w2 & 255, b3 = (w2 >> 8) & 255, g3 = (w2 >> 16) & 255, r3 = w2 >> 24;
+            const uint32_t y0 = (3735u * b0 + 19235u * g0 + 9798u * r0 + (1u << 14)) >> 15;
+            const uint32_t y1 = (3735u * b1 + 19235u * g1 + 9798u * r1 + (1u << 14)) >> 15;
+            const uint32_t y2 = (3735u * b2 + 19235u * g2 + 9798u * r2 + (1u << 14)) >> 15;
+            const uint32_t y3 = (3735u * b3 + 19235u * g3 + 9798u * r3 + (1u << 14)) >> 15;
+            *reinterpret_cast<uint32_t*>(d) = y0 | (y1 << 8) | (y2 << 16) | (y3 << 24);
+        } else {
+            for (int k = 0; k < 4 && x0 + k < width; ++k)
+                d[k] = (uint8_t)((3735u * s[3 * k] + 19235u * s[3 * k + 1] + 9798u * s[3 * k + 2] + (1u << 14)) >> 15);
+        }
+    }
+}
+}  // namespace
+
 extern "C" {
 
 int sd_hog_feature_length(int num_landmarks, const sd_hog_param* p)
@@ -707,6 +744,23 @@ int sd_hog_debug(sd_ctx* ctx, const sd_image_batch* images, const int32_t* d_ima
     if (!ctx) return SD_ERR_INVALID;
     return launch_hog(ctx, images, d_image_index, d_x, ldx, num_samples, num_landmarks, eyes, p, nullptr, 0,
                       d_geometry, d_patches, d_bins);
+}
+
+int sd_bgr2gray(sd_ctx* ctx, const uint8_t* d_bgr, int width, int height, int64_t bgr_row_stride, int64_t bgr_image_stride,
+                int count, uint8_t* d_gray, int64_t gray_row_stride, int64_t gray_image_stride)
+{
+    if (!ctx) return SD_ERR_INVALID;
+    SD_REQUIRE(ctx, count >= 0 && width > 0 && height > 0, "bad argument");
+    if (count == 0) return SD_OK;
+    SD_REQUIRE(ctx, d_bgr && d_gray && bgr_row_stride >= 3LL * width && gray_row_stride >= width, "bad argument");
+    const int vec_ok = ((reinterpret_cast<uintptr_t>(d_bgr) | reinterpret_cast<uintptr_t>(d_gray) | (uintptr_t)bgr_row_stride |
+                         (uintptr_t)bgr_image_stride | (uintptr_t)gray_row_stride | (uintptr_t)gray_image_stride) & 3) == 0;
+    const long long total = (long long)count * height * ((width + 3) >> 2);
+    const int blocks = (int)(sd_div_up(total, 256) < 16LL * ctx->sm_count ? sd_div_up(total, 256) : 16LL * ctx->sm_count);
+    bgr2gray_kernel<<<blocks, 256, 0, ctx->stream>>>(d_bgr, width, height, bgr_row_stride, bgr_image_stride, count, d_gray,
+                                                     gray_row_stride, gray_image_stride, vec_ok);
+    SD_LAUNCH_CHECK(ctx, "bgr2gray_kernel");
+    return SD_OK;
 }
 
 }  // extern "C"

@@ -90,24 +90,21 @@ private:
         const size_t frame = static_cast<size_t>(w) * h;
         dev->buf.allocate(frame * images.size());
         sd_ctx* ctx = sd_b200::context();
-        std::vector<unsigned char> gray;
+        sd_b200::DeviceBuffer bgr;                 // staging for one colour frame
         for (size_t i = 0; i < images.size(); ++i) {
             const cv::Mat& im = images[i];
             if (im.cols != w || im.rows != h) throw std::runtime_error("HogTransform: the batched device path needs equally sized images");
-            const unsigned char* src = nullptr;
+            unsigned char* d_frame = dev->buf.as<unsigned char>() + i * frame;
             if (im.channels() == 3) {
-                // cv::cvtColor(BGR2GRAY), adaptive_vlhog.hpp:115-117 (cv2 >= 3 fixed-point constants)
-                gray.resize(frame);
-                for (int y = 0; y < h; ++y) {
-                    const unsigned char* s = im.ptr<unsigned char>(y);
-                    for (int x = 0; x < w; ++x) gray[static_cast<size_t>(y) * w + x] = static_cast<unsigned char>((3735 * s[3 * x] + 19235 * s[3 * x + 1] + 9798 * s[3 * x + 2] + (1 << 14)) >> 15);
-                }
-                src = gray.data();
-                sd_b200::check(ctx, sd_memcpy_h2d(ctx, dev->buf.as<unsigned char>() + i * frame, src, frame), "HogTransform upload");
-                sd_b200::check(ctx, sd_sync(ctx), "HogTransform upload");
+                // cv::cvtColor(BGR2GRAY), adaptive_vlhog.hpp:115-117: on the device, once per frame (sd_bgr2gray)
+                bgr.allocate(3 * frame);
+                for (int y = 0; y < h; ++y)
+                    sd_b200::check(ctx, sd_memcpy_h2d(ctx, bgr.as<unsigned char>() + static_cast<size_t>(y) * 3 * w, im.ptr<unsigned char>(y), 3 * static_cast<size_t>(w)), "HogTransform upload");
+                sd_b200::check(ctx, sd_bgr2gray(ctx, bgr.as<unsigned char>(), w, h, 3 * static_cast<int64_t>(w), 3 * static_cast<int64_t>(frame), 1,
+                                                d_frame, w, static_cast<int64_t>(frame)), "sd_bgr2gray");
             } else {
                 for (int y = 0; y < h; ++y)
-                    sd_b200::check(ctx, sd_memcpy_h2d(ctx, dev->buf.as<unsigned char>() + i * frame + static_cast<size_t>(y) * w, im.ptr<unsigned char>(y), w), "HogTransform upload");
+                    sd_b200::check(ctx, sd_memcpy_h2d(ctx, d_frame + static_cast<size_t>(y) * w, im.ptr<unsigned char>(y), w), "HogTransform upload");
             }
         }
         sd_b200::check(ctx, sd_sync(ctx), "HogTransform upload");

@@ -101,11 +101,10 @@ public:
     LandmarkCollection<cv::Vec2f> detect(cv::Mat image, cv::Mat initialisation)
     {
         sd_ctx* ctx = sd_b200::context();
-        const cv::Mat gray = to_gray(image);
+        const cv::Mat& gray = image;               // size only; colour frames are converted on the device
         const size_t frame = static_cast<size_t>(gray.cols) * gray.rows;
-        sd_b200::DeviceBuffer dimg(frame), dx, dout(static_cast<size_t>(initialisation.cols) * sizeof(float));
-        for (int y = 0; y < gray.rows; ++y)
-            sd_b200::check(ctx, sd_memcpy_h2d(ctx, dimg.as<unsigned char>() + static_cast<size_t>(y) * gray.cols, gray.ptr<unsigned char>(y), gray.cols), "detect");
+        sd_b200::DeviceBuffer dimg(frame), dx, dout(static_cast<size_t>(initialisation.cols) * sizeof(float)), bgr;
+        upload_gray(ctx, image, dimg.as<unsigned char>(), bgr);
         sd_b200::upload(initialisation, dx, initialisation.cols);
         sd_image_batch ib{};
         ib.d_data = dimg.as<unsigned char>(); ib.width = gray.cols; ib.height = gray.rows; ib.row_stride = gray.cols; ib.image_stride = static_cast<int64_t>(frame); ib.count = 1;
@@ -121,11 +120,35 @@ public:
         const int n = static_cast<int>(images.size());
         const int w = images[0].cols, h = images[0].rows;
         const int P = 2 * sd_model_num_landmarks(handle.get());
+        bool colour = false;
+        for (int i = 0; i < n; ++i) {
+            if (images[i].cols != w || images[i].rows != h) throw std::runtime_error("detect: the batched path needs equally sized images");
+            colour = colour || images[i].channels() == 3;
+        }
+        if (colour) {
+            // colour frames: upload B,G,R, convert on the device (sd_bgr2gray), start from the aligned mean, stay on the device
+            const size_t frame = static_cast<size_t>(w) * h;
+            sd_b200::DeviceBuffer dimg(frame * n), dx(static_cast<size_t>(n) * P * sizeof(float)), dout(static_cast<size_t>(n) * P * sizeof(float)), bgr;
+            std::vector<float> x0(static_cast<size_t>(n) * P);
+            const cv::Mat mean = get_mean();
+            for (int i = 0; i < n; ++i) {
+                upload_gray(ctx, images[i], dimg.as<unsigned char>() + i * frame, bgr);
+                sd_b200::check(ctx, sd_align_mean(mean.ptr<float>(0), P / 2, faceboxes[i].x, faceboxes[i].y, faceboxes[i].width, faceboxes[i].height,
+                                                  1.f, 1.f, 0.f, 0.f, &x0[static_cast<size_t>(i) * P]), "sd_align_mean");
+            }
+            sd_b200::check(ctx, sd_memcpy_h2d(ctx, dx.as<float>(), x0.data(), x0.size() * sizeof(float)), "detect");
+            sd_image_batch ib{};
+            ib.d_data = dimg.as<unsigned char>(); ib.width = w; ib.height = h; ib.row_stride = w; ib.image_stride = static_cast<int64_t>(frame); ib.count = n;
+            sd_b200::check(ctx, sd_detect_batch_device(ctx, handle.get(), &ib, dx.as<float>(), n, dout.as<float>()), "sd_detect_batch_device");
+            const cv::Mat all = sd_b200::download(dout.as<float>(), n, P, P);
+            std::vector<cv::Mat> rows;
+            for (int i = 0; i < n; ++i) rows.push_back(all.row(i).clone());
+            return rows;
+        }
         std::vector<unsigned char> frames(static_cast<size_t>(n) * w * h);
         std::vector<int32_t> boxes(static_cast<size_t>(n) * 4);
         for (int i = 0; i < n; ++i) {
-            const cv::Mat g = to_gray(images[i]);
-            if (g.cols != w || g.rows != h) throw std::runtime_error("detect: the batched path needs equally sized images");
+            const cv::Mat& g = images[i];
             for (int y = 0; y < h; ++y) std::memcpy(&frames[(static_cast<size_t>(i) * h + y) * w], g.ptr<unsigned char>(y), w);
             boxes[4 * i] = faceboxes[i].x; boxes[4 * i + 1] = faceboxes[i].y; boxes[4 * i + 2] = faceboxes[i].width; boxes[4 * i + 3] = faceboxes[i].height;
         }
@@ -151,16 +174,22 @@ public:
 
 private:
     friend detection_model load_detection_model(std::string filename);
-    static cv::Mat to_gray(const cv::Mat& image)
+    // frame -> device as 8UC1; colour frames go up as B,G,R and are converted there
+    // (cv::cvtColor BGR2GRAY of adaptive_vlhog.hpp:115-117 == sd_bgr2gray)
+    static void upload_gray(sd_ctx* ctx, const cv::Mat& image, unsigned char* d_dst, sd_b200::DeviceBuffer& bgr)
     {
-        if (image.channels() != 3) return image;
-        cv::Mat g(image.rows, image.cols, CV_8UC1);   // cv::cvtColor BGR2GRAY (adaptive_vlhog.hpp:115-117)
-        for (int y = 0; y < image.rows; ++y) {
-            const unsigned char* s = image.ptr<unsigned char>(y);
-            unsigned char* d = g.ptr<unsigned char>(y);
-            for (int x = 0; x < image.cols; ++x) d[x] = static_cast<unsigned char>((3735 * s[3 * x] + 19235 * s[3 * x + 1] + 9798 * s[3 * x + 2] + (1 << 14)) >> 15);
+        const int w = image.cols, h = image.rows;
+        const size_t frame = static_cast<size_t>(w) * h;
+        if (image.channels() == 3) {
+            bgr.allocate(3 * frame);
+            for (int y = 0; y < h; ++y)
+                sd_b200::check(ctx, sd_memcpy_h2d(ctx, bgr.as<unsigned char>() + static_cast<size_t>(y) * 3 * w, image.ptr<unsigned char>(y), 3 * static_cast<size_t>(w)), "detect upload");
+            sd_b200::check(ctx, sd_bgr2gray(ctx, bgr.as<unsigned char>(), w, h, 3 * static_cast<int64_t>(w), 3 * static_cast<int64_t>(frame), 1, d_dst, w,
+                                            static_cast<int64_t>(frame)), "sd_bgr2gray");
+        } else {
+            for (int y = 0; y < h; ++y)
+                sd_b200::check(ctx, sd_memcpy_h2d(ctx, d_dst + static_cast<size_t>(y) * w, image.ptr<unsigned char>(y), w), "detect upload");
         }
-        return g;
     }
 
     std::shared_ptr<sd_model> handle;

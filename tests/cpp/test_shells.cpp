@@ -172,6 +172,20 @@ int main(int argc, char** argv)
             std::printf("LANDMARKS");
             for (const auto& l : lms) std::printf(" %s %.6f %.6f", l.name.c_str(), l.coordinates[0], l.coordinates[1]);
             std::printf("\n");
+            // the same frame as a colour image with B = G = R: cvtColor(BGR2GRAY) gives the grey frame back exactly, so the
+            // colour routes (device-side sd_bgr2gray; box and previous-landmarks entry points) must return the same landmarks
+            std::vector<unsigned char> bgr(raw.size() * 3);
+            for (size_t i = 0; i < raw.size(); ++i) bgr[3 * i] = bgr[3 * i + 1] = bgr[3 * i + 2] = raw[i];
+            Mat colour(h, w, CV_8UC3, bgr.data());
+            const cv::Rect box(std::atoi(argv[5]), std::atoi(argv[6]), std::atoi(argv[7]), std::atoi(argv[8]));
+            auto lms_c = m.detect(colour, box);
+            auto lms_t = m.detect(colour, rcr::align_mean(m.get_mean(), box));
+            for (size_t i = 0; i < lms.size(); ++i) {
+                EXPECT_REL(lms[i].coordinates[0], lms_c[i].coordinates[0], 1e-6);
+                EXPECT_REL(lms[i].coordinates[1], lms_c[i].coordinates[1], 1e-6);
+                EXPECT_REL(lms[i].coordinates[0], lms_t[i].coordinates[0], 1e-6);
+                EXPECT_REL(lms[i].coordinates[1], lms_t[i].coordinates[1], 1e-6);
+            }
             rcr::save_detection_model(m, argv[9]);
             try {
                 rcr::load_detection_model("/nonexistent/model.bin");

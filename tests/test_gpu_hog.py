@@ -90,3 +90,25 @@ def test_hog_ragged_and_empty_inputs(sd, oracle, golden):
     assert A[0, -1] == 1.0 and np.all(A[0, :-1] == 0.0)
     with pytest.raises(RuntimeError):
         sd.HogTransform(images, [sd.HoGParam(1, 5, 6, 4, 0.25)], m.landmark_ids, ["nope"], m.left_ids)(far, 0)
+
+
+def test_bgr2gray_device_is_bit_exact(sd, oracle, golden):
+    """cv::cvtColor(BGR2GRAY) (adaptive_vlhog.hpp:114-120) on the device against the cv2-pinned oracle: the golden crop,
+    random frames with widths that exercise the 4-pixel vector path and the scalar tail, and a HogTransform fed with
+    colour frames (must equal the one fed with the converted frames)."""
+    crop = golden.examples["bgr_crop"]
+    got = sd.bgr2gray(crop[None]).cpu().numpy()[0]
+    assert np.array_equal(got, golden.examples["bgr_crop_gray"])
+    rng = np.random.default_rng(5)
+    for (n, h, w) in [(3, 17, 64), (2, 9, 63), (1, 5, 1), (4, 33, 130)]:
+        bgr = rng.integers(0, 256, size=(n, h, w, 3), dtype=np.uint8)
+        want = np.stack([oracle.bgr2gray_u8(bgr[i]) for i in range(n)])
+        assert np.array_equal(sd.bgr2gray(bgr).cpu().numpy(), want), (n, h, w)
+    m = oracle.Model(golden.model_path)
+    bgr = rng.integers(0, 256, size=(2, 120, 160, 3), dtype=np.uint8)
+    gray = np.stack([oracle.bgr2gray_u8(bgr[i]) for i in range(2)])
+    x0 = np.stack([oracle.align_mean(m.mean, (30, 20, 90, 90)) for _ in range(2)]).astype(np.float32)
+    hp = [sd.HoGParam(1, 5, 11, 4, 1.0)]
+    fa = sd.HogTransform(bgr, hp, m.landmark_ids, m.right_ids, m.left_ids)(x0, 0).cpu().numpy()
+    fb = sd.HogTransform(gray, hp, m.landmark_ids, m.right_ids, m.left_ids)(x0, 0).cpu().numpy()
+    assert np.array_equal(fa, fb)
