@@ -129,7 +129,10 @@ SD_API int sd_hog_feature_length(int num_landmarks, const sd_hog_param* p);
 /* For sample i: image = images[d_image_index ? d_image_index[i] : i], landmarks = d_x[i, 0:2L].
  * Writes the reference's feature row (per landmark [dim][cell col][cell row], then bias 1)
  * to d_A[i*ld .. i*ld + D).  Columns [D, ld) are left untouched.  hog.c:174-204,595-728,857-1062
- * run fused with the crop / zero-pad / cv::resize glue of adaptive_vlhog.hpp:123-176. */
+ * run fused with the crop / zero-pad / cv::resize glue of adaptive_vlhog.hpp:123-176.
+ * eyes == NULL (or eyes->kind == 0) selects the NON-adaptive HogTransform of the hello-world example
+ * (examples/landmark_detection.cpp:195-261): patch half-size = num_cells * (cell_size / 2), no resize,
+ * relative_patch_size ignored; cell_size must be even.  That functor has no bias column: use the first D - 1 columns. */
 SD_API int sd_hog_batch(sd_ctx* ctx, const sd_image_batch* images, const int32_t* d_image_index,
                         const float* d_x, int64_t ldx, int num_samples, int num_landmarks,
                         const sd_normalisation* eyes, const sd_hog_param* p,

@@ -200,6 +200,23 @@ def hog_transform(image: np.ndarray, params: np.ndarray, p: HogParam, right_idx,
     return out
 
 
+def hog_transform_fixed(image: np.ndarray, params: np.ndarray, p: HogParam, use_ref: bool = False) -> np.ndarray:
+    """The non-adaptive HogTransform of examples/landmark_detection.cpp:195-261 on one 8UC1 image (no bias column)."""
+    image = np.ascontiguousarray(image, dtype=np.uint8)
+    h, w = image.shape
+    params = np.ascontiguousarray(params, dtype=np.float32).ravel()
+    L = params.size // 2
+    n = C.c_int(0)
+    rc = lib().orc_hog_transform_fixed(_u8p(image), w, h, w, _fp(params), L, C.byref(p), _core_ptr(use_ref), None, C.byref(n))
+    if rc:
+        raise RuntimeError(f"orc_hog_transform_fixed failed ({rc})")
+    out = np.zeros(n.value, dtype=np.float32)
+    rc = lib().orc_hog_transform_fixed(_u8p(image), w, h, w, _fp(params), L, C.byref(p), _core_ptr(use_ref), _fp(out), None)
+    if rc:
+        raise RuntimeError(f"orc_hog_transform_fixed failed ({rc})")
+    return out
+
+
 def hog_transform_batch(images: np.ndarray, params: np.ndarray, p: HogParam, right_idx, left_idx,
                         use_ref: bool = False, threads: int = 1) -> np.ndarray:
     """One image per sample: images (N, h, w) u8, params (N, 2L) -> (N, D)."""

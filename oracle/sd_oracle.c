@@ -351,6 +351,42 @@ int orc_hog_transform(const uint8_t* image, int w, int h, int stride, const floa
     return 0;
 }
 
+/* examples/landmark_detection.cpp:195-261 -- the non-adaptive HogTransform of the hello-world example:
+ * patch half-size = num_cells * (cell_size / 2) (:213), zero padding outside the frame (:222-234), NO resize, vl_hog on
+ * the patch itself (:238-246), per-dimension transpose (:247-256), NO bias column.  The HOG grid is whatever vl_hog
+ * derives from the patch: (P + cell_size/2) / cell_size cells per side (hog.c:548-549). out_row: L * hw*hw*dd floats;
+ * *out_len (may be NULL) receives that length. */
+int orc_hog_transform_fixed(const uint8_t* image, int w, int h, int stride, const float* params, int L,
+                            const orc_hog_param* p, orc_hog_core_fn hog_core, float* out_row, int* out_len)
+{
+    if (!hog_core) hog_core = orc_hog_core;
+    const int half = p->num_cells * (p->cell_size / 2);
+    const int P = 2 * half;
+    if (P <= 3) return 1;
+    const int hw = (P + p->cell_size / 2) / p->cell_size;
+    const int dd = orc_hog_dimension(p->variant, p->num_bins);
+    const int per_lm = hw * hw * dd;
+    if (out_len) *out_len = L * per_lm;
+    if (!out_row) return 0;
+    uint8_t* patch = (uint8_t*)malloc((size_t)P * P);
+    float* fimg = (float*)malloc(sizeof(float) * P * P);
+    float* planar = (float*)malloc(sizeof(float) * per_lm);
+    for (int i = 0; i < L; ++i) {
+        int cx = orc_cv_round(params[i]);
+        int cy = orc_cv_round(params[i + L]);
+        orc_crop_patch_u8(image, w, h, stride, cx, cy, half, patch);
+        for (int k = 0; k < P * P; ++k) fimg[k] = (float)patch[k];
+        hog_core(fimg, P, P, p->cell_size, p->num_bins, p->variant, planar);
+        float* o = out_row + (size_t)i * per_lm;
+        for (int j = 0; j < dd; ++j)
+            for (int yy = 0; yy < hw; ++yy)
+                for (int xx = 0; xx < hw; ++xx)
+                    o[j * hw * hw + xx * hw + yy] = planar[j * hw * hw + yy * hw + xx];
+    }
+    free(patch); free(fimg); free(planar);
+    return 0;
+}
+
 int orc_hog_transform_batch(const uint8_t* images, int count, int w, int h, int stride,
                             const float* params, int L, const orc_hog_param* p,
                             const int32_t* ridx, int nr, const int32_t* lidx, int nl,

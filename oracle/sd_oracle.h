@@ -149,6 +149,9 @@ int orc_detect_batch(const orc_model* m, const uint8_t* images, int count, int w
                      const int32_t* boxes /* count x 4 */, orc_hog_core_fn hog_core, int threads,
                      float* landmarks /* count x 2L */);
 /* batched HogTransform over many samples (one image per sample), `threads` OpenMP threads */
+/* examples/landmark_detection.cpp:195-261: fixed patch (half = num_cells * (cell_size / 2)), no resize, no bias */
+int orc_hog_transform_fixed(const uint8_t* image, int w, int h, int stride, const float* params, int L,
+                            const orc_hog_param* p, orc_hog_core_fn hog_core, float* out_row, int* out_len);
 int orc_hog_transform_batch(const uint8_t* images, int count, int w, int h, int stride,
                             const float* params, int num_landmarks, const orc_hog_param* p,
                             const int32_t* right_idx, int n_right, const int32_t* left_idx, int n_left,

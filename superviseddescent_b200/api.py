@@ -214,6 +214,54 @@ class InterEyeDistanceNormalisation:
 # ------------------------------------------------------------------------------------------------
 # rcr::HogTransform (adaptive_vlhog.hpp:70-195), batched
 # ------------------------------------------------------------------------------------------------
+class FixedHogTransform:
+    """The non-adaptive projection functor of the reference's hello-world (examples/landmark_detection.cpp:127-272):
+    HogTransform(images, vlhog_variant, num_cells, cell_size, num_bins) -- a fixed patch of half-size
+    num_cells * (cell_size / 2) around every landmark, no resize, no bias column.  Batched like HogTransform."""
+
+    def __init__(self, images, vlhog_variant: int, num_cells: int, cell_size: int, num_bins: int, ctx: Optional["Context"] = None):
+        self.ctx = ctx or default_context()
+        imgs = images if isinstance(images, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(images))
+        if imgs.dim() == 2:
+            imgs = imgs.unsqueeze(0)
+        if imgs.dtype == torch.uint8 and imgs.dim() == 4 and imgs.shape[3] == 3:
+            imgs = bgr2gray(imgs, self.ctx)                      # :201-206
+        if imgs.dtype != torch.uint8 or imgs.dim() != 3:
+            raise ValueError("images must be (count, H, W) uint8 or (count, H, W, 3) uint8")
+        self.images = imgs.to(f"cuda:{self.ctx.device}").contiguous()
+        self.param = HoGParam(int(vlhog_variant), num_cells, cell_size, num_bins, 0.0)
+
+    def feature_length(self, num_landmarks: int) -> int:
+        return _capi.lib().sd_hog_feature_length(num_landmarks, C.byref(self.param)) - 1     # no bias column
+
+    def __call__(self, parameters, regressor_level: int = 0, training_index=None) -> torch.Tensor:
+        ctx = self.ctx
+        x = _dev(parameters, ctx)
+        single = x.dim() == 1
+        if single:
+            x = x.unsqueeze(0)
+        n, L = x.shape[0], x.shape[1] // 2
+        idx = None
+        if training_index is not None:
+            idx = torch.as_tensor(np.atleast_1d(np.asarray(training_index)), dtype=torch.int32).to(x.device)
+        D = self.feature_length(L) + 1
+        out = torch.empty((n, D), dtype=torch.float32, device=x.device)
+        self.into(x, out, idx)
+        feats = out[:, :D - 1]
+        return feats[0] if single else feats
+
+    def into(self, parameters: torch.Tensor, out: torch.Tensor, image_index: Optional[torch.Tensor] = None):
+        """Writes the feature rows into out[:, :D]; column D receives the kernel's bias 1 (not part of this functor's
+        output: callers overwrite or ignore it)."""
+        ctx = self.ctx
+        n, L = parameters.shape[0], parameters.shape[1] // 2
+        h, w = self.images.shape[1], self.images.shape[2]
+        ib = ImageBatchC(C.c_void_p(self.images.data_ptr()), w, h, self.images.stride(1), self.images.stride(0), self.images.shape[0])
+        _check(ctx.h, _capi.lib().sd_hog_batch(ctx.h, C.byref(ib), ptr(image_index) if image_index is not None else C.c_void_p(0),
+                                               ptr(parameters), C.c_int64(parameters.stride(0)), n, L, None, C.byref(self.param),
+                                               ptr(out), C.c_int64(out.stride(0))))
+
+
 def bgr2gray(images, ctx: Optional["Context"] = None) -> torch.Tensor:
     """cv::cvtColor(BGR2GRAY) on the device (adaptive_vlhog.hpp:114-120): (count, H, W, 3) uint8 -> (count, H, W) uint8.
     Host arrays are uploaded first; the result stays in HBM."""
@@ -346,6 +394,12 @@ class SupervisedDescentOptimiser:
             ld = (D + extra + 3) // 4 * 4
             buf = torch.empty((n, ld), dtype=torch.float32, device=x.device)
             h.into(x, level, buf)
+            return buf, D
+        if isinstance(h, FixedHogTransform):
+            D = h.feature_length(x.shape[1] // 2)
+            ld = (D + max(extra, 1) + 3) // 4 * 4                 # the kernel's bias lands in the first spare column
+            buf = torch.empty((n, ld), dtype=torch.float32, device=x.device)
+            h.into(x, buf)
             return buf, D
         xs = x.cpu().numpy()
         rows = [np.atleast_1d(np.asarray(h(xs[i].copy(), level, i), dtype=np.float32)).ravel() for i in range(n)]

@@ -51,10 +51,14 @@ struct HogArgs {
 // ---- per-sample geometry: IED -> half patch size (adaptive_vlhog.hpp:123), once per sample instead of
 //      once per thread of every patch ---------------------------------------------------------------
 __global__ void hog_geometry_kernel(const float* __restrict__ x, long long ldx, int N, int L, const sd_eyes_dev eyes, float rel,
-                                    int* __restrict__ half_out, int* __restrict__ status)
+                                    int fixed_half, int* __restrict__ half_out, int* __restrict__ status)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
+    if (fixed_half > 0) {    // non-adaptive HogTransform of examples/landmark_detection.cpp:213
+        half_out[i] = fixed_half;
+        return;
+    }
     const double ied = sd_device_ied(x + (long long)i * ldx, L, eyes);
     int half = (int)round(__dmul_rn(__dmul_rn((double)rel, ied), 0.5));   // std::round(float rel * double ied / 2)
     if (half < 1) {          // cv::resize would throw on the empty ROI; flag it and keep going
@@ -613,11 +617,23 @@ int launch_hog(sd_ctx* ctx, const sd_image_batch* images, const int32_t* d_image
     SD_REQUIRE(ctx, (fs + p->cell_size / 2) / p->cell_size == p->num_cells, "hogWidth != num_cells");
     SD_REQUIRE(ctx, ldx >= 2 * L, "ldx < 2L");
     if (N == 0) return SD_OK;
-    if (!eyes || eyes->kind != 1) return sd_fail(ctx, SD_ERR_INVALID, "HogTransform needs the eye landmark indices (adaptive patch size)");
+    // eyes == NULL (or kind 0): the fixed-patch HogTransform of the hello-world example (examples/landmark_detection.cpp:
+    // 195-261): half = num_cells * (cell_size / 2), no resize.  The kernel's resize stage is the identity when the patch is
+    // already num_cells * cell_size wide, which holds for even cell sizes; an odd cell size would change the HOG grid of
+    // the un-resized patch and is rejected.
+    const bool fixed = !eyes || eyes->kind == 0;
+    int fixed_half = 0;
+    if (fixed) {
+        fixed_half = p->num_cells * (p->cell_size / 2);
+        SD_REQUIRE(ctx, 2 * fixed_half == fs, "the fixed-patch HogTransform needs an even cell_size (patch == num_cells * cell_size)");
+    } else if (eyes->kind != 1) {
+        return sd_fail(ctx, SD_ERR_INVALID, "unknown normalisation kind");
+    }
 
     HogArgs a;
     sd_eyes_dev eyes_dev;
-    int rc = sd_eyes_to_dev(ctx, eyes, L, &eyes_dev);
+    memset(&eyes_dev, 0, sizeof(eyes_dev));
+    int rc = fixed ? SD_OK : sd_eyes_to_dev(ctx, eyes, L, &eyes_dev);
     if (rc) return rc;
     a.images = images->d_data;
     a.width = images->width; a.height = images->height; a.row_stride = images->row_stride;
@@ -654,7 +670,7 @@ int launch_hog(sd_ctx* ctx, const sd_image_batch* images, const int32_t* d_image
 
     int* d_half = (int*)sd_workspace(ctx, SD_WS_GEOM, (size_t)N * sizeof(int));
     if (!d_half) return SD_ERR_CUDA;
-    hog_geometry_kernel<<<sd_div_up(N, 128), 128, 0, ctx->stream>>>(d_x, ldx, N, L, eyes_dev, p->relative_patch_size, d_half, a.status);
+    hog_geometry_kernel<<<sd_div_up(N, 128), 128, 0, ctx->stream>>>(d_x, ldx, N, L, eyes_dev, p->relative_patch_size, fixed_half, d_half, a.status);
     SD_LAUNCH_CHECK(ctx, "hog_geometry_kernel");
     a.half = d_half;
 

@@ -112,3 +112,29 @@ def test_bgr2gray_device_is_bit_exact(sd, oracle, golden):
     fa = sd.HogTransform(bgr, hp, m.landmark_ids, m.right_ids, m.left_ids)(x0, 0).cpu().numpy()
     fb = sd.HogTransform(gray, hp, m.landmark_ids, m.right_ids, m.left_ids)(x0, 0).cpu().numpy()
     assert np.array_equal(fa, fb)
+
+
+@pytest.mark.parametrize("variant,nc,cs,K", [(1, 3, 12, 4), (0, 3, 12, 4), (1, 5, 10, 9), (1, 4, 6, 4)])
+def test_fixed_patch_hog_transform_vs_oracle(sd, oracle, variant, nc, cs, K):
+    """The non-adaptive HogTransform of the reference's hello-world (examples/landmark_detection.cpp:195-261): fixed patch
+    of half-size num_cells * (cell_size / 2), zero padding at the border, no resize, no bias.  Landmarks include points
+    at and beyond the frame border.  An odd cell size is rejected (the un-resized patch would get a different HOG grid)."""
+    import synth
+    rng = np.random.default_rng(nc * 100 + cs)
+    imgs = synth.smooth_images(3, 120, 160, seed=11)
+    L = 7
+    x = np.concatenate([rng.uniform(-5, 165, size=(3, L)), rng.uniform(-5, 125, size=(3, L))], axis=1).astype(np.float32)
+    x[0, 0], x[0, L] = 0.0, 0.0                                   # patch centred on the corner pixel
+    x[1, 1], x[1, L + 1] = 159.5, 119.5                           # cvRound half-to-even at the far corner
+    h = sd.FixedHogTransform(imgs, variant, nc, cs, K)
+    got = h(x, 0).cpu().numpy()
+    hp = oracle.HogParam(variant, nc, cs, K, 0.0)
+    want = np.stack([oracle.hog_transform_fixed(imgs[i], x[i], hp) for i in range(3)])
+    assert got.shape == want.shape
+    err = rel_err(got, want)
+    print(f"fixed-patch HOG variant {variant} nc {nc} cs {cs} K {K}: rel err {err:.2e}")
+    assert err <= 1e-5
+    one = h(x[2], 0, 2).cpu().numpy()                             # predict()'s call shape: one row + image index
+    assert np.array_equal(one, got[2])
+    with pytest.raises(Exception):
+        sd.FixedHogTransform(imgs, variant, nc, 11, K)(x, 0)

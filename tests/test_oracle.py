@@ -250,3 +250,26 @@ def test_pose_estimation_example_config2(oracle):
     pred = oracle.cascade_apply(P.TEST_INIT, P.TEST_LANDMARKS, w, P.projection, None)[0]
     print("oracle pose residuals", residuals, "predicted pitch/yaw/roll", pred[:3])
     assert np.all(np.abs(pred[:3] - np.array([11.0, -25.0, -10.0])) < 6.0)      # example's ground truth (:334)
+
+
+def test_fixed_patch_transform_equals_adaptive_one_at_matching_size(oracle):
+    """examples/landmark_detection.cpp:195-261 (fixed patch, no resize, no bias) against adaptive_vlhog.hpp:109-185: when
+    the inter-eye distance makes the adaptive patch exactly num_cells * cell_size wide, cv::resize is the identity and the
+    two functors must agree value for value (the adaptive one appends its bias)."""
+    import synth
+    img = synth.smooth_images(1, 120, 160, seed=3)[0]
+    nc, cs, K = 3, 12, 4
+    L = 6
+    rng = np.random.default_rng(2)
+    x = np.concatenate([rng.uniform(10, 150, L), rng.uniform(10, 110, L)]).astype(np.float32)
+    x[0], x[L] = 40.0, 60.0                       # right eye
+    x[1], x[L + 1] = 40.0 + nc * cs, 60.0         # left eye: IED = 36 -> half = round(1.0 * 36 / 2) = 18 = nc * (cs / 2)
+    x[2], x[L + 2] = 2.0, 118.0                   # near a corner: zero padding on two sides
+    for variant in (0, 1):
+        hp = oracle.HogParam(variant, nc, cs, K, 1.0)
+        adaptive = oracle.hog_transform(img, x, hp, [0], [1])
+        fixed = oracle.hog_transform_fixed(img, x, hp)
+        assert fixed.size == adaptive.size - 1 and adaptive[-1] == 1.0
+        assert np.array_equal(fixed, adaptive[:-1])
+        if oracle.ref_available():
+            assert np.array_equal(oracle.hog_transform_fixed(img, x, hp, use_ref=True), fixed)
