@@ -224,6 +224,15 @@ SD_API const char* sd_model_landmark_id(const sd_model* m, int i);
 SD_API int sd_align_mean(const float* h_mean, int num_landmarks, int box_x, int box_y, int box_w, int box_h,
                          float scaling_x, float scaling_y, float translation_x, float translation_y,
                          float* h_out);
+/* Training front end of apps/rcr/rcr-train.cpp.
+ * perturb (:130-146): translate a face box by fractions of its size and scale it about its centre (float arithmetic,
+ * truncation toward zero like cv::Rect(int)); host-side, a few flops. */
+SD_API int sd_perturb_box(int box_x, int box_y, int box_w, int box_h, float translation_x, float translation_y,
+                          float scaling, int32_t out_box[4]);
+/* calculate_normalised_landmark_errors (:149-212): d_err[r, i] = || pred[r, i] - gt[r, i] ||_2 / IED(pred[r]) for N rows of
+ * 2L landmarks each ([x.., y..]); d_err: N x L, row pitch lde. */
+SD_API int sd_normalised_landmark_errors(sd_ctx* ctx, const float* d_pred, int64_t ldp, const float* d_gt, int64_t ldgt,
+                                         int N, int num_landmarks, const sd_normalisation* eyes, float* d_err, int64_t lde);
 /* detection_model::detect(image, initialisation) batched, everything on the device
  * (model.hpp:147-157 -> superviseddescent.hpp:323-344).  d_x0: B x 2L initial landmarks. */
 SD_API int sd_detect_batch_device(sd_ctx* ctx, const sd_model* m, const sd_image_batch* images,

@@ -150,6 +150,26 @@ def bgr2gray_u8(bgr: np.ndarray) -> np.ndarray:
     return g
 
 
+def perturb_box(box, tx: float, ty: float, scaling: float = 1.0):
+    """apps/rcr/rcr-train.cpp:130-146."""
+    b = (C.c_int32 * 4)(*[int(v) for v in box])
+    o = (C.c_int32 * 4)()
+    lib().orc_perturb_box(b, C.c_float(tx), C.c_float(ty), C.c_float(scaling), o)
+    return tuple(int(v) for v in o)
+
+
+def normalised_landmark_errors(pred: np.ndarray, gt: np.ndarray, right_idx, left_idx) -> np.ndarray:
+    """apps/rcr/rcr-train.cpp:200-212: (N, L) IED-normalised per-landmark errors."""
+    pred = np.ascontiguousarray(pred, dtype=np.float32)
+    gt = np.ascontiguousarray(gt, dtype=np.float32)
+    n, p2 = pred.shape
+    r = np.asarray(right_idx, dtype=np.int32)
+    l = np.asarray(left_idx, dtype=np.int32)
+    out = np.zeros((n, p2 // 2), dtype=np.float32)
+    lib().orc_normalised_landmark_errors(_fp(pred), _fp(gt), n, p2 // 2, _ip(r), r.size, _ip(l), l.size, _fp(out))
+    return out
+
+
 def cv_round(v: float) -> int:
     return lib().orc_cv_round(C.c_float(v))
 

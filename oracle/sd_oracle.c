@@ -406,6 +406,40 @@ int orc_hog_transform_batch(const uint8_t* images, int count, int w, int h, int 
     return rc;
 }
 
+/* apps/rcr/rcr-train.cpp:130-146: perturb a face box by a translation (fractions of its size) and a scaling about
+ * its centre.  All arithmetic in float; cv::Rect(int) truncates the float expressions toward zero. */
+void orc_perturb_box(const int32_t box[4], float tx, float ty, float scaling, int32_t out[4])
+{
+    const float tx_pixel = tx * (float)box[2];
+    const float ty_pixel = ty * (float)box[3];
+    const float pw = (float)box[2] * scaling;
+    const float ph = (float)box[3] * scaling;
+    out[0] = (int32_t)((float)box[0] + ((float)box[2] - pw) / 2.0f + tx_pixel);
+    out[1] = (int32_t)((float)box[1] + ((float)box[3] - ph) / 2.0f + ty_pixel);
+    out[2] = (int32_t)pw;
+    out[3] = (int32_t)ph;
+}
+
+/* apps/rcr/rcr-train.cpp:149-212: per-landmark L2 error of every row, normalised by the inter-eye distance of the
+ * PREDICTION.  cv::norm(Vec2f, Vec2f): float differences, squares summed in double, sqrt in double, stored as float
+ * (:169); .mul(1.0f / ied): the double quotient becomes a float factor, the product is a float multiply
+ * (OpenCV arithm on CV_32F with a scalar operand -- "parity unpinned": OpenCV C++ cannot run here). */
+void orc_normalised_landmark_errors(const float* pred, const float* gt, int N, int L, const int32_t* ridx, int nr,
+                                    const int32_t* lidx, int nl, float* out)
+{
+    for (int r = 0; r < N; ++r) {
+        const float* p = pred + (size_t)r * 2 * L;
+        const float* g = gt + (size_t)r * 2 * L;
+        const double ied = orc_get_ied(p, L, ridx, nr, lidx, nl);
+        const float f = (float)((double)1.0f / ied);
+        for (int i = 0; i < L; ++i) {
+            const float dx = p[i] - g[i], dy = p[i + L] - g[i + L];
+            const float n = (float)sqrt((double)dx * (double)dx + (double)dy * (double)dy);
+            out[(size_t)r * L + i] = n * f;
+        }
+    }
+}
+
 /* model.hpp:64-76 */
 void orc_align_mean(const float* mean, int L, int bx, int by, int bw, int bh,
                     float sx, float sy, float tx, float ty, float* out)

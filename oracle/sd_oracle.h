@@ -75,6 +75,10 @@ int orc_feature_length(int num_landmarks, const orc_hog_param* p);      /* D = L
 int orc_hog_transform(const uint8_t* image, int w, int h, int stride, const float* params,
                       int num_landmarks, const orc_hog_param* p, const int32_t* right_idx, int n_right,
                       const int32_t* left_idx, int n_left, orc_hog_core_fn hog_core, float* out_row);
+/* apps/rcr/rcr-train.cpp:130-146 and :149-212 (training front-end helpers) */
+void orc_perturb_box(const int32_t box[4], float tx, float ty, float scaling, int32_t out[4]);
+void orc_normalised_landmark_errors(const float* pred, const float* gt, int N, int L, const int32_t* ridx, int nr,
+                                    const int32_t* lidx, int nl, float* out);
 /* debug/parity taps: geometry (cx, cy, half) per landmark and the resized u8 patch of one landmark */
 void orc_patch_geometry(const float* params, int num_landmarks, const orc_hog_param* p,
                         const int32_t* right_idx, int n_right, const int32_t* left_idx, int n_left,

@@ -48,6 +48,7 @@ EXPORTS = [
     "sd_model_load", "sd_model_save", "sd_model_create", "sd_model_destroy", "sd_model_num_levels",
     "sd_model_num_landmarks", "sd_model_hog_param", "sd_model_regulariser", "sd_model_normalisation",
     "sd_model_get_mean", "sd_model_get_weights", "sd_model_landmark_id", "sd_align_mean",
+    "sd_perturb_box", "sd_normalised_landmark_errors",
     "sd_detect_batch_device", "sd_detect_batch_host",
 ]
 

@@ -486,6 +486,31 @@ def align_mean(mean, facebox, scaling_x=1.0, scaling_y=1.0, translation_x=0.0, t
     return out
 
 
+def perturb(facebox, translation_x: float, translation_y: float, scaling: float = 1.0):
+    """perturb() of apps/rcr/rcr-train.cpp:130-146: (x, y, w, h) -> perturbed (x, y, w, h)."""
+    out = (C.c_int32 * 4)()
+    rc = _capi.lib().sd_perturb_box(int(facebox[0]), int(facebox[1]), int(facebox[2]), int(facebox[3]), C.c_float(translation_x),
+                                    C.c_float(translation_y), C.c_float(scaling), out)
+    if rc != 0:
+        raise SdError(rc, "sd_perturb_box")
+    return tuple(int(v) for v in out)
+
+
+def calculate_normalised_landmark_errors(predictions, groundtruth, model_landmarks: Sequence[str], right_eye_identifiers: Sequence[str],
+                                         left_eye_identifiers: Sequence[str], ctx: Optional[Context] = None) -> torch.Tensor:
+    """calculate_normalised_landmark_errors() of apps/rcr/rcr-train.cpp:200-212: (N, L) per-landmark L2 errors divided by
+    the inter-eye distance of the prediction; the mean over everything is the figure rcr-train prints (:520-524)."""
+    ctx = ctx or default_context()
+    p = _dev(predictions, ctx)
+    g = _dev(groundtruth, ctx)
+    n, L = p.shape[0], p.shape[1] // 2
+    eyes = InterEyeDistanceNormalisation(model_landmarks, right_eye_identifiers, left_eye_identifiers).c(L)
+    out = torch.empty((n, L), dtype=torch.float32, device=p.device)
+    _check(ctx.h, _capi.lib().sd_normalised_landmark_errors(ctx.h, ptr(p), C.c_int64(p.stride(0)), ptr(g), C.c_int64(g.stride(0)), n, L,
+                                                            C.byref(eyes), ptr(out), C.c_int64(out.stride(0))))
+    return out
+
+
 class detection_model:
     """rcr::detection_model (model.hpp:122-183) resident on the GPU."""
 

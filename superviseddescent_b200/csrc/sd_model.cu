@@ -234,6 +234,26 @@ sd_roi face_roi(const sd_model* m, const float* x0, int width, int height, int r
 
 }  // namespace
 
+namespace {
+// apps/rcr/rcr-train.cpp:149-212: one warp per row; cv::norm's float differences / double sum / double sqrt, the result
+// stored as float (:169) and multiplied by the float factor (float)(1.0f / IED(prediction)).
+__global__ void landmark_error_kernel(const float* __restrict__ pred, long long ldp, const float* __restrict__ gt, long long ldgt, int N,
+                                      int L, const sd_eyes_dev eyes, float* __restrict__ err, long long lde)
+{
+    const int r = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (r >= N) return;
+    const float* p = pred + (long long)r * ldp;
+    const float* g = gt + (long long)r * ldgt;
+    const double ied = sd_device_ied(p, L, eyes);
+    const float f = (float)(1.0 / ied);
+    for (int i = lane; i < L; i += 32) {
+        const float dx = __fsub_rn(p[i], g[i]), dy = __fsub_rn(p[i + L], g[i + L]);
+        const float n = (float)sqrt(__dadd_rn(__dmul_rn((double)dx, (double)dx), __dmul_rn((double)dy, (double)dy)));
+        err[(long long)r * lde + i] = __fmul_rn(n, f);
+    }
+}
+}  // namespace
+
 extern "C" {
 
 int sd_align_mean(const float* h_mean, int L, int box_x, int box_y, int box_w, int box_h, float sx, float sy,
@@ -252,6 +272,38 @@ int sd_align_mean(const float* h_mean, int L, int box_x, int box_y, int box_w, i
         volatile float py = h_mean[i + L] * ay;
         h_out[i + L] = py + by;
     }
+    return SD_OK;
+}
+
+int sd_perturb_box(int box_x, int box_y, int box_w, int box_h, float tx, float ty, float scaling, int32_t out_box[4])
+{
+    if (!out_box) return SD_ERR_INVALID;
+    // rcr-train.cpp:133-143, float arithmetic; volatile keeps every product / sum a separately rounded float
+    volatile float tx_pixel = tx * (float)box_w;
+    volatile float ty_pixel = ty * (float)box_h;
+    volatile float pw = (float)box_w * scaling;
+    volatile float ph = (float)box_h * scaling;
+    volatile float hx = ((float)box_w - pw) / 2.0f, hy = ((float)box_h - ph) / 2.0f;
+    volatile float x = (float)box_x + hx, y = (float)box_y + hy;
+    out_box[0] = (int32_t)(x + tx_pixel);
+    out_box[1] = (int32_t)(y + ty_pixel);
+    out_box[2] = (int32_t)pw;
+    out_box[3] = (int32_t)ph;
+    return SD_OK;
+}
+
+int sd_normalised_landmark_errors(sd_ctx* ctx, const float* d_pred, int64_t ldp, const float* d_gt, int64_t ldgt, int N, int L,
+                                  const sd_normalisation* eyes, float* d_err, int64_t lde)
+{
+    if (!ctx) return SD_ERR_INVALID;
+    SD_REQUIRE(ctx, d_pred && d_gt && d_err && N >= 0 && L >= 1 && ldp >= 2 * L && ldgt >= 2 * L && lde >= L, "bad argument");
+    SD_REQUIRE(ctx, eyes && eyes->kind == 1, "the normalised error needs the eye landmark indices");
+    if (N == 0) return SD_OK;
+    sd_eyes_dev eyes_dev;
+    int rc = sd_eyes_to_dev(ctx, eyes, L, &eyes_dev);
+    if (rc) return rc;
+    landmark_error_kernel<<<sd_div_up(N, 4), 128, 0, ctx->stream>>>(d_pred, ldp, d_gt, ldgt, N, L, eyes_dev, d_err, lde);
+    SD_LAUNCH_CHECK(ctx, "landmark_error_kernel");
     return SD_OK;
 }
 

@@ -1,6 +1,8 @@
 """GPU parity of the RCR training path (HogTransform projection -> targets -> tensor-core Gram -> Cholesky
 solve -> update), level by level from identical inputs, against a float64 restatement of
 regressors.hpp:199-234 / superviseddescent.hpp:165-219 fed with the oracle's features."""
+import os
+
 import numpy as np
 import pytest
 
@@ -61,3 +63,20 @@ def test_training_levels_teacher_forced(sd, oracle, golden, mode):
             cur = nxt_ref
     finally:
         ctx.set_gram_mode(0)
+
+
+def test_rcr_train_front_end_helpers(sd, oracle):
+    """perturb() and calculate_normalised_landmark_errors() of apps/rcr/rcr-train.cpp (:130-146, :149-212) against the
+    oracle: the box arithmetic is integer-exact, the errors float-exact."""
+    rng = np.random.default_rng(9)
+    for _ in range(200):
+        box = (int(rng.integers(-20, 400)), int(rng.integers(-20, 300)), int(rng.integers(20, 300)), int(rng.integers(20, 300)))
+        tx, ty, s = float(rng.normal(0, 0.04)), float(rng.normal(0, 0.04)), float(rng.normal(1, 0.04))
+        assert sd.perturb(box, tx, ty, s) == oracle.perturb_box(box, tx, ty, s), (box, tx, ty, s)
+    m = oracle.Model(os.path.join(os.path.dirname(__file__), "golden", "face_landmarks_model_rcr_22.bin"))
+    L = len(m.landmark_ids)
+    gt = rng.uniform(40, 400, size=(257, 2 * L)).astype(np.float32)
+    pred = (gt + rng.normal(0, 4, size=gt.shape)).astype(np.float32)
+    got = sd.calculate_normalised_landmark_errors(pred, gt, m.landmark_ids, m.right_ids, m.left_ids).cpu().numpy()
+    want = oracle.normalised_landmark_errors(pred, gt, m.right_idx, m.left_idx)
+    assert np.array_equal(got, want)

@@ -273,3 +273,29 @@ def test_fixed_patch_transform_equals_adaptive_one_at_matching_size(oracle):
         assert np.array_equal(fixed, adaptive[:-1])
         if oracle.ref_available():
             assert np.array_equal(oracle.hog_transform_fixed(img, x, hp, use_ref=True), fixed)
+
+
+def test_perturb_box_rcr_train_semantics(oracle):
+    """perturb() of apps/rcr/rcr-train.cpp:130-146: float arithmetic, truncation toward zero in cv::Rect(int)."""
+    assert oracle.perturb_box((100, 50, 200, 100), 0.0, 0.0, 1.0) == (100, 50, 200, 100)
+    assert oracle.perturb_box((100, 50, 200, 100), 0.1, -0.1, 1.0) == (120, 40, 200, 100)
+    # scaling keeps the centre: width 200 -> 220, x moves by -10; 0.95 -> 190 wide, x + 5
+    assert oracle.perturb_box((100, 50, 200, 100), 0.0, 0.0, 1.1) == (90, 45, 220, 110)
+    assert oracle.perturb_box((100, 50, 200, 100), 0.0, 0.0, 0.95) == (105, 52, 190, 95)
+    # truncation toward zero (not floor) for negative coordinates: -0.5 -> 0
+    assert oracle.perturb_box((0, 0, 10, 10), -0.05, -0.05, 1.0) == (0, 0, 10, 10)
+    assert oracle.perturb_box((0, 0, 10, 10), -0.15, -0.25, 1.0) == (-1, -2, 10, 10)
+
+
+def test_normalised_landmark_errors_match_a_float64_restatement(oracle):
+    rng = np.random.default_rng(4)
+    L = 22
+    gt = rng.uniform(50, 300, size=(9, 2 * L)).astype(np.float32)
+    pred = (gt + rng.normal(0, 3, size=gt.shape)).astype(np.float32)
+    r, l = [4, 7], [10, 13]
+    got = oracle.normalised_landmark_errors(pred, gt, r, l)
+    re = np.stack([pred[:, r].mean(1), pred[:, [i + L for i in r]].mean(1)], 1).astype(np.float64)
+    le = np.stack([pred[:, l].mean(1), pred[:, [i + L for i in l]].mean(1)], 1).astype(np.float64)
+    ied = np.linalg.norm(re - le, axis=1)
+    d = np.hypot(pred[:, :L].astype(np.float64) - gt[:, :L], pred[:, L:].astype(np.float64) - gt[:, L:])
+    assert np.allclose(got, d / ied[:, None], rtol=1e-6, atol=0)
