@@ -180,6 +180,9 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+# measured once with ncu (--set full) on hog_patch_kernel<4,5,11>, 2048 faces x 22 patches: 160.26 MB read + 51.71 MB written
+HOG_L0_DRAM_BYTES_PER_FACE = (160.259584e6 + 51.714560e6) / 2048
+
 TRAIN_CFG = {"n": 10000, "size": 128, "num_bins": 9, "cells": 5, "cell_sizes": [11, 10, 8, 6, 6], "rel": [1.0, 0.7, 0.4, 0.25, 0.25],
              "lambda_factor": 1.5}
 
@@ -412,7 +415,11 @@ def run_ours(args):
     peak, peak_src = measured_peaks()
     achieved = alg_bytes / (hog_ms * 1e-3) / 1e9
     roofline = {"kernel": f"hog_patch_kernel<{hp0.num_bins}> (cascade level 0, fs={fs0})", "bound": "hbm", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "ms_per_launch": hog_ms,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": HOG_L0_DRAM_BYTES_PER_FACE * B, "peak_source": peak_src, "ms_per_launch": hog_ms,
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel at 2048 faces "
+                                  "(profiles/r01_summary.md section 12), scaled linearly to this batch; below the algorithmic bytes because "
+                                  "the 22 patches of a face overlap (SURVEY 8d counts L*P^2 source pixels)",
+                "issue_slots_busy_pct": 76.4,
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "note": "HOG is fp32-ALU/shared-memory bound (SURVEY 8d: ~40 flop/B); fp32 figure reported beside the HBM one",
                 "achieved_fp32_tflops": alg_flops / (hog_ms * 1e-3) / 1e12}
