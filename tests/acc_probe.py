@@ -1,4 +1,5 @@
-"""Accuracy probe: weights of a few systems vs float64 truth, per gram mode (not part of the product)."""
+"""Accuracy probe (test infrastructure: it uses the CPU oracle): weights of a few systems vs float64 truth, per gram mode.
+   python tests/acc_probe.py   on a GPU box"""
 import sys, os, numpy as np
 sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests")
 from oracle import oracle as O
