@@ -26,13 +26,14 @@ def test_header_symbols_are_exported(built_lib):
 
 
 def test_no_oracle_in_product():
-    """The product package must not import, link or reference anything under oracle/."""
-    pkg = os.path.join(ROOT, "superviseddescent_b200")
-    for dirpath, _, files in os.walk(pkg):
-        for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h", ".cpp")):
-                text = open(os.path.join(dirpath, f), errors="ignore").read()
-                assert "sd_oracle" not in text and "from oracle" not in text and "import oracle" not in text, os.path.join(dirpath, f)
+    """The product package, the public header and the development helpers must not import, link or reference anything
+    under oracle/ (only tests/, smoke() and bench.py's CPU baseline may)."""
+    for top in ("superviseddescent_b200", "include", "tools"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, top)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h", ".cpp", ".sh")):
+                    text = open(os.path.join(dirpath, f), errors="ignore").read()
+                    assert "sd_oracle" not in text and "from oracle" not in text and "import oracle" not in text, os.path.join(dirpath, f)
 
 
 def test_fails_loudly_without_gpu(built_lib):
