@@ -442,7 +442,9 @@ def run_ours(args):
                    "parallelism": f"face-batch sharded over {world} GPU(s), no collective",
                    "l2": f"inputs ({B * W_IMG * H_IMG / 1e6:.0f} MB of frames per GPU) exceed the 126 MB L2"},
         "e2e": {"value": e2e, "unit": "faces/s", "h2d_bytes_per_step": int(B * W_IMG * H_IMG + B * 2 * L * 4), "d2h_bytes_per_step": int(B * 2 * L * 4),
-                "ms_per_step": ms_e2e / args.steps, "api": "detection_model.detect_batch (sd_detect_batch_host), pinned host frames"},
+                "ms_per_step": ms_e2e / args.steps, "api": "detection_model.detect_batch (sd_detect_batch_host), pinned host frames",
+                "note": "h2d_bytes_per_step counts the host frames handed to the call; the engine's region-of-interest route reads only "
+                        "each face's window (~1/4 of a frame) over PCIe inside the timed region (DESIGN.md 4.5)"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
