@@ -58,3 +58,20 @@ def test_align_mean_host_function(built_lib):
     exp_x = (mean[:22] * 1.0 + 0.5) * 240 + 100
     exp_y = (mean[22:] * 1.0 + 0.5) * 260 + 50
     assert np.allclose(out[:22], exp_x, rtol=0, atol=1e-3) and np.allclose(out[22:], exp_y, rtol=0, atol=1e-3)
+
+
+def test_host_side_functions_match_the_oracle(built_lib):
+    """sd_align_mean and sd_perturb_box are pure host code (no device needed): bit-exact against the oracle's restatement
+    of model.hpp:64-76 and apps/rcr/rcr-train.cpp:130-146 on random inputs."""
+    import numpy as np
+    from oracle import oracle as O
+    from superviseddescent_b200 import api
+    O.build()
+    rng = np.random.default_rng(11)
+    mean = rng.uniform(-0.5, 0.5, 44).astype(np.float32)
+    for _ in range(300):
+        box = (int(rng.integers(-50, 600)), int(rng.integers(-50, 400)), int(rng.integers(10, 400)), int(rng.integers(10, 400)))
+        sx, sy = float(rng.normal(1, 0.05)), float(rng.normal(1, 0.05))
+        tx, ty = float(rng.normal(0, 0.05)), float(rng.normal(0, 0.05))
+        assert np.array_equal(api.align_mean(mean, box, sx, sy, tx, ty), O.align_mean(mean, box, sx, sy, tx, ty))
+        assert api.perturb(box, tx, ty, sx) == O.perturb_box(box, tx, ty, sx)
