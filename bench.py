@@ -256,7 +256,8 @@ def run_train(sd, ctx, model, world, rank, dev, barrier, max_over_ranks, group):
     return {"metric": "regressor train sec (RCR, all cascade levels)", "value": secs, "unit": "s", "higher_is_better": False, "scaling": "strong",
             "config": {"workload": "configs[3]: RCR training, 10k synthetic 128x128 crops, 22 landmarks, 31-bin HOG (K=9), 5 cascade levels",
                        "samples_global": cfg["n"], "samples_this_rank": e - b, "feature_dim": D, "levels": S,
-                       "parallelism": f"samples sharded over {world} GPU(s), one all-reduce of [AtA|Atb] ({D * (D + 44) * 4 / 1e9:.2f} GB) per level, replicated solve"},
+                       "parallelism": f"samples sharded over {world} GPU(s), one all-reduce of the upper row bands of [AtA|Atb] "
+                                      f"({sum((min(b + 1024, D) - b) * (D + 44 - b) for b in range(0, D, 1024)) * 4 / 1e9:.2f} of {D * (D + 44) * 4 / 1e9:.2f} GB) per level, replicated solve"},
             "gpu_launches": int(ctx.launches() - l0),
             "algorithmic_tflop": {"gram_syrk": gram_flops / 1e12, "cholesky_and_solve": chol_flops / 1e12},
             "train_residual": {"before": res0, "after": res1},

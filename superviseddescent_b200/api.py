@@ -432,7 +432,7 @@ class SupervisedDescentOptimiser:
             G = torch.empty((D, ldg), dtype=torch.float32, device=cur.device)
             _check(ctx.h, lib.sd_gram(ctx.h, ptr(A), C.c_int64(A.stride(0)), ptr(Bv), C.c_int64(A.stride(0)), n, D, P, ptr(G), C.c_int64(ldg)))
             if distributed:
-                parallel.allreduce_gram(G, group)                            #    the one collective per level
+                parallel.allreduce_gram(G, group, D)                         #    the one collective per level (upper bands only)
             X = torch.empty((D, P), dtype=torch.float32, device=cur.device)
             lam = C.c_float(0)
             rc_ = reg.regulariser.c()

@@ -31,11 +31,34 @@ def global_count(n_local: int, group=None, device=None) -> int:
     return int(t.item())
 
 
-def allreduce_gram(G: torch.Tensor, group=None) -> torch.Tensor:
-    """The one collective per cascade level: sums the packed [A^T A | A^T b] buffer over the ranks, in place."""
+def allreduce_gram(G: torch.Tensor, group=None, D: Optional[int] = None, band: int = 1024) -> torch.Tensor:
+    """The one collective per cascade level: sums the packed [A^T A | A^T b] buffer over the ranks, in place.
+
+    Only the upper triangle of A^T A (and the right-hand-side columns) is ever read by the solve, so with `D` given the
+    buffer is sent as row bands of `band` rows, each from its first diagonal column to the end of the row: about half the
+    bytes of the full buffer (0.62 instead of 1.17 GB for config 4, 5.7 instead of 11.1 GB for config 5).  The bands are
+    staged through one contiguous buffer (two HBM-speed copies) because the collective needs contiguous memory.  Elements
+    below a band's first column keep this rank's partial sums; nothing reads them."""
     if group is None and not (dist.is_available() and dist.is_initialized()):
         return G
-    dist.all_reduce(G, op=dist.ReduceOp.SUM, group=group)
+    rows, ld = G.shape
+    if D is None or band < 1 or rows <= 2 * band:
+        dist.all_reduce(G, op=dist.ReduceOp.SUM, group=group)
+        return G
+    starts = list(range(0, rows, band))
+    sizes = [(min(b0 + band, rows) - b0) * (ld - b0) for b0 in starts]
+    flat = torch.empty(sum(sizes), dtype=G.dtype, device=G.device)
+    off = 0
+    for b0, sz in zip(starts, sizes):
+        b1 = min(b0 + band, rows)
+        flat[off:off + sz].view(b1 - b0, ld - b0).copy_(G[b0:b1, b0:])
+        off += sz
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    off = 0
+    for b0, sz in zip(starts, sizes):
+        b1 = min(b0 + band, rows)
+        G[b0:b1, b0:].copy_(flat[off:off + sz].view(b1 - b0, ld - b0))
+        off += sz
     return G
 
 

@@ -47,7 +47,12 @@ def _worker(rank, world, port, n, d, m, out):
     Al, Bl = A[b:e].astype(np.float64), B[b:e].astype(np.float64)
     G = torch.from_numpy(np.hstack([Al.T @ Al, Al.T @ Bl]).astype(np.float32))
     n_global = parallel.global_count(e - b)
-    parallel.allreduce_gram(G)
+    G_full = G.clone()
+    parallel.allreduce_gram(G_full)                          # whole buffer
+    parallel.allreduce_gram(G, None, d, band=5)              # upper row bands only (ragged last band: 24 = 4*5 + 4)
+    iu = np.triu_indices(d)
+    assert np.array_equal(G.numpy()[:, :d][iu], G_full.numpy()[:, :d][iu])       # every element the solve reads ...
+    assert np.array_equal(G.numpy()[:, d:], G_full.numpy()[:, d:])              # ... including the right-hand sides
     X = _solve(G.numpy(), d, 1.5, n_global)
     x_local = torch.from_numpy(A[b:e, :4].copy())
     gathered = parallel.gather_rows(x_local)
