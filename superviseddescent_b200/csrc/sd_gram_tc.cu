@@ -688,6 +688,303 @@ int make_map(sd_ctx* ctx, CUtensorMap* map, const float* base, int64_t ld, int r
     return SD_OK;
 }
 
+#ifdef SD_EXPERIMENTAL_2CTA
+// =====================================================================================================
+// DRAFT, NOT BUILT INTO THE PRODUCT AND NOT YET RUN ON HARDWARE (tools/build_experimental.sh only compiles it):
+// variant 3 = the in-kernel-split SYRK as a CTA PAIR (cta_group::2), the next step named in DESIGN.md section 8.
+//
+// Why: variant 2 moves 144 KB per 16-sample stage through one SM's shared memory (1125 clk at 128 B/clk) while its six
+// MMAs need ~800 clk.  In a CTA pair the 256 x 256 output tile is split by rows (each CTA keeps 128 x 256 of it in its
+// own TMEM, exactly as today) and the 256-column operand is split by columns: every CTA stages its own 128-column "A"
+// operand and ONE HALF of the "B" operand, the tensor cores of the pair read both halves.  Per SM and stage:
+// 16 KB TMA write + 16 KB transform read + 16 KB lo write + 6 x 8 KB operand fetch = 96 KB = 750 clk < 800 clk of MMA.
+//
+// Barrier topology (same shared-memory offsets in both CTAs; rank 0 = leader, the only MMA issuer):
+//   raw_full[s]   local   TMA bytes of this CTA's 16 KB landed                        -> local transform warps
+//   xf_done[s]    local   this CTA's 128 transform threads wrote lo                    -> local relay lane (warp 2)
+//   lo_ready[s]   LEADER  one arrive per CTA (relay lane; the peer's arrive is remote)  -> MMA issuer
+//   empty[s]      both    tcgen05.commit ... multicast::cluster 0b11: MMAs retired      -> local TMA producer
+//   tmem_full[b]  both    commit multicast                                             -> local epilogue warps
+//   tmem_empty[b] LEADER  8 epilogue warps of EACH CTA (peer: remote arrive)            -> MMA issuer
+// Open points to check on hardware before trusting it: (1) both CTAs issue tcgen05.alloc.cta_group::2 (as the guide's
+// allocator does) and receive the same column base; (2) the N split of an MN-major B operand follows the same
+// descriptor in both CTAs; (3) proxy fencing of the peer's generic-proxy lo writes towards the leader's tensor core
+// (fence.proxy.async + release.cluster arrive below); (4) cluster launch with 226 KB of dynamic shared memory per CTA.
+// =====================================================================================================
+constexpr int P_STAGES = 6;
+constexpr int P_RAW_BYTES = OPER_BYTES_A + OPER_BYTES_A;          // own A (128 cols) + half of B (128 cols): 16 KB
+constexpr int P_STAGE_BYTES = 2 * P_RAW_BYTES;                    // raw + lo: 32 KB
+constexpr int P_SMEM_BYTES = P_STAGES * P_STAGE_BYTES + 1024 /*align*/ + 1024 /*barriers*/ + EPI_WARPS * CBOX_BYTES;
+constexpr uint32_t kInstrDesc2 = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((256u >> 3) << 17) | ((256u >> 4) << 24);
+
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank)
+{
+    uint32_t raddr;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(bar)), "r"(rank));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity)
+{
+    const long long t0 = clock64();
+    for (;;) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (ok) return;
+        if (clock64() - t0 > 8000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void tcgen05_commit_pair(uint64_t* bar)
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma_tf32_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// tiles: (ti, tj) in units of 256 x 256; a.tiles / a.num_tiles as for variant 2; gridDim.x is even, cluster = CTA pair
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
+syrk_tc3_pair_kernel(const __grid_constant__ CUtensorMap map_raw, const __grid_constant__ CUtensorMap map_c, const TcArgs a)
+{
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P_STAGES * P_STAGE_BYTES);
+    uint64_t* raw_full = bars;                        // [P_STAGES]
+    uint64_t* xf_done = bars + P_STAGES;              // [P_STAGES]
+    uint64_t* lo_ready = bars + 2 * P_STAGES;         // [P_STAGES]  (used in the leader)
+    uint64_t* empty_bar = bars + 3 * P_STAGES;        // [P_STAGES]
+    uint64_t* tmem_full = bars + 4 * P_STAGES;        // [2]
+    uint64_t* tmem_empty = bars + 4 * P_STAGES + 2;   // [2]        (used in the leader)
+    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 4 * P_STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int num_k = (a.K + BK - 1) / BK;
+    const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < P_STAGES; ++s) {
+            mbar_init(&raw_full[s], 1); mbar_init(&xf_done[s], 128); mbar_init(&lo_ready[s], 2); mbar_init(&empty_bar[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 2 * EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_raw) : "memory");
+        if (a.tma_c) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c) : "memory");
+    }
+    cluster_sync_all();                                // barrier inits visible to the peer before any remote arrive
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    cluster_sync_all();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_base_slot;
+
+    if (warp < 4) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;" ::: "memory");
+        if (warp == 0) {
+            // ===================== TMA producer (each CTA: its own A columns + its half of B) =====================
+            if (elect_one_sync()) {
+                uint32_t stage = 0, phase = 0;
+                for (int t = pair; t < a.num_tiles; t += num_pairs) {
+                    const int2 tile = a.tiles[t];
+                    const int i0 = tile.x * 256 + (int)rank * 128, j0 = tile.y * 256 + (int)rank * 128;
+                    for (int kb = 0; kb < num_k; ++kb) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        mbar_arrive_expect_tx(&raw_full[stage], P_RAW_BYTES);
+                        unsigned char* sa = smem + stage * P_STAGE_BYTES;
+                        unsigned char* sb = sa + OPER_BYTES_A;
+                        const int k0 = kb * BK;
+#pragma unroll
+                        for (int cb = 0; cb < A_BLOCKS; ++cb) tma_load_2d(sa + cb * BOX_BYTES, &map_raw, &raw_full[stage], i0 + cb * BOX_COLS, k0);
+#pragma unroll
+                        for (int cb = 0; cb < A_BLOCKS; ++cb) tma_load_2d(sb + cb * BOX_BYTES, &map_raw, &raw_full[stage], j0 + cb * BOX_COLS, k0);
+                        if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        } else if (warp == 1 && leader) {
+            // ===================== MMA issuer (leader CTA only) =====================
+            uint32_t stage = 0, phase = 0, buf = 0, buf_phase = 0;
+            for (int t = pair; t < a.num_tiles; t += num_pairs) {
+                for (int kb = 0; kb < num_k; ++kb) {
+                    const bool chunk_first = (kb % KC_STAGES) == 0;
+                    const bool chunk_last = (kb % KC_STAGES) == KC_STAGES - 1 || kb == num_k - 1;
+                    if (chunk_first) {
+                        mbar_wait_cluster(&tmem_empty[buf], buf_phase ^ 1);     // both CTAs' epilogues drained this accumulator
+                        tcgen05_fence_after();
+                    }
+                    const uint32_t tmem_d = tmem_base + buf * BN;
+                    mbar_wait_cluster(&lo_ready[stage], phase);                  // both CTAs' raw tiles landed and were split
+                    tcgen05_fence_after();
+                    if (elect_one_sync()) {
+                        const uint32_t sa_hi = smem_u32(smem + stage * P_STAGE_BYTES);
+                        const uint32_t sb_hi = sa_hi + OPER_BYTES_A;
+                        const uint32_t sa_lo = sa_hi + P_RAW_BYTES;
+                        const uint32_t sb_lo = sa_lo + OPER_BYTES_A;
+#pragma unroll
+                        for (int ks = 0; ks < BK / 8; ++ks) {
+                            const uint32_t koff = ks * 8 * 128;
+                            const uint32_t first = (chunk_first && ks == 0) ? 0u : 1u;
+                            tcgen05_mma_tf32_pair(tmem_d, make_desc(sa_lo + koff), make_desc(sb_hi + koff), kInstrDesc2, first);
+                            tcgen05_mma_tf32_pair(tmem_d, make_desc(sa_hi + koff), make_desc(sb_lo + koff), kInstrDesc2, 1u);
+                            tcgen05_mma_tf32_pair(tmem_d, make_desc(sa_hi + koff), make_desc(sb_hi + koff), kInstrDesc2, 1u);
+                        }
+                        tcgen05_commit_pair(&empty_bar[stage]);                  // frees the slot in BOTH CTAs
+                        if (chunk_last) tcgen05_commit_pair(&tmem_full[buf]);    // wakes BOTH epilogues
+                    }
+                    __syncwarp();
+                    if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
+                    if (chunk_last) { if (++buf == 2) { buf = 0; buf_phase ^= 1; } }
+                }
+            }
+        } else if (warp == 2) {
+            // ===================== relay: "this CTA's lo tile is complete" -> leader =====================
+            if (elect_one_sync()) {
+                uint32_t stage = 0, phase = 0;
+                for (int t = pair; t < a.num_tiles; t += num_pairs)
+                    for (int kb = 0; kb < num_k; ++kb) {
+                        mbar_wait(&xf_done[stage], phase);
+                        asm volatile("fence.proxy.async;" ::: "memory");
+                        mbar_arrive_remote(&lo_ready[stage], 0);
+                        if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
+                    }
+            }
+        }
+    } else if (warp < 8) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 72;" ::: "memory");
+        // ===================== transform (as variant 2, on this CTA's 16 KB) =====================
+        const int tt = threadIdx.x - 128;
+        uint32_t stage = 0, phase = 0;
+        for (int t = pair; t < a.num_tiles; t += num_pairs) {
+            for (int kb = 0; kb < num_k; ++kb) {
+                mbar_wait(&raw_full[stage], phase);
+                const uint32_t raw = smem_u32(smem + stage * P_STAGE_BYTES) + tt * 16;
+                const uint32_t lo = raw + P_RAW_BYTES;
+#pragma unroll 4
+                for (int i = 0; i < P_RAW_BYTES / 16 / 128; ++i) {
+                    const float4 v = lds128(raw + i * 2048);
+                    float4 l;
+                    if (a.unbiased) {
+                        float4 h;
+                        h.x = rna_tf32(v.x); h.y = rna_tf32(v.y); h.z = rna_tf32(v.z); h.w = rna_tf32(v.w);
+                        l.x = rna_tf32(v.x - h.x); l.y = rna_tf32(v.y - h.y); l.z = rna_tf32(v.z - h.z); l.w = rna_tf32(v.w - h.w);
+                        sts128(raw + i * 2048, h);
+                    } else {
+                        l.x = rna_tf32(v.x - trunc_tf32(v.x)); l.y = rna_tf32(v.y - trunc_tf32(v.y));
+                        l.z = rna_tf32(v.z - trunc_tf32(v.z)); l.w = rna_tf32(v.w - trunc_tf32(v.w));
+                    }
+                    sts128(lo + i * 2048, l);
+                }
+                asm volatile("fence.proxy.async;" ::: "memory");
+                mbar_arrive(&xf_done[stage]);
+                if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 176;" ::: "memory");
+        // ===================== epilogue (as variant 2; rows of this CTA's half of the 256 x 256 tile) =====================
+        const int q = warp & 3;
+        const int half = (warp - 8) >> 2;
+        uint32_t buf = 0, buf_phase = 0;
+        const int num_chunks = (num_k + KC_STAGES - 1) / KC_STAGES;
+        for (int t = pair; t < a.num_tiles; t += num_pairs) {
+            const int2 tile = a.tiles[t];
+            const int i = tile.x * 256 + (int)rank * 128 + q * 32 + lane;
+            const int j0 = tile.y * 256 + half * 128;
+            float acc[128];
+#pragma unroll
+            for (int v = 0; v < 128; ++v) acc[v] = 0.f;
+            for (int c = 0; c < num_chunks; ++c) {
+                mbar_wait(&tmem_full[buf], buf_phase);
+                tcgen05_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + half * 128;
+#pragma unroll
+                for (int c0 = 0; c0 < 128; c0 += 32) {
+                    uint32_t r[32];
+                    tmem_ld_32x32b_x32(taddr + c0, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int v = 0; v < 32; ++v) acc[c0 + v] = __fadd_rn(acc[c0 + v], __uint_as_float(r[v]));
+                }
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_remote(&tmem_empty[buf], 0);
+                if (++buf == 2) { buf = 0; buf_phase ^= 1; }
+            }
+            if (a.tma_c) {
+                unsigned char* box = smem + P_STAGES * P_STAGE_BYTES + 1024 + (warp - 8) * CBOX_BYTES;
+                const uint32_t box_u32 = smem_u32(box);
+#pragma unroll
+                for (int c0 = 0; c0 < 128; c0 += 32) {
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    __syncwarp();
+#pragma unroll
+                    for (int v = 0; v < 8; ++v) {
+                        const float4 o = make_float4(a.alpha * acc[c0 + 4 * v + 0], a.alpha * acc[c0 + 4 * v + 1],
+                                                     a.alpha * acc[c0 + 4 * v + 2], a.alpha * acc[c0 + 4 * v + 3]);
+                        sts128(box_u32 + lane * 128 + ((v ^ (lane & 7)) << 4), o);
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        const int cx = j0 + c0, cy = tile.x * 256 + (int)rank * 128 + q * 32;
+                        if (a.tma_c == 2)
+                            asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2}], [%3];"
+                                         ::"l"(&map_c), "r"(cx), "r"(cy), "r"(box_u32) : "memory");
+                        else
+                            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];"
+                                         ::"l"(&map_c), "r"(cx), "r"(cy), "r"(box_u32) : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                }
+            } else if (i < a.MI) {
+                float* crow = a.C + (long long)i * a.ldc;
+#pragma unroll 4
+                for (int v = 0; v < 128; ++v) {
+                    if (j0 + v < a.NJ) {
+                        float o = a.alpha * acc[v];
+                        if (a.beta != 0.f) o = fmaf(a.beta, crow[j0 + v], o);
+                        crow[j0 + v] = o;
+                    }
+                }
+            }
+        }
+    }
+
+    if (warp >= 8 && lane == 0 && a.tma_c) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    tcgen05_fence_before();
+    cluster_sync_all();                                // both CTAs are done with the pair's tensor memory
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+#endif  // SD_EXPERIMENTAL_2CTA
+
 // C (rows x cols, pitch ld) as 32 x 32 boxes, 128B-swizzled in shared memory
 int make_map_c(sd_ctx* ctx, CUtensorMap* map, float* base, int64_t ld, int rows, int cols)
 {
