@@ -1076,3 +1076,52 @@ int sd_syrk_tc(sd_ctx* ctx, const float* d_S, int64_t lds, int K, int MI, int NJ
     }
     return SD_OK;
 }
+
+#ifdef SD_EXPERIMENTAL_2CTA
+// DRAFT host side of the CTA-pair variant (see the kernel's header comment): 256 x 256 tiles, one CTA pair per tile,
+// cluster launch.  Not reachable from the C ABI.
+int sd_syrk_tc_pair_draft(sd_ctx* ctx, const float* d_S, int64_t lds, int K, int MI, int NJ, float* d_C, int64_t ldc,
+                          float alpha, float beta, bool unbiased_split)
+{
+    if (MI <= 0 || NJ <= 0 || K <= 0) return SD_OK;
+    CUtensorMap map_raw, map_c;
+    int rc = make_map(ctx, &map_raw, d_S, lds, K, NJ);
+    if (rc) return rc;
+    const int TI = sd_div_up(MI, 256), TJ = sd_div_up(NJ, 256);
+    std::vector<int2> tiles;
+    for (int si = 0; si < TI; si += 6)
+        for (int sj = 0; sj < TJ; sj += 12)
+            for (int ti = si; ti < si + 6 && ti < TI; ++ti)
+                for (int tj = sj; tj < sj + 12 && tj < TJ; ++tj)
+                    if (tj * 256 + 255 >= ti * 256) tiles.push_back(make_int2(ti, tj));
+    if (tiles.empty()) return SD_OK;
+    int2* d_tiles = (int2*)sd_workspace(ctx, SD_WS_DIAGINV, tiles.size() * sizeof(int2));
+    if (!d_tiles) return SD_ERR_CUDA;
+    SD_CUDA(ctx, cudaMemcpyAsync(d_tiles, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
+    TcArgs a;
+    a.K = K; a.MI = MI; a.NJ = NJ; a.C = d_C; a.ldc = ldc; a.alpha = alpha; a.beta = beta; a.passes = 3;
+    a.unbiased = unbiased_split ? 1 : 0;
+    a.tiles = d_tiles; a.num_tiles = (int)tiles.size();
+    a.tma_c = 0;
+    map_c = map_raw;
+    if ((beta == 0.f || beta == 1.f) && (ldc % 4) == 0 && (reinterpret_cast<uintptr_t>(d_C) & 15) == 0) {
+        rc = make_map_c(ctx, &map_c, d_C, ldc, MI, NJ);
+        if (rc) return rc;
+        a.tma_c = beta == 1.f ? 2 : 1;
+    }
+    const int pairs = a.num_tiles < ctx->sm_count / 2 ? a.num_tiles : ctx->sm_count / 2;
+    SD_CUDA(ctx, cudaFuncSetAttribute(syrk_tc3_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(T2_THREADS);
+    cfg.dynamicSmemBytes = P_SMEM_BYTES;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    SD_CUDA(ctx, cudaLaunchKernelEx(&cfg, syrk_tc3_pair_kernel, map_raw, map_c, a));
+    return SD_OK;
+}
+#endif
+
