@@ -299,3 +299,29 @@ def test_normalised_landmark_errors_match_a_float64_restatement(oracle):
     ied = np.linalg.norm(re - le, axis=1)
     d = np.hypot(pred[:, :L].astype(np.float64) - gt[:, :L], pred[:, L:].astype(np.float64) - gt[:, L:])
     assert np.allclose(got, d / ied[:, None], rtol=1e-6, atol=0)
+
+
+def test_hog_transform_properties(oracle):
+    """Size-independent properties of the projection (adaptive_vlhog.hpp:109-185) that any restatement must keep:
+    a constant image gives the zero descriptor (plus the bias); shifting the frame and the landmarks by the same integer
+    offset leaves interior descriptors unchanged; cv::resize to the same size is the identity."""
+    import synth
+    rng = np.random.default_rng(21)
+    hp = oracle.HogParam(1, 5, 10, 4, 1.0)
+    L = 6
+    x = np.concatenate([rng.uniform(70, 130, L), rng.uniform(70, 110, L)]).astype(np.float32)
+    x[0], x[L], x[1], x[L + 1] = 80.0, 90.0, 130.0, 90.0          # IED = 50 -> half = 25, patch 50 = num_cells * cell_size
+    flat = np.full((200, 220), 97, np.uint8)
+    f = oracle.hog_transform(flat, x, hp, [0], [1])
+    assert f[-1] == 1.0 and not np.any(f[:-1])
+    img = synth.smooth_images(1, 200, 220, seed=8)[0]
+    base = oracle.hog_transform(img, x, hp, [0], [1])
+    dx, dy = 7, 11
+    shifted = np.zeros_like(img)
+    shifted[dy:, dx:] = img[:-dy, :-dx]
+    xs = x.copy()
+    xs[:L] += dx
+    xs[L:] += dy
+    assert np.array_equal(oracle.hog_transform(shifted, xs, hp, [0], [1]), base)
+    patch = rng.integers(0, 256, size=(37, 37), dtype=np.uint8)
+    assert np.array_equal(oracle.resize_linear_u8(patch, 37, 37), patch)
