@@ -180,117 +180,224 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-# measured once with ncu (--set full) on hog_patch_kernel<4,5,11>, 2048 faces x 22 patches: 160.26 MB read + 51.71 MB written
-HOG_L0_DRAM_BYTES_PER_FACE = (160.259584e6 + 51.714560e6) / 2048
+# static profile facts about the level-0 HOG kernel: NOT measured in the bench run, quoted from the committed ncu summary
+HOG_STATIC_PROFILE = {"source": "profiles/r01_summary.md section 12 (one `ncu --set full` capture of hog_patch_kernel<4,5,11>, 2048 faces)",
+                      "dram_bytes_per_face": (160.259584e6 + 51.714560e6) / 2048, "issue_slots_busy_pct": 76.4,
+                      "warp_instructions_per_patch": 22723}
 
-TRAIN_CFG = {"n": 10000, "size": 128, "num_bins": 9, "cells": 5, "cell_sizes": [11, 10, 8, 6, 6], "rel": [1.0, 0.7, 0.4, 0.25, 0.25],
-             "lambda_factor": 1.5}
+TRAIN_CFGS = {
+    # SURVEY 8d config 4 / BASELINE configs[3]
+    "train": {"name": "configs[3]: RCR training, 10k synthetic 128x128 crops, 22 landmarks, 31-bin HOG (K=9), 5 cascade levels",
+              "n": 10000, "size": 128, "landmarks": 22, "num_bins": 9, "cells": 5, "cell_sizes": [11, 10, 8, 6, 6],
+              "rel": [1.0, 0.7, 0.4, 0.25, 0.25], "lambda_factor": 1.5, "seed": 2024},
+    # SURVEY 8d config 5 / BASELINE configs[4]
+    "train5": {"name": "configs[4]: RCR training, 100k synthetic 256x256 crops, 68 landmarks, 31-bin HOG (K=9), 6 cascade levels",
+               "n": 100000, "size": 256, "landmarks": 68, "num_bins": 9, "cells": 5, "cell_sizes": [11, 10, 8, 6, 6, 6],
+               "rel": [1.0, 0.7, 0.4, 0.25, 0.25, 0.25], "lambda_factor": 1.5, "seed": 2025},
+}
+TRAIN_CFG = TRAIN_CFGS["train"]
+GEN_CHUNK = 256      # synthetic samples are generated in global chunks of this many, seeded by the chunk index
 
 
-def synth_train_set(sd, model, n_local, seed, dev):
-    """128x128 8UC1 crops, box = crop shrunk by 10 %, ground truth = mean shape in a box
-    jittered N(0, 0.04) in translation and N(1, 0.04) in scale (rcr-train.cpp:387-395), x0 = mean in the box."""
+def train_shape_model(cfg, model):
+    """(mean, landmark ids, right eye ids, left eye ids) of a training config: the rcr_22 model's for 22 landmarks, the
+    reference's 68-point mean (examples/data/mean_ibug_lfpw_68.txt, committed as tests/golden/mean_ibug_lfpw_68.npy) otherwise."""
+    if cfg["landmarks"] == 22:
+        import ctypes as C
+        from superviseddescent_b200 import _capi
+        from superviseddescent_b200 import api as sd
+        ids = model.landmark_ids
+        norm_c = sd.NormalisationC()
+        _capi.lib().sd_model_normalisation(model._m, C.byref(norm_c))
+        return (model.get_mean(), ids, [ids[norm_c.right_idx[i]] for i in range(norm_c.n_right)],
+                [ids[norm_c.left_idx[i]] for i in range(norm_c.n_left)])
+    mean = np.load(os.path.join(ROOT, "tests", "golden", "mean_ibug_lfpw_68.npy")).astype(np.float32).reshape(-1)
+    return mean, [str(i) for i in range(1, 69)], ["37", "40"], ["43", "46"]
+
+
+def synth_train_images(cfg, b, e, dev):
+    """Crops [b, e) of the GLOBAL synthetic training set (low-pass filtered noise, 8UC1): every chunk of GEN_CHUNK samples has
+    its own seed, so the set is the same whatever the number of ranks it is sharded over."""
     import torch
     import torch.nn.functional as F
-    size = TRAIN_CFG["size"]
-    g = torch.Generator(device=dev)
-    g.manual_seed(seed)
+    size = cfg["size"]
     sigma, r = 3.0, 9
     k = torch.exp(-0.5 * (torch.arange(-r, r + 1, device=dev, dtype=torch.float32) / sigma) ** 2)
     k = k / k.sum()
-    imgs = torch.empty((n_local, size, size), dtype=torch.uint8, device=dev)
-    for i0 in range(0, n_local, 1024):
-        n = min(1024, n_local - i0)
-        x = torch.rand((n, 1, size + 2 * r, size + 2 * r), generator=g, device=dev)
+    imgs = torch.empty((e - b, size, size), dtype=torch.uint8, device=dev)
+    g = torch.Generator(device=dev)
+    for c in range(b // GEN_CHUNK, (e + GEN_CHUNK - 1) // GEN_CHUNK):
+        g.manual_seed(cfg["seed"] * 1000003 + c)
+        x = torch.rand((GEN_CHUNK, 1, size + 2 * r, size + 2 * r), generator=g, device=dev)
         x = F.conv2d(F.conv2d(x, k.view(1, 1, -1, 1)), k.view(1, 1, 1, -1))
         lo, hi = x.amin(dim=(2, 3), keepdim=True), x.amax(dim=(2, 3), keepdim=True)
-        imgs[i0:i0 + n] = ((x - lo) / (hi - lo) * 255.0).round().clamp(0, 255).to(torch.uint8)[:, 0]
-    rng = np.random.Generator(np.random.PCG64(seed))
-    mean = model.get_mean()
+        x = ((x - lo) / (hi - lo) * 255.0).round().clamp(0, 255).to(torch.uint8)[:, 0]
+        g0, g1 = max(b, c * GEN_CHUNK), min(e, (c + 1) * GEN_CHUNK)
+        imgs[g0 - b:g1 - b] = x[g0 - c * GEN_CHUNK:g1 - c * GEN_CHUNK]
+    return imgs
+
+
+def synth_train_landmarks(sd, mean, cfg, b, e):
+    """box = crop shrunk by 10 %, ground truth = mean shape in a box jittered N(0, 0.04) in translation and
+    N(1, 0.04) in scale (rcr-train.cpp:387-395), x0 = mean in the unjittered box; rows [b, e) of the global set."""
+    size = cfg["size"]
+    rng = np.random.Generator(np.random.PCG64(cfg["seed"]))
+    jit = rng.normal(0.0, 0.04, size=(cfg["n"], 4))[b:e]
     m = int(round(size * 0.05))
     box = (m, m, size - 2 * m, size - 2 * m)
-    x0 = np.tile(sd.align_mean(mean, box), (n_local, 1)).astype(np.float32)
-    x_gt = np.stack([sd.align_mean(mean, box, 1.0 + rng.normal(0, 0.04), 1.0 + rng.normal(0, 0.04), rng.normal(0, 0.04), rng.normal(0, 0.04))
-                     for _ in range(n_local)]).astype(np.float32)
-    return imgs, x0, x_gt
+    x0 = np.tile(sd.align_mean(mean, box), (e - b, 1)).astype(np.float32)
+    x_gt = np.stack([sd.align_mean(mean, box, 1.0 + j[0], 1.0 + j[1], j[2], j[3]) for j in jit]).astype(np.float32)
+    return x0, x_gt
 
 
-def run_train(sd, ctx, model, world, rank, dev, barrier, max_over_ranks, group):
-    """Regressor-train seconds (all S levels: HOG + targets + Gram + all-reduce + solve + update), strong scaling."""
+def syrk_executed_flops(n, D, M, passes=3):
+    """MMA flops the Gram kernel executes: every 128 x 256 tile that touches the upper triangle of [AtA | Atb], three TF32 passes."""
+    TI, TJ = (D + 127) // 128, (D + M + 255) // 256
+    tiles = sum(1 for ti in range(TI) for tj in range(TJ) if tj * 256 + 255 >= ti * 128)
+    return passes * 2.0 * n * tiles * 128 * 256
+
+
+def run_train(sd, ctx, model, world, rank, dev, barrier, max_over_ranks, comm, cfg=None, steps=1, warmup=1, e2e=False, distributed_solve=None):
+    """Regressor-train seconds (all S levels: HOG + targets + Gram + exchange + solve + update), strong scaling: the SAME global
+    training set for every number of ranks (samples are generated by global index)."""
     import torch
     from superviseddescent_b200 import parallel
-    cfg = TRAIN_CFG
+    cfg = cfg or TRAIN_CFG
+    mean, ids, right, left = train_shape_model(cfg, model)
+    L = cfg["landmarks"]
     b, e = parallel.shard_range(cfg["n"], world, rank)
-    imgs, x0, x_gt = synth_train_set(sd, model, e - b, 2024 + rank, dev)
-    ids = model.landmark_ids
-    norm_c = sd.NormalisationC()
-    import ctypes as C
-    from superviseddescent_b200 import _capi
-    _capi.lib().sd_model_normalisation(model._m, C.byref(norm_c))
-    right = [ids[norm_c.right_idx[i]] for i in range(norm_c.n_right)]
-    left = [ids[norm_c.left_idx[i]] for i in range(norm_c.n_left)]
+    imgs = synth_train_images(cfg, b, e, dev)
+    x0, x_gt = synth_train_landmarks(sd, mean, cfg, b, e)
     hps = [sd.HoGParam(1, cfg["cells"], cs, cfg["num_bins"], rel) for cs, rel in zip(cfg["cell_sizes"], cfg["rel"])]
     ht = sd.HogTransform(imgs, hps, ids, right, left, ctx)
     D = ht.feature_length(0)
+    S = len(hps)
+    ds = (D >= parallel.DIST_SOLVE_MIN_D) if distributed_solve is None else bool(distributed_solve)
+    gram_ms = []
 
-    def one_run():
-        regs = [sd.LinearRegressor(sd.Regulariser(sd.RegularisationType.MatrixNorm, cfg["lambda_factor"], False), ctx) for _ in hps]
+    def one_run(levels=None):
+        use = hps if levels is None else hps[:levels]
+        regs = [sd.LinearRegressor(sd.Regulariser(sd.RegularisationType.MatrixNorm, cfg["lambda_factor"], False), ctx) for _ in use]
         sdo = sd.SupervisedDescentOptimiser(regs, sd.InterEyeDistanceNormalisation(ids, right, left), ctx)
-        xf = sdo.train(x_gt, x0, None, ht, None, group)
+        xf = sdo.train(x_gt, x0, None, ht, None, comm=comm, distributed_solve=ds)
         return sdo, xf
 
-    one_run()                                  # warm-up (workspaces, tensor maps, NCCL channels)
+    for _ in range(max(warmup, 1)):
+        one_run(1 if cfg["n"] > 20000 else None)     # warm-up (workspaces, tensor maps, NCCL channels); one level of the big config
     barrier()
     l0 = ctx.launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    sdo, xf = one_run()
+    for _ in range(steps):
+        sdo, xf = one_run()
     e1.record()
     barrier()
-    secs = max_over_ranks(e0.elapsed_time(e1)) * 1e-3
-    res0 = float(torch.linalg.norm(torch.from_numpy(x0).to(dev) - torch.from_numpy(x_gt).to(dev)) / torch.linalg.norm(torch.from_numpy(x_gt).to(dev)))
-    res1 = float(torch.linalg.norm(xf - torch.from_numpy(x_gt).to(dev)) / torch.linalg.norm(torch.from_numpy(x_gt).to(dev)))
-    S = len(hps)
-    gram_flops = S * (cfg["n"] * D * (D + 1) + 2.0 * cfg["n"] * D * 44)
-    chol_flops = S * (D ** 3 / 3.0 + 2.0 * D * D * 44)
-    return {"metric": "regressor train sec (RCR, all cascade levels)", "value": secs, "unit": "s", "higher_is_better": False, "scaling": "strong",
-            "config": {"workload": "configs[3]: RCR training, 10k synthetic 128x128 crops, 22 landmarks, 31-bin HOG (K=9), 5 cascade levels",
-                       "samples_global": cfg["n"], "samples_this_rank": e - b, "feature_dim": D, "levels": S,
-                       "parallelism": f"samples sharded over {world} GPU(s), one all-reduce of the upper row bands of [AtA|Atb] "
-                                      f"({sum((min(b + 1024, D) - b) * (D + 44 - b) for b in range(0, D, 1024)) * 4 / 1e9:.2f} of {D * (D + 44) * 4 / 1e9:.2f} GB) per level, replicated solve"},
-            "gpu_launches": int(ctx.launches() - l0),
-            "algorithmic_tflop": {"gram_syrk": gram_flops / 1e12, "cholesky_and_solve": chol_flops / 1e12},
-            "train_residual": {"before": res0, "after": res1},
-            "last_level_solver_ms": ctx.solver_timings()}
+    secs = max_over_ranks(e0.elapsed_time(e1)) * 1e-3 / steps
+    launches = int(ctx.launches() - l0) // steps
+    solver_ms = ctx.solver_timings()
+    g = torch.from_numpy(x_gt).to(dev)
+    num = torch.stack([torch.sum((torch.from_numpy(x0).to(dev) - g) ** 2), torch.sum((xf - g) ** 2), torch.sum(g ** 2)]).double()
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(num)
+    res0, res1 = float(torch.sqrt(num[0] / num[2])), float(torch.sqrt(num[1] / num[2]))
+    # the trained model's fingerprint: identical data for every N, so these agree across N up to summation order
+    checksum = [float(r.x.double().abs().sum()) for r in sdo.regressors]
+    out = {"metric": "regressor train sec (RCR, all cascade levels)", "value": secs, "unit": "s", "higher_is_better": False, "scaling": "strong",
+           "n_gpus": world, "steps": steps, "warmup": max(warmup, 1), "ms_per_step": secs * 1e3, "dtype": "f32", "data": "synthetic", "vs_baseline": None,
+           "config": {"workload": cfg["name"], "samples_global": cfg["n"], "samples_this_rank": e - b, "feature_dim": D, "levels": S,
+                      "landmarks": L, "l2": f"per-level operands ({(e - b) * D * 4 / 1e9:.2f} GB of features, {D * (D + 2 * L) * 4 / 1e9:.2f} GB Gram) exceed the 126 MB L2",
+                      "parallelism": (f"samples sharded over {world} GPU(s); per level one exchange of the upper row bands of [AtA|Atb] "
+                                      f"({parallel.band_offsets(D, (D + 2 * L + 3) // 4 * 4)[-1] * 4 / 1e9:.2f} of {D * (D + 2 * L) * 4 / 1e9:.2f} GB): "
+                                      + ("reduce to the block-row-cyclic owners + distributed blocked Cholesky (panel broadcast)" if (ds and world > 1)
+                                         else "all-reduce + replicated solve" if world > 1 else "single GPU"))},
+           "gpu_launches": launches,
+           "train_residual": {"before": res0, "after": res1},
+           "weights_checksum_abs_sum_per_level": checksum,
+           "last_level_solver_ms": solver_ms}
+    # roofline of the dominant kernel: the tensor-core Gram SYRK of the last level, timed by CUDA events inside the library on
+    # the launching stream ("At * A" of the reference's VerbosePartialPivLUSolver)
+    n_loc = e - b
+    alg = n_loc * D * (D + 1.0) + 2.0 * n_loc * D * 2 * L
+    t = solver_ms["At * A"] * 1e-3
+    if t > 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("bf16_tflops_sustained", 0) or 0) or 1500.0
+        out["roofline"] = {"kernel": "syrk_tc2_kernel ([AtA|Atb] of the last level, tcgen05 3xTF32)", "bound": "tensor", "achieved": alg / t / 1e12, "peak": peak,
+                           "unit": "TFLOP/s", "frac": alg / t / 1e12 / peak, "traffic": None,
+                           "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (dense bf16; the kernel runs kind::tf32 at half that rate, three passes)" if peaks else "fallback 1500 (B200_PROFILING.md)",
+                           "ms_per_launch": solver_ms["At * A"], "algorithmic_flops_per_launch": alg,
+                           "executed_tf32_tflops": syrk_executed_flops(n_loc, D, 2 * L) / t / 1e12,
+                           "static_profile": {"source": "profiles/r01_summary.md section 6", "tensor_pipe_active_pct": 72.7}}
+    out["algorithmic_tflop"] = {"gram_syrk": S * (cfg["n"] * D * (D + 1.0) + 2.0 * cfg["n"] * D * 2 * L) / 1e12, "cholesky_and_solve": S * (D ** 3 / 3.0 + 2.0 * D * D * 2 * L) / 1e12}
+    if e2e:
+        # the same run from HOST buffers: crops and landmark rows in pinned memory, uploads inside the timed region, the trained
+        # weights read back to the host
+        h_imgs = torch.empty(imgs.shape, dtype=torch.uint8).pin_memory()
+        h_imgs.copy_(imgs)
+        del ht, imgs
+        torch.cuda.synchronize()
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            d_imgs = h_imgs.to(dev, non_blocking=True)
+            ht2 = sd.HogTransform(d_imgs, hps, ids, right, left, ctx)
+            regs = [sd.LinearRegressor(sd.Regulariser(sd.RegularisationType.MatrixNorm, cfg["lambda_factor"], False), ctx) for _ in hps]
+            sdo = sd.SupervisedDescentOptimiser(regs, sd.InterEyeDistanceNormalisation(ids, right, left), ctx)
+            sdo.train(x_gt, x0, None, ht2, None, comm=comm, distributed_solve=ds)
+            w_host = [r.x.cpu() for r in regs]
+            del ht2, d_imgs
+        e1.record()
+        barrier()
+        secs2 = max_over_ranks(e0.elapsed_time(e1)) * 1e-3 / steps
+        out["e2e"] = {"value": secs2, "unit": "s", "h2d_bytes_per_step": int(h_imgs.numel() + x0.nbytes + x_gt.nbytes),
+                      "d2h_bytes_per_step": int(sum(w.numel() * 4 for w in w_host)),
+                      "api": "SupervisedDescentOptimiser.train with HogTransform over crops uploaded from pinned host memory; trained weights copied back"}
+    return out
 
 
-def cpu_train_level_seconds(n_samples, threads, seed=2024):
-    """Reference CPU path for ONE training level of config 4 (level 0: the most expensive one), all host threads:
-    the reference's hog.c inside the restated HogTransform glue (one sample per thread, as the thread pool of
-    superviseddescent.hpp:173-189), then BLAS/LAPACK (numpy/scipy sgemm, sgetrf, sgetrs) standing in for Eigen's
-    A^T A and PartialPivLU (regressors.hpp:199-234) -- BASELINE.md section 3."""
+def cpu_train_level_seconds(n_samples, threads, cfg=None):
+    """Reference CPU path for ONE training level (level 0: the most expensive one), all host threads: the reference's hog.c
+    inside the restated HogTransform glue (one sample per thread, as the thread pool of superviseddescent.hpp:173-189), then
+    BLAS/LAPACK (numpy/scipy sgemm, sgetrf, sgetrs) standing in for Eigen's A^T A and PartialPivLU (regressors.hpp:199-234) --
+    BASELINE.md section 3.  n_samples may be a bounded sample of the config's N; total_extrapolated_s scales the parts."""
     import scipy.linalg
     from oracle import oracle as O
     O.build()
+    cfg = cfg or TRAIN_CFG
     om = O.Model(MODEL)
     use_ref = O.ref_available()
-    cfg = TRAIN_CFG
     size = cfg["size"]
+    L = cfg["landmarks"]
+    if L == 22:
+        mean, right_idx, left_idx = om.mean, om.right_idx, om.left_idx
+    else:
+        mean = np.load(os.path.join(ROOT, "tests", "golden", "mean_ibug_lfpw_68.npy")).astype(np.float32).reshape(-1)
+        right_idx, left_idx = [36, 39], [42, 45]          # ids "37","40" / "43","46" of the 1-based 68-point list
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import synth
-    base = synth.smooth_images(64, size, size, seed)
+    base = synth.smooth_images(64, size, size, cfg["seed"])
     imgs = np.concatenate([base] * ((n_samples + 63) // 64))[:n_samples]
     m = int(round(size * 0.05))
     box = (m, m, size - 2 * m, size - 2 * m)
-    rng = np.random.Generator(np.random.PCG64(seed))
-    x0 = np.tile(O.align_mean(om.mean, box), (n_samples, 1)).astype(np.float32)
-    x_gt = np.stack([O.align_mean(om.mean, box, 1.0 + rng.normal(0, 0.04), 1.0 + rng.normal(0, 0.04), rng.normal(0, 0.04), rng.normal(0, 0.04))
+    rng = np.random.Generator(np.random.PCG64(cfg["seed"]))
+    x0 = np.tile(O.align_mean(mean, box), (n_samples, 1)).astype(np.float32)
+    x_gt = np.stack([O.align_mean(mean, box, 1.0 + rng.normal(0, 0.04), 1.0 + rng.normal(0, 0.04), rng.normal(0, 0.04), rng.normal(0, 0.04))
                      for _ in range(n_samples)]).astype(np.float32)
     hp = O.HogParam(1, cfg["cells"], cfg["cell_sizes"][0], cfg["num_bins"], cfg["rel"][0])
     t0 = time.perf_counter()
-    A = O.hog_transform_batch(imgs, x0, hp, om.right_idx, om.left_idx, use_ref=use_ref, threads=threads)
+    A = O.hog_transform_batch(imgs, x0, hp, right_idx, left_idx, use_ref=use_ref, threads=threads)
     t_hog = time.perf_counter() - t0
-    ied = np.array([O.get_ied(x0[i], om.right_idx, om.left_idx) for i in range(n_samples)])
+    D_full = A.shape[1]
+    if D_full > 20000:                                   # bounded sample: a 52,701-column LU does not fit a bench run
+        keep = np.r_[0:17050, D_full - 1]
+        A = np.ascontiguousarray(A[:, keep])
+    D = A.shape[1]
+    ied = np.array([O.get_ied(x0[i], right_idx, left_idx) for i in range(n_samples)])
     b = ((x0 - x_gt) / ied[:, None]).astype(np.float32)
     t0 = time.perf_counter()
     G = A.T @ A
@@ -305,8 +412,42 @@ def cpu_train_level_seconds(n_samples, threads, seed=2024):
     t0 = time.perf_counter()
     _ = x0 - (A @ X) * ied[:, None]
     t_upd = time.perf_counter() - t0
+    fn = cfg["n"] / n_samples
+    fd = D_full / D
+    total_x = t_hog * fn + t_gram * fn * fd * fd + t_lu * fd ** 3 + t_upd * fn * fd
     return {"hog_s": t_hog, "gram_s": t_gram, "lu_solve_s": t_lu, "update_s": t_upd, "total_s": t_hog + t_gram + t_lu + t_upd,
+            "total_extrapolated_s": total_x, "D": D, "D_full": D_full,
             "kind": "reference hog.c + BLAS/LAPACK for Eigen" if use_ref else "port + BLAS/LAPACK"}
+
+
+def run_train_workload(args, sd, ctx, model, world, rank, local, dev, barrier, max_over_ranks, comm):
+    """--workload train / train5: the regressor-train metric of BASELINE.json as the line itself."""
+    cfg = TRAIN_CFGS[args.workload]
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ds = {"auto": None, "replicated": False, "distributed": True}[args.solve]
+    line = run_train(sd, ctx, model, world, rank, dev, barrier, max_over_ranks, comm, cfg, steps=args.steps, warmup=args.warmup, e2e=True,
+                     distributed_solve=ds)
+    clocks = sampler.stop() if rank == 0 else None
+    if rank != 0:
+        return
+    line["clocks"] = clocks
+    if world == 1 and not args.no_cpu:
+        try:
+            cores = host_cores()
+            n_cpu = min(cfg["n"], 10000) if cfg["landmarks"] == 22 else 1500
+            lvl = cpu_train_level_seconds(n_cpu, cores, cfg)
+            S = len(cfg["cell_sizes"])
+            line["cpu_baseline"] = {"value": lvl["total_extrapolated_s"] * S, "unit": "s", "cores": cores, "kind": "port",
+                                    "sample": f"ONE level (level 0) on {n_cpu} of the {cfg['n']} samples on the host: HOG {lvl['hog_s']:.2f} s, "
+                                              f"Gram {lvl['gram_s']:.2f} s, LU+solve {lvl['lu_solve_s']:.2f} s, update {lvl['update_s']:.2f} s; "
+                                              f"HOG/Gram/update scaled linearly to {cfg['n']} samples"
+                                              + (", LU at the sample's D" if lvl["D"] == lvl["D_full"] else f", LU scaled by (D/{lvl['D']})^3 to D={lvl['D_full']}")
+                                              + f"; x{S} levels (extrapolated); {lvl['kind']}"}
+        except Exception as ex:
+            line["cpu_baseline"] = {"error": repr(ex)[:200]}
+    print(json.dumps(line))
 
 
 def run_ours(args):
@@ -322,20 +463,10 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
         group = dist.group.WORLD
     from superviseddescent_b200 import api as sd
+    from superviseddescent_b200 import parallel
     ctx = sd.Context(local)
     model = sd.load_detection_model(MODEL, ctx)
-    B = args.batch
-    L = model.num_landmarks
-
-    frames = synth_frames_torch(B, 1234 + rank, dev)
-    boxes = synth_boxes(B, 1234 + rank)
-    mean = model.get_mean()
-    x0 = np.stack([sd.align_mean(mean, b) for b in boxes])
-    x0_dev = torch.from_numpy(x0).to(dev)
-    h_frames = torch.empty((B, H_IMG, W_IMG), dtype=torch.uint8).pin_memory()
-    h_frames.copy_(frames)
-    torch.cuda.synchronize()
-    h_np = h_frames.numpy()
+    comm = parallel.Communicator(ctx, group) if world > 1 else None   # the C ABI's NCCL communicator (training exchange)
 
     def barrier():
         if world > 1:
@@ -348,6 +479,27 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             return float(t.item())
         return v
+
+    if args.workload != "detect":
+        run_train_workload(args, sd, ctx, model, world, rank, local, dev, barrier, max_over_ranks, comm)
+        if comm is not None:
+            comm.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    B = args.batch
+    L = model.num_landmarks
+
+    frames = synth_frames_torch(B, 1234 + rank, dev)
+    boxes = synth_boxes(B, 1234 + rank)
+    mean = model.get_mean()
+    x0 = np.stack([sd.align_mean(mean, b) for b in boxes])
+    x0_dev = torch.from_numpy(x0).to(dev)
+    h_frames = torch.empty((B, H_IMG, W_IMG), dtype=torch.uint8).pin_memory()
+    h_frames.copy_(frames)
+    torch.cuda.synchronize()
+    h_np = h_frames.numpy()
 
     # ---------------- device-resident throughput ----------------
     for _ in range(args.warmup):
@@ -415,22 +567,25 @@ def run_ours(args):
     alg_flops = float(B * L * fs0 * fs0 * (24 + 4 * hp0.num_bins))
     peak, peak_src = measured_peaks()
     achieved = alg_bytes / (hog_ms * 1e-3) / 1e9
-    roofline = {"kernel": f"hog_patch_kernel<{hp0.num_bins}> (cascade level 0, fs={fs0})", "bound": "hbm", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": HOG_L0_DRAM_BYTES_PER_FACE * B, "peak_source": peak_src, "ms_per_launch": hog_ms,
-                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel at 2048 faces "
-                                  "(profiles/r01_summary.md section 12), scaled linearly to this batch; below the algorithmic bytes because "
-                                  "the 22 patches of a face overlap (SURVEY 8d counts L*P^2 source pixels)",
-                "issue_slots_busy_pct": 76.4,
-                "algorithmic_bytes_per_launch": alg_bytes,
-                "note": "HOG is fp32-ALU/shared-memory bound (SURVEY 8d: ~40 flop/B); fp32 figure reported beside the HBM one",
-                "achieved_fp32_tflops": alg_flops / (hog_ms * 1e-3) / 1e12}
+    fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12      # 148 SMs x 128 FMA lanes x 2 flop x boost clock (B200_PROFILING.md)
+    roofline = {"kernel": f"hog_patch_kernel<{hp0.num_bins}> (cascade level 0, fs={fs0})",
+                "bound": "issue", "bound_note": "instruction-issue / fp32-ALU + shared-memory bound (~40 flop per algorithmic byte, SURVEY 8d), not HBM; "
+                                                 "achieved/peak/frac are the HBM figures the contract asks for, frac_binding is the fp32 one",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "ms_per_launch": hog_ms,
+                "traffic": None, "algorithmic_bytes_per_launch": alg_bytes,
+                "achieved_fp32_tflops": alg_flops / (hog_ms * 1e-3) / 1e12, "fp32_peak_tflops": fp32_peak,
+                "frac_binding": alg_flops / (hog_ms * 1e-3) / 1e12 / fp32_peak,
+                "static_profile": dict(HOG_STATIC_PROFILE, dram_bytes_this_batch=HOG_STATIC_PROFILE["dram_bytes_per_face"] * B,
+                                       note="quoted from a committed ncu capture, not measured in this run")}
 
     train = None
     if not args.no_train:
         try:
-            train = run_train(sd, ctx, model, world, rank, dev, barrier, max_over_ranks, group)
+            train = run_train(sd, ctx, model, world, rank, dev, barrier, max_over_ranks, comm)
         except Exception as ex:   # the headline line must still be printed
             train = {"error": repr(ex)[:300]}
+    if comm is not None:
+        comm.close()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -455,7 +610,7 @@ def run_ours(args):
     if world == 1 and not args.no_cpu and train is not None and "value" in train:
         try:
             cores = host_cores()
-            lvl = cpu_train_level_seconds(TRAIN_CFG["n"], cores)
+            lvl = cpu_train_level_seconds(TRAIN_CFG["n"], cores, TRAIN_CFG)
             train["cpu_baseline"] = {"value": lvl["total_s"] * len(TRAIN_CFG["cell_sizes"]), "unit": "s", "cores": cores, "kind": "port",
                                      "sample": f"ONE full level (level 0, all {TRAIN_CFG['n']} samples) timed on the host: HOG {lvl['hog_s']:.2f} s, "
                                                f"Gram {lvl['gram_s']:.2f} s, LU+solve {lvl['lu_solve_s']:.2f} s, update {lvl['update_s']:.2f} s; "
@@ -478,13 +633,21 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--workload", default="detect", choices=["detect", "train", "train5"],
+                    help="detect = configs[2] (the default headline line); train = configs[3] and train5 = configs[4]: regressor-train "
+                         "seconds as a first-class line (strong scaling over --gpus)")
+    ap.add_argument("--solve", default="auto", choices=["auto", "replicated", "distributed"], help="multi-GPU solve route of the train workloads")
     ap.add_argument("--batch", type=int, default=4096, help="frames per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-train", action="store_true", help="skip the extra regressor-train measurement")
     args = ap.parse_args()
+    if args.steps is None:
+        args.steps = {"detect": 10, "train": 3, "train5": 1}[args.workload]
+    if args.warmup is None:
+        args.warmup = {"detect": 3, "train": 1, "train5": 1}[args.workload]
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -122,11 +122,18 @@ SD_API int sd_host_free(sd_ctx* ctx, void* h_ptr);
 SD_API int sd_memcpy_h2d(sd_ctx* ctx, void* d_dst, const void* h_src, size_t bytes);  /* async */
 SD_API int sd_memcpy_d2h(sd_ctx* ctx, void* h_dst, const void* d_src, size_t bytes);  /* async */
 SD_API int sd_memset(sd_ctx* ctx, void* d_dst, int value, size_t bytes);
+/* strided rows in one call (cv::Mat rows with a step, or [A | B] side by side on the device): `rows` rows of `row_bytes`
+ * bytes, pitches in bytes; async on the context's stream */
+SD_API int sd_memcpy2d_h2d(sd_ctx* ctx, void* d_dst, size_t dst_pitch, const void* h_src, size_t src_pitch, size_t row_bytes, size_t rows);
+SD_API int sd_memcpy2d_d2h(sd_ctx* ctx, void* h_dst, size_t dst_pitch, const void* d_src, size_t src_pitch, size_t row_bytes, size_t rows);
 
 /* ---- projection h: rcr::HogTransform::operator() batched (adaptive_vlhog.hpp:109-185) -- */
 /* D = L * num_cells^2 * (3K+4 | 4K) + 1 */
 SD_API int sd_hog_feature_length(int num_landmarks, const sd_hog_param* p);
-/* For sample i: image = images[d_image_index ? d_image_index[i] : i], landmarks = d_x[i, 0:2L].
+/* Asynchronous.  A degenerate sample (inter-eye distance too small for a patch: the reference's cv::resize would throw) or an
+ * image index out of range raises a flag on the device that the NEXT synchronising call on the context reports as
+ * SD_ERR_INVALID: sd_sync, sd_hog_debug, sd_detect_batch_device / _host.
+ * For sample i: image = images[d_image_index ? d_image_index[i] : i], landmarks = d_x[i, 0:2L].
  * Writes the reference's feature row (per landmark [dim][cell col][cell row], then bias 1)
  * to d_A[i*ld .. i*ld + D).  Columns [D, ld) are left untouched.  hog.c:174-204,595-728,857-1062
  * run fused with the crop / zero-pad / cv::resize glue of adaptive_vlhog.hpp:123-176.
@@ -185,6 +192,45 @@ SD_API int sd_solver_timings(sd_ctx* ctx, float ms_out[4]);
  * 3 = 3xTF32 split with the hi part rounded in shared memory (unbiased: Gram ~7e-8, ~15 % slower),
  * 1 = single TF32 pass (~7e-5), 2 = force the fp32 SIMT kernel (~3e-7) */
 SD_API int sd_set_gram_mode(sd_ctx* ctx, int mode);
+
+/* ---- multi-GPU training: the exchange at superviseddescent.hpp:207 ----------------------------------------
+ * One process per GPU, samples (rows of A) sharded over the ranks.  [A^T A | A^T b] is a sum over the shards, so per cascade
+ * level there is ONE collective on it; lambda uses the global sample count.  The collectives are NCCL (bound at run time:
+ * libnccl.so.2 must be loadable when nranks > 1).  Two routes:
+ *   replicated : sd_gram -> sd_allreduce_gram -> sd_solve_gram on every rank (small systems; the solve does not scale)
+ *   distributed: sd_gram -> sd_reduce_scatter_gram -> sd_solve_gram_dist: the 256-row panels of [AtA|Atb] are owned
+ *                block-row-cyclically (panel p by rank p % nranks); the owner factors its panel, broadcasts it, every rank
+ *                updates the block rows it owns (blocked right-looking Cholesky, same kernels as on one GPU); every rank
+ *                ends with the same X.  sd_learn_dist runs either route from the local rows.
+ * Determinism: for a fixed nranks the result is reproducible bit for bit; it differs from the one-GPU result only by the
+ * summation order of the partial Gram matrices (~1e-7 relative). */
+typedef struct sd_comm sd_comm;
+#define SD_COMM_ID_BYTES 128
+/* rank 0 obtains an id and hands it to the other ranks by any means the host has (MPI, torch.distributed, a file) */
+SD_API int sd_comm_get_unique_id(uint8_t* id_out /* SD_COMM_ID_BYTES */);
+SD_API int sd_comm_create(sd_ctx* ctx, const uint8_t* id, int rank, int nranks, sd_comm** out);   /* collective */
+/* adopt a ncclComm_t the host already owns (it is not destroyed by sd_comm_destroy) */
+SD_API int sd_comm_adopt(sd_ctx* ctx, void* nccl_comm, int rank, int nranks, sd_comm** out);
+SD_API void sd_comm_destroy(sd_comm* comm);
+SD_API int sd_comm_rank(const sd_comm* comm);
+SD_API int sd_comm_size(const sd_comm* comm);
+/* sum of one host integer over the ranks (the N of the MatrixNorm rule, regressors.hpp:135) */
+SD_API int sd_comm_sum_int64(sd_ctx* ctx, sd_comm* comm, int64_t* h_value);
+/* d_recv[r * bytes_per_rank ..] = rank r's d_send (current landmarks for a training callback, superviseddescent.hpp:217) */
+SD_API int sd_comm_allgather(sd_ctx* ctx, sd_comm* comm, const void* d_send, size_t bytes_per_rank, void* d_recv);
+/* in place on d_G (D x ldg, as written by sd_gram): sums over the ranks the part the solve reads -- every 256-row band from
+ * its diagonal column to the end of its rows (the upper triangle and the right-hand sides; about half of the buffer) */
+SD_API int sd_allreduce_gram(sd_ctx* ctx, sd_comm* comm, float* d_G, int64_t ldg, int D, int M);
+/* the same sums, but band p is only delivered to rank p % nranks (what sd_solve_gram_dist expects) */
+SD_API int sd_reduce_scatter_gram(sd_ctx* ctx, sd_comm* comm, float* d_G, int64_t ldg, int D, int M);
+/* sd_solve_gram on a reduce-scattered d_G; collective, every rank receives X (and the same lambda) */
+SD_API int sd_solve_gram_dist(sd_ctx* ctx, sd_comm* comm, float* d_G, int64_t ldg, int D, int M,
+                              const sd_regulariser* reg, int n_train_global, float* d_X, float* lambda_out);
+/* LinearRegressor::learn on sharded rows: local Gram, exchange, solve.  distributed_solve != 0 selects the distributed
+ * factorisation (pays from D of a few ten thousand), 0 the replicated one.  N_local may be 0. */
+SD_API int sd_learn_dist(sd_ctx* ctx, sd_comm* comm, const float* d_A, int64_t lda, const float* d_B, int64_t ldb,
+                         int N_local, int D, int M, const sd_regulariser* reg, int n_train_global, int distributed_solve,
+                         float* d_X, float* lambda_out);
 
 /* ---- cascade steps: SupervisedDescentOptimiser (superviseddescent.hpp:165-344) ---------- */
 /* b_i = (x_i - x_gt_i) (.) norm(x_i)     (superviseddescent.hpp:199-205) */

@@ -409,9 +409,12 @@ class SupervisedDescentOptimiser:
         host[:, :D] = np.stack(rows)
         return _dev(host, ctx), D
 
-    def train(self, parameters, initialisations, templates, projection, on_training_epoch_callback=None, group=None):
-        """superviseddescent.hpp:165-219.  `group`: optional torch.distributed process group -- each rank
-        passes its own shard of rows; one all-reduce of [AtA | Atb] per level."""
+    def train(self, parameters, initialisations, templates, projection, on_training_epoch_callback=None, group=None, comm=None,
+              distributed_solve=None):
+        """superviseddescent.hpp:165-219.  Multi-GPU: pass `comm` (a parallel.Communicator) or a torch.distributed `group`
+        (a communicator is then made from it) -- each rank passes its own shard of rows; per level the C ABI does ONE exchange of
+        [AtA | Atb] and the solve.  distributed_solve: None = by size (parallel.DIST_SOLVE_MIN_D), True = reduce-scatter +
+        distributed blocked Cholesky, False = all-reduce + replicated solve."""
         from . import parallel
         ctx = self._ctx()
         lib = _capi.lib()
@@ -419,8 +422,11 @@ class SupervisedDescentOptimiser:
         cur = _dev(initialisations, ctx).clone()
         n, P = cur.shape
         tmpl = _dev(templates, ctx) if templates is not None and np.size(templates) > 0 else None
-        distributed = group is not None
-        n_global = parallel.global_count(n, group, cur.device) if distributed else n
+        own_comm = False
+        if comm is None and group is not None:
+            comm, own_comm = parallel.Communicator(ctx, group), True
+        distributed = comm is not None and comm.size > 1
+        n_global = comm.sum_int(n) if distributed else n
         for level, reg in enumerate(self.regressors):
             norm = self.normalisation_strategy.c(P // 2)
             A, D = self._project(projection, cur, level, extra=P)             # 1) features (:173-189)
@@ -428,21 +434,26 @@ class SupervisedDescentOptimiser:
                 _check(ctx.h, lib.sd_subtract_templates(ctx.h, ptr(A), C.c_int64(A.stride(0)), ptr(tmpl), C.c_int64(tmpl.stride(0)), n, D))
             Bv = A[:, D:D + P]                                               # 2) b = (x - x_gt) .* norm(x)  (:199-205)
             _check(ctx.h, lib.sd_cascade_targets(ctx.h, ptr(cur), ptr(x_gt), n, P, C.byref(norm), ptr(Bv), C.c_int64(A.stride(0))))
-            ldg = (D + P + 3) // 4 * 4                                       # 3) learn (:207)
-            G = torch.empty((D, ldg), dtype=torch.float32, device=cur.device)
-            _check(ctx.h, lib.sd_gram(ctx.h, ptr(A), C.c_int64(A.stride(0)), ptr(Bv), C.c_int64(A.stride(0)), n, D, P, ptr(G), C.c_int64(ldg)))
-            if distributed:
-                parallel.allreduce_gram(G, group, D)                         #    the one collective per level (upper bands only)
-            X = torch.empty((D, P), dtype=torch.float32, device=cur.device)
+            X = torch.empty((D, P), dtype=torch.float32, device=cur.device)  # 3) learn (:207)
             lam = C.c_float(0)
             rc_ = reg.regulariser.c()
-            _check(ctx.h, lib.sd_solve_gram(ctx.h, ptr(G), C.c_int64(ldg), D, P, C.byref(rc_), n_global, ptr(X), C.byref(lam)))
+            if distributed:
+                ds = (D >= parallel.DIST_SOLVE_MIN_D) if distributed_solve is None else bool(distributed_solve)
+                _check(ctx.h, lib.sd_learn_dist(ctx.h, comm.h, ptr(A), C.c_int64(A.stride(0)), ptr(Bv), C.c_int64(A.stride(0)), n, D, P,
+                                                C.byref(rc_), n_global, int(ds), ptr(X), C.byref(lam)))
+            else:
+                _check(ctx.h, lib.sd_learn(ctx.h, ptr(A), C.c_int64(A.stride(0)), ptr(Bv), C.c_int64(A.stride(0)), n, D, P, C.byref(rc_),
+                                           ptr(X), C.byref(lam)))
             reg.x, reg.last_lambda = X, lam.value
             nxt = torch.empty_like(cur)                                      # 4) x <- x - (A X) .* 1/norm(x) (:209-215)
             _check(ctx.h, lib.sd_cascade_update(ctx.h, ptr(A), C.c_int64(A.stride(0)), n, D, ptr(X), P, ptr(cur), C.byref(norm), ptr(nxt)))
             cur = nxt
+            del A, Bv
             if on_training_epoch_callback is not None:                       # 5) callback (:217)
-                on_training_epoch_callback(parallel.gather_rows(cur, group) if distributed else cur)
+                on_training_epoch_callback(comm.allgather_rows(cur) if distributed else cur)
+        ctx.sync()                                                           # surfaces flags raised by the projection kernels
+        if own_comm:
+            comm.close()
         return cur
 
     def test(self, initialisations, templates, projection, on_regressor_iteration_callback=None):

@@ -20,7 +20,7 @@ LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(LIBDIR, "libsd_b200.so")
 
-SOURCES = ["sd_api.cu", "sd_hog.cu", "sd_linalg.cu", "sd_gram_tc.cu", "sd_model.cu"]
+SOURCES = ["sd_api.cu", "sd_hog.cu", "sd_linalg.cu", "sd_gram_tc.cu", "sd_model.cu", "sd_comm.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo",
          "-Xcompiler", "-fPIC,-fvisibility=hidden", "-I", os.path.join(ROOT, "include"), "-I", CSRC]
@@ -57,7 +57,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             if rc:
                 raise RuntimeError("nvcc failed: " + " ".join(cmd))
     if jobs or force or _stale(LIB, objs):
-        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart", "-ldl"]
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         if r.returncode:
             sys.stderr.write(r.stdout)

@@ -71,6 +71,23 @@ int sd_eyes_to_dev(sd_ctx* ctx, const sd_normalisation* n, int num_landmarks, sd
     return SD_OK;
 }
 
+// The projection kernels raise bits in their own status word (d_scratch[1]); every synchronising entry point that consumed
+// HOG output reports and clears them, so an error belongs to the call (or the sd_sync) that follows the launch.
+int sd_check_hog_status(sd_ctx* ctx, const char* what)
+{
+    int* h = reinterpret_cast<int*>(ctx->h_scratch) + 1;
+    int* d = reinterpret_cast<int*>(ctx->d_scratch) + 1;
+    SD_CUDA(ctx, cudaMemcpyAsync(h, d, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const int st = *h;
+    if (st) {
+        SD_CUDA(ctx, cudaMemsetAsync(d, 0, sizeof(int), ctx->stream));
+        if (st & 2) return sd_fail(ctx, SD_ERR_INVALID, "%s: image index out of range", what);
+        if (st & 1) return sd_fail(ctx, SD_ERR_INVALID, "%s: empty HOG patch (inter-eye distance too small)", what);
+    }
+    return SD_OK;
+}
+
 extern "C" {
 
 const char* sd_version(void) { return "superviseddescent_b200 0.1 (sm_100a)"; }
@@ -111,7 +128,6 @@ int sd_ctx_create(int device, void* stream, sd_ctx** out)
          cudaMemset(ctx->d_scratch, 0, 4096) == cudaSuccess;
     if (!ok) { sd_ctx_destroy(ctx); return SD_ERR_CUDA; }
     { const char* e = getenv("SD_B200_NO_ROI"); ctx->disable_roi = e && e[0] == '1'; }
-    { const char* e = getenv("SD_B200_TC_VARIANT"); if (e && e[0] == '1') ctx->tc_variant = 1; }
     *out = ctx;
     return SD_OK;
 }
@@ -144,8 +160,7 @@ const char* sd_last_error(const sd_ctx* ctx) { return ctx ? ctx->err.c_str() : "
 int sd_sync(sd_ctx* ctx)
 {
     if (!ctx) return SD_ERR_INVALID;
-    SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return SD_OK;
+    return sd_check_hog_status(ctx, "sync");                  // synchronises the stream; reports flags raised by sd_hog_batch
 }
 
 int64_t sd_launch_count(const sd_ctx* ctx) { return ctx ? ctx->launches : 0; }
@@ -191,6 +206,22 @@ int sd_memcpy_d2h(sd_ctx* ctx, void* h_dst, const void* d_src, size_t bytes)
 {
     if (!ctx) return SD_ERR_INVALID;
     SD_CUDA(ctx, cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return SD_OK;
+}
+
+int sd_memcpy2d_h2d(sd_ctx* ctx, void* d_dst, size_t dst_pitch, const void* h_src, size_t src_pitch, size_t row_bytes, size_t rows)
+{
+    if (!ctx) return SD_ERR_INVALID;
+    if (rows == 0 || row_bytes == 0) return SD_OK;
+    SD_CUDA(ctx, cudaMemcpy2DAsync(d_dst, dst_pitch, h_src, src_pitch, row_bytes, rows, cudaMemcpyHostToDevice, ctx->stream));
+    return SD_OK;
+}
+
+int sd_memcpy2d_d2h(sd_ctx* ctx, void* h_dst, size_t dst_pitch, const void* d_src, size_t src_pitch, size_t row_bytes, size_t rows)
+{
+    if (!ctx) return SD_ERR_INVALID;
+    if (rows == 0 || row_bytes == 0) return SD_OK;
+    SD_CUDA(ctx, cudaMemcpy2DAsync(h_dst, dst_pitch, d_src, src_pitch, row_bytes, rows, cudaMemcpyDeviceToHost, ctx->stream));
     return SD_OK;
 }
 

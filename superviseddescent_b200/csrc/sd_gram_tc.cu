@@ -1,17 +1,19 @@
-// Tensor-core SYRK for sm_100a:  C[i,j] = beta*C[i,j] + alpha * sum_k S[k,i]*S[k,j]  (upper-triangle tiles)
+// Tensor-core SYRK / TN-GEMM for sm_100a:  C[i,j] = beta*C[i,j] + alpha * sum_k SA[k,i]*SB[k,j]
 //
 // This is LinearRegressor::learn's "At * A" (reference verbose_solver.hpp:67, regressors.hpp:208) with
-// A^T b folded in as extra columns, and the trailing update of the blocked Cholesky that replaces
-// PartialPivLU (verbose_solver.hpp:89).  S is row-major [K x NJ] -- one sample per row, exactly as the
-// optimiser stacks the feature rows (superviseddescent.hpp:186-189) -- so BOTH MMA operands are
+// A^T b folded in as extra columns (SA == SB, upper-triangle tiles only), the trailing update of the blocked
+// Cholesky that replaces PartialPivLU (verbose_solver.hpp:89), and -- with two different operands -- the
+// block-row solves P = U_jj^-T B of that factorisation.  S is row-major [K x NJ] -- one sample per row, exactly
+// as the optimiser stacks the feature rows (superviseddescent.hpp:186-189) -- so BOTH MMA operands are
 // "MN-major" (the contraction index K is the slow one).  For 32-bit operands tcgen05 accepts MN-major
 // tiles only in the 128B-swizzle / 32B-atom shared-memory layout, which TMA produces directly
 // (CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): no transposition of A anywhere.
 //
 // Precision: kind::tf32 keeps 10 mantissa bits.  passes == 3 runs the 3xTF32 split
-//     a = hi + lo,  hi = rna_tf32(a), lo = rna_tf32(a - hi);   a_i*a_j ~= hi_i*hi_j + hi_i*lo_j + lo_i*hi_j
-// (relative error ~2^-21 per product, fp32 accumulation in TMEM) on operands pre-split in HBM by
-// split_tf32_kernel; passes == 1 is a single TF32 pass on the raw operand.
+//     a = hi + lo,  lo = rna_tf32(a - hi);   a_i*a_j ~= hi_i*hi_j + hi_i*lo_j + lo_i*hi_j
+// (relative error ~2^-21 per product, fp32 accumulation in TMEM); hi is the raw tile as the tensor core
+// truncates it, or rna_tf32(a) written back in place (unbiased split).  The split happens in shared memory,
+// no hi/lo copies of the operands exist in HBM.  passes == 1 is a single TF32 pass on the raw operand.
 //
 // Accumulation: the tensor core adds into the fp32 TMEM accumulator with truncation, so a long chain
 // drifts low (measured: -1.6e-5 relative after 564 accumulating MMAs).  The chain is therefore cut every
@@ -19,11 +21,7 @@
 // fold the finished chunk into running sums held in REGISTERS with round-to-nearest adds, while the
 // tensor core already works on the next chunk in the other TMEM buffer.
 //
-// Kernel shape (persistent, one CTA per SM, 320 threads):
-//   warp 0      TMA producer   : 4-stage ring of [hi|lo] x [A 128 cols | B 256 cols] x 16 samples
-//   warp 1      MMA issuer     : tcgen05.mma cta_group::1 kind::tf32, M=128 N=256 K=8, accumulators in TMEM
-//   warps 2..9  epilogue       : tcgen05.ld 32x32b -> running sums (128 regs/thread) -> alpha/beta -> global
-//                                (double-buffered TMEM: 2 x 256 columns)
+// Kernel shape (persistent, one CTA per SM, 512 threads): see syrk_tc2_kernel below.
 #include "sd_internal.cuh"
 
 #include <cuda.h>
@@ -44,11 +42,9 @@ constexpr int B_BLOCKS = BN / BOX_COLS;                   // 8
 constexpr int OPER_BYTES_A = A_BLOCKS * BOX_BYTES;        // 8 KB
 constexpr int OPER_BYTES_B = B_BLOCKS * BOX_BYTES;        // 16 KB
 constexpr int STAGE_BYTES = 2 * (OPER_BYTES_A + OPER_BYTES_B);   // hi + lo: 48 KB
-constexpr int TC_THREADS = 320;
 constexpr int KC_STAGES = 8;      // pipeline stages per accumulation chunk: KC = 8 * BK = 128 samples
 constexpr int EPI_WARPS = 8;
 constexpr int TMEM_COLS = 512;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
 // super-tile for L2 reuse: tiles that run concurrently share (GI*128 + GJ*256) operand columns
 constexpr int GI = 12, GJ = 12;
@@ -166,192 +162,21 @@ struct TcArgs {
     long long ldc;
     float alpha, beta;
     int passes;          // 1 or 3
-    int unbiased;        // variant 2: round hi in place (slower, unbiased) instead of using the truncated raw tile
+    int unbiased;        // round hi in place (slower, unbiased) instead of using the truncated raw tile
     const int2* tiles;   // (ti, tj) per tile
     int num_tiles;
-    int tma_c;           // variant 2: 0 = register epilogue, 1 = TMA store (beta == 0), 2 = TMA reduce-add (beta == 1)
+    int tma_c;           // 0 = register epilogue, 1 = TMA store (beta == 0), 2 = TMA reduce-add (beta == 1)
 };
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
-syrk_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, const TcArgs a)
-{
-    extern __shared__ unsigned char smem_raw[];
-    // 1024-byte alignment for the swizzled tiles
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-    uint64_t* full_bar = bars;                  // [STAGES]
-    uint64_t* empty_bar = bars + STAGES;        // [STAGES]
-    uint64_t* tmem_full = bars + 2 * STAGES;    // [2]
-    uint64_t* tmem_empty = bars + 2 * STAGES + 2;   // [2]
-    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int num_k = (a.K + BK - 1) / BK;
-
-    if (warp == 0 && lane == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], EPI_WARPS); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_hi) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_lo) : "memory");
-    }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "r"(TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    tcgen05_fence_before();
-    __syncthreads();
-    tcgen05_fence_after();
-    const uint32_t tmem_base = *tmem_base_slot;
-
-    if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (elect_one_sync()) {
-            uint32_t stage = 0, phase = 0;
-            const uint32_t tx_bytes = (a.passes == 3) ? STAGE_BYTES : (OPER_BYTES_A + OPER_BYTES_B);
-            for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
-                const int2 tile = a.tiles[t];
-                const int i0 = tile.x * BM, j0 = tile.y * BN;
-                for (int kb = 0; kb < num_k; ++kb) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
-                    mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
-                    unsigned char* sa_hi = smem + stage * STAGE_BYTES;
-                    unsigned char* sb_hi = sa_hi + OPER_BYTES_A;
-                    unsigned char* sa_lo = sb_hi + OPER_BYTES_B;
-                    unsigned char* sb_lo = sa_lo + OPER_BYTES_A;
-                    const int k0 = kb * BK;
-#pragma unroll
-                    for (int cb = 0; cb < A_BLOCKS; ++cb) tma_load_2d(sa_hi + cb * BOX_BYTES, &map_hi, &full_bar[stage], i0 + cb * BOX_COLS, k0);
-#pragma unroll
-                    for (int cb = 0; cb < B_BLOCKS; ++cb) tma_load_2d(sb_hi + cb * BOX_BYTES, &map_hi, &full_bar[stage], j0 + cb * BOX_COLS, k0);
-                    if (a.passes == 3) {
-#pragma unroll
-                        for (int cb = 0; cb < A_BLOCKS; ++cb) tma_load_2d(sa_lo + cb * BOX_BYTES, &map_lo, &full_bar[stage], i0 + cb * BOX_COLS, k0);
-#pragma unroll
-                        for (int cb = 0; cb < B_BLOCKS; ++cb) tma_load_2d(sb_lo + cb * BOX_BYTES, &map_lo, &full_bar[stage], j0 + cb * BOX_COLS, k0);
-                    }
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        uint32_t stage = 0, phase = 0;
-        uint32_t buf = 0, buf_phase = 0;
-        for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
-            for (int kb = 0; kb < num_k; ++kb) {
-                const bool chunk_first = (kb % KC_STAGES) == 0;
-                const bool chunk_last = (kb % KC_STAGES) == KC_STAGES - 1 || kb == num_k - 1;
-                if (chunk_first) {
-                    mbar_wait(&tmem_empty[buf], buf_phase ^ 1);      // epilogue has drained this accumulator
-                    tcgen05_fence_after();
-                }
-                const uint32_t tmem_d = tmem_base + buf * BN;
-                mbar_wait(&full_bar[stage], phase);
-                tcgen05_fence_after();
-                if (elect_one_sync()) {
-                    const uint32_t sa_hi = smem_u32(smem + stage * STAGE_BYTES);
-                    const uint32_t sb_hi = sa_hi + OPER_BYTES_A;
-                    const uint32_t sa_lo = sb_hi + OPER_BYTES_B;
-                    const uint32_t sb_lo = sa_lo + OPER_BYTES_A;
-#pragma unroll
-                    for (int ks = 0; ks < BK / 8; ++ks) {
-                        const uint32_t koff = ks * 8 * 128;      // 8 rows of 128 B per UMMA K step
-                        const uint32_t first = (chunk_first && ks == 0) ? 0u : 1u;
-                        if (a.passes == 3) {
-                            tcgen05_mma_tf32(tmem_d, make_desc(sa_lo + koff), make_desc(sb_hi + koff), kInstrDesc, first);
-                            tcgen05_mma_tf32(tmem_d, make_desc(sa_hi + koff), make_desc(sb_lo + koff), kInstrDesc, 1u);
-                            tcgen05_mma_tf32(tmem_d, make_desc(sa_hi + koff), make_desc(sb_hi + koff), kInstrDesc, 1u);
-                        } else {
-                            tcgen05_mma_tf32(tmem_d, make_desc(sa_hi + koff), make_desc(sb_hi + koff), kInstrDesc, first);
-                        }
-                    }
-                    tcgen05_commit(&empty_bar[stage]);                   // smem slot free once these MMAs retire
-                    if (chunk_last) tcgen05_commit(&tmem_full[buf]);     // chunk accumulator complete
-                }
-                __syncwarp();
-                if (++stage == STAGES) { stage = 0; phase ^= 1; }
-                if (chunk_last) { if (++buf == 2) { buf = 0; buf_phase ^= 1; } }
-            }
-        }
-    } else {
-        // ===================== epilogue (warps 2..9) =====================
-        const int q = warp & 3;                       // TMEM lane quarter this warp may access
-        const int half = (warp - 2) >> 2;             // which 128 of the tile's 256 columns
-        uint32_t buf = 0, buf_phase = 0;
-        const bool vec_ok = (a.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.C) & 15) == 0);
-        const int num_chunks = (num_k + KC_STAGES - 1) / KC_STAGES;
-        for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
-            const int2 tile = a.tiles[t];
-            const int i = tile.x * BM + q * 32 + lane;
-            const int j0 = tile.y * BN + half * 128;
-            float acc[128];
-#pragma unroll
-            for (int v = 0; v < 128; ++v) acc[v] = 0.f;
-            for (int c = 0; c < num_chunks; ++c) {
-                mbar_wait(&tmem_full[buf], buf_phase);
-                tcgen05_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + half * 128;
-#pragma unroll
-                for (int c0 = 0; c0 < 128; c0 += 32) {
-                    uint32_t r[32];
-                    tmem_ld_32x32b_x32(taddr + c0, r);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int v = 0; v < 32; ++v) acc[c0 + v] = __fadd_rn(acc[c0 + v], __uint_as_float(r[v]));
-                }
-                tcgen05_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&tmem_empty[buf]);
-                if (++buf == 2) { buf = 0; buf_phase ^= 1; }
-            }
-            if (i < a.MI) {
-                float* crow = a.C + (long long)i * a.ldc;
-                if (vec_ok && j0 + 128 <= a.NJ) {
-#pragma unroll
-                    for (int v = 0; v < 32; ++v) {
-                        float4 o;
-                        o.x = a.alpha * acc[4 * v + 0]; o.y = a.alpha * acc[4 * v + 1];
-                        o.z = a.alpha * acc[4 * v + 2]; o.w = a.alpha * acc[4 * v + 3];
-                        float4* p = reinterpret_cast<float4*>(crow + j0 + 4 * v);
-                        if (a.beta != 0.f) {
-                            const float4 old = *p;
-                            o.x = fmaf(a.beta, old.x, o.x); o.y = fmaf(a.beta, old.y, o.y);
-                            o.z = fmaf(a.beta, old.z, o.z); o.w = fmaf(a.beta, old.w, o.w);
-                        }
-                        *p = o;
-                    }
-                } else {
-#pragma unroll
-                    for (int v = 0; v < 128; ++v) {
-                        if (j0 + v < a.NJ) {
-                            float o = a.alpha * acc[v];
-                            if (a.beta != 0.f) o = fmaf(a.beta, crow[j0 + v], o);
-                            crow[j0 + v] = o;
-                        }
-                    }
-                }
-            }
-        }
-    }
-
-    tcgen05_fence_before();
-    __syncthreads();
-    if (warp == 1) {
-        tcgen05_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
-    }
-}
-
 // =====================================================================================================
-// Variant 2 (default): ONE raw fp32 tile per operand travels L2 -> shared memory; the tensor core truncates it
-// to TF32 by itself (that is the "hi" operand), and a transform warpgroup writes lo = a - trunc_tf32(a) next
-// to it in shared memory.  Halves the operand traffic of the pre-split variant (ncu r01: 9.7 TB/s L2->SM, the
-// binding limit at 57 % tensor-pipe activity) and needs no hi/lo copies of A in HBM.
+// ONE raw fp32 tile per operand travels L2 -> shared memory; the tensor core truncates it to TF32 by itself
+// (that is the "hi" operand), and a transform warpgroup writes lo = a - trunc_tf32(a) next to it in shared
+// memory.  (A first version with operands pre-split in HBM was L2-bound at 57 % tensor-pipe activity:
+// profiles/r01_summary.md.)
 //   warp 0       TMA producer        (raw tiles, 24 KB per stage)
-//   warp 1       MMA issuer          (lo*hi, hi*lo, hi*hi; accumulators in TMEM, chunked as in variant 1)
+//   warp 1       MMA issuer          (lo*hi, hi*lo, hi*hi; accumulators in TMEM, one fresh accumulator per 128-sample chunk)
 //   warps 4..7   transform           (raw -> lo, element-wise in the swizzled layout; fence.proxy.async)
-//   warps 8..15  epilogue            (running sums in registers)
+//   warps 8..15  epilogue            (running sums in registers, write-back through the TMA)
 // Register budget is rebalanced with setmaxnreg: producer/MMA/transform warpgroups give registers back,
 // the two epilogue warpgroups take them (128 running sums + a 32-value TMEM fragment per thread).
 // =====================================================================================================
@@ -382,7 +207,8 @@ __device__ __forceinline__ float rna_tf32(float x)
 }
 
 __global__ void __launch_bounds__(T2_THREADS, 1)
-syrk_tc2_kernel(const __grid_constant__ CUtensorMap map_raw, const __grid_constant__ CUtensorMap map_c, const TcArgs a)
+syrk_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_c,
+                const TcArgs a)
 {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -402,7 +228,8 @@ syrk_tc2_kernel(const __grid_constant__ CUtensorMap map_raw, const __grid_consta
         for (int s = 0; s < STAGES; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&lo_ready[s], 128); mbar_init(&empty_bar[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_raw) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
         if (a.tma_c) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c) : "memory");
     }
     if (warp == 1) {
@@ -430,9 +257,9 @@ syrk_tc2_kernel(const __grid_constant__ CUtensorMap map_raw, const __grid_consta
                         unsigned char* sb = sa + OPER_BYTES_A;
                         const int k0 = kb * BK;
 #pragma unroll
-                        for (int cb = 0; cb < A_BLOCKS; ++cb) tma_load_2d(sa + cb * BOX_BYTES, &map_raw, &raw_full[stage], i0 + cb * BOX_COLS, k0);
+                        for (int cb = 0; cb < A_BLOCKS; ++cb) tma_load_2d(sa + cb * BOX_BYTES, &map_a, &raw_full[stage], i0 + cb * BOX_COLS, k0);
 #pragma unroll
-                        for (int cb = 0; cb < B_BLOCKS; ++cb) tma_load_2d(sb + cb * BOX_BYTES, &map_raw, &raw_full[stage], j0 + cb * BOX_COLS, k0);
+                        for (int cb = 0; cb < B_BLOCKS; ++cb) tma_load_2d(sb + cb * BOX_BYTES, &map_b, &raw_full[stage], j0 + cb * BOX_COLS, k0);
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -632,31 +459,6 @@ syrk_tc2_kernel(const __grid_constant__ CUtensorMap map_raw, const __grid_consta
     }
 }
 
-// hi = rna_tf32(s), lo = rna_tf32(s - hi); columns [NJ, ldw) are zero-filled
-__global__ void split_tf32_kernel(const float* __restrict__ S, long long lds, int K, int NJ,
-                                  float* __restrict__ hi, float* __restrict__ lo, long long ldw)
-{
-    const long long total = (long long)K * (ldw / 4);
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-        const long long k = idx / (ldw / 4);
-        const int c = (int)(idx - k * (ldw / 4)) * 4;
-        float v[4], h[4], l[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) v[e] = (c + e < NJ) ? S[k * lds + c + e] : 0.f;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            uint32_t hb, lb;
-            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v[e]));
-            h[e] = __uint_as_float(hb);
-            const float d = __fsub_rn(v[e], h[e]);
-            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(d));
-            l[e] = __uint_as_float(lb);
-        }
-        *reinterpret_cast<float4*>(hi + k * ldw + c) = make_float4(h[0], h[1], h[2], h[3]);
-        *reinterpret_cast<float4*>(lo + k * ldw + c) = make_float4(l[0], l[1], l[2], l[3]);
-    }
-}
-
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -688,303 +490,6 @@ int make_map(sd_ctx* ctx, CUtensorMap* map, const float* base, int64_t ld, int r
     return SD_OK;
 }
 
-#ifdef SD_EXPERIMENTAL_2CTA
-// =====================================================================================================
-// DRAFT, NOT BUILT INTO THE PRODUCT AND NOT YET RUN ON HARDWARE (tools/build_experimental.sh only compiles it):
-// variant 3 = the in-kernel-split SYRK as a CTA PAIR (cta_group::2), the next step named in DESIGN.md section 8.
-//
-// Why: variant 2 moves 144 KB per 16-sample stage through one SM's shared memory (1125 clk at 128 B/clk) while its six
-// MMAs need ~800 clk.  In a CTA pair the 256 x 256 output tile is split by rows (each CTA keeps 128 x 256 of it in its
-// own TMEM, exactly as today) and the 256-column operand is split by columns: every CTA stages its own 128-column "A"
-// operand and ONE HALF of the "B" operand, the tensor cores of the pair read both halves.  Per SM and stage:
-// 16 KB TMA write + 16 KB transform read + 16 KB lo write + 6 x 8 KB operand fetch = 96 KB = 750 clk < 800 clk of MMA.
-//
-// Barrier topology (same shared-memory offsets in both CTAs; rank 0 = leader, the only MMA issuer):
-//   raw_full[s]   local   TMA bytes of this CTA's 16 KB landed                        -> local transform warps
-//   xf_done[s]    local   this CTA's 128 transform threads wrote lo                    -> local relay lane (warp 2)
-//   lo_ready[s]   LEADER  one arrive per CTA (relay lane; the peer's arrive is remote)  -> MMA issuer
-//   empty[s]      both    tcgen05.commit ... multicast::cluster 0b11: MMAs retired      -> local TMA producer
-//   tmem_full[b]  both    commit multicast                                             -> local epilogue warps
-//   tmem_empty[b] LEADER  8 epilogue warps of EACH CTA (peer: remote arrive)            -> MMA issuer
-// Open points to check on hardware before trusting it: (1) both CTAs issue tcgen05.alloc.cta_group::2 (as the guide's
-// allocator does) and receive the same column base; (2) the N split of an MN-major B operand follows the same
-// descriptor in both CTAs; (3) proxy fencing of the peer's generic-proxy lo writes towards the leader's tensor core
-// (fence.proxy.async + release.cluster arrive below); (4) cluster launch with 226 KB of dynamic shared memory per CTA.
-// =====================================================================================================
-constexpr int P_STAGES = 6;
-constexpr int P_RAW_BYTES = OPER_BYTES_A + OPER_BYTES_A;          // own A (128 cols) + half of B (128 cols): 16 KB
-constexpr int P_STAGE_BYTES = 2 * P_RAW_BYTES;                    // raw + lo: 32 KB
-constexpr int P_SMEM_BYTES = P_STAGES * P_STAGE_BYTES + 1024 /*align*/ + 1024 /*barriers*/ + EPI_WARPS * CBOX_BYTES;
-constexpr uint32_t kInstrDesc2 = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((256u >> 3) << 17) | ((256u >> 4) << 24);
-
-__device__ __forceinline__ uint32_t cluster_ctarank()
-{
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all()
-{
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster
-__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank)
-{
-    uint32_t raddr;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(bar)), "r"(rank));
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity)
-{
-    const long long t0 = clock64();
-    for (;;) {
-        uint32_t ok;
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-        if (ok) return;
-        if (clock64() - t0 > 8000000000LL) __trap();
-    }
-}
-__device__ __forceinline__ void tcgen05_commit_pair(uint64_t* bar)
-{
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
-}
-__device__ __forceinline__ void tcgen05_mma_tf32_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-
-// tiles: (ti, tj) in units of 256 x 256; a.tiles / a.num_tiles as for variant 2; gridDim.x is even, cluster = CTA pair
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
-syrk_tc3_pair_kernel(const __grid_constant__ CUtensorMap map_raw, const __grid_constant__ CUtensorMap map_c, const TcArgs a)
-{
-    extern __shared__ unsigned char smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P_STAGES * P_STAGE_BYTES);
-    uint64_t* raw_full = bars;                        // [P_STAGES]
-    uint64_t* xf_done = bars + P_STAGES;              // [P_STAGES]
-    uint64_t* lo_ready = bars + 2 * P_STAGES;         // [P_STAGES]  (used in the leader)
-    uint64_t* empty_bar = bars + 3 * P_STAGES;        // [P_STAGES]
-    uint64_t* tmem_full = bars + 4 * P_STAGES;        // [2]
-    uint64_t* tmem_empty = bars + 4 * P_STAGES + 2;   // [2]        (used in the leader)
-    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 4 * P_STAGES + 4);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t rank = cluster_ctarank();
-    const bool leader = rank == 0;
-    const int num_k = (a.K + BK - 1) / BK;
-    const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
-
-    if (warp == 0 && lane == 0) {
-        for (int s = 0; s < P_STAGES; ++s) {
-            mbar_init(&raw_full[s], 1); mbar_init(&xf_done[s], 128); mbar_init(&lo_ready[s], 2); mbar_init(&empty_bar[s], 1);
-        }
-        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 2 * EPI_WARPS); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_raw) : "memory");
-        if (a.tma_c) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c) : "memory");
-    }
-    cluster_sync_all();                                // barrier inits visible to the peer before any remote arrive
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "r"(TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-    }
-    tcgen05_fence_before();
-    cluster_sync_all();
-    tcgen05_fence_after();
-    const uint32_t tmem_base = *tmem_base_slot;
-
-    if (warp < 4) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;" ::: "memory");
-        if (warp == 0) {
-            // ===================== TMA producer (each CTA: its own A columns + its half of B) =====================
-            if (elect_one_sync()) {
-                uint32_t stage = 0, phase = 0;
-                for (int t = pair; t < a.num_tiles; t += num_pairs) {
-                    const int2 tile = a.tiles[t];
-                    const int i0 = tile.x * 256 + (int)rank * 128, j0 = tile.y * 256 + (int)rank * 128;
-                    for (int kb = 0; kb < num_k; ++kb) {
-                        mbar_wait(&empty_bar[stage], phase ^ 1);
-                        mbar_arrive_expect_tx(&raw_full[stage], P_RAW_BYTES);
-                        unsigned char* sa = smem + stage * P_STAGE_BYTES;
-                        unsigned char* sb = sa + OPER_BYTES_A;
-                        const int k0 = kb * BK;
-#pragma unroll
-                        for (int cb = 0; cb < A_BLOCKS; ++cb) tma_load_2d(sa + cb * BOX_BYTES, &map_raw, &raw_full[stage], i0 + cb * BOX_COLS, k0);
-#pragma unroll
-                        for (int cb = 0; cb < A_BLOCKS; ++cb) tma_load_2d(sb + cb * BOX_BYTES, &map_raw, &raw_full[stage], j0 + cb * BOX_COLS, k0);
-                        if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
-                    }
-                }
-            }
-        } else if (warp == 1 && leader) {
-            // ===================== MMA issuer (leader CTA only) =====================
-            uint32_t stage = 0, phase = 0, buf = 0, buf_phase = 0;
-            for (int t = pair; t < a.num_tiles; t += num_pairs) {
-                for (int kb = 0; kb < num_k; ++kb) {
-                    const bool chunk_first = (kb % KC_STAGES) == 0;
-                    const bool chunk_last = (kb % KC_STAGES) == KC_STAGES - 1 || kb == num_k - 1;
-                    if (chunk_first) {
-                        mbar_wait_cluster(&tmem_empty[buf], buf_phase ^ 1);     // both CTAs' epilogues drained this accumulator
-                        tcgen05_fence_after();
-                    }
-                    const uint32_t tmem_d = tmem_base + buf * BN;
-                    mbar_wait_cluster(&lo_ready[stage], phase);                  // both CTAs' raw tiles landed and were split
-                    tcgen05_fence_after();
-                    if (elect_one_sync()) {
-                        const uint32_t sa_hi = smem_u32(smem + stage * P_STAGE_BYTES);
-                        const uint32_t sb_hi = sa_hi + OPER_BYTES_A;
-                        const uint32_t sa_lo = sa_hi + P_RAW_BYTES;
-                        const uint32_t sb_lo = sa_lo + OPER_BYTES_A;
-#pragma unroll
-                        for (int ks = 0; ks < BK / 8; ++ks) {
-                            const uint32_t koff = ks * 8 * 128;
-                            const uint32_t first = (chunk_first && ks == 0) ? 0u : 1u;
-                            tcgen05_mma_tf32_pair(tmem_d, make_desc(sa_lo + koff), make_desc(sb_hi + koff), kInstrDesc2, first);
-                            tcgen05_mma_tf32_pair(tmem_d, make_desc(sa_hi + koff), make_desc(sb_lo + koff), kInstrDesc2, 1u);
-                            tcgen05_mma_tf32_pair(tmem_d, make_desc(sa_hi + koff), make_desc(sb_hi + koff), kInstrDesc2, 1u);
-                        }
-                        tcgen05_commit_pair(&empty_bar[stage]);                  // frees the slot in BOTH CTAs
-                        if (chunk_last) tcgen05_commit_pair(&tmem_full[buf]);    // wakes BOTH epilogues
-                    }
-                    __syncwarp();
-                    if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
-                    if (chunk_last) { if (++buf == 2) { buf = 0; buf_phase ^= 1; } }
-                }
-            }
-        } else if (warp == 2) {
-            // ===================== relay: "this CTA's lo tile is complete" -> leader =====================
-            if (elect_one_sync()) {
-                uint32_t stage = 0, phase = 0;
-                for (int t = pair; t < a.num_tiles; t += num_pairs)
-                    for (int kb = 0; kb < num_k; ++kb) {
-                        mbar_wait(&xf_done[stage], phase);
-                        asm volatile("fence.proxy.async;" ::: "memory");
-                        mbar_arrive_remote(&lo_ready[stage], 0);
-                        if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
-                    }
-            }
-        }
-    } else if (warp < 8) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 72;" ::: "memory");
-        // ===================== transform (as variant 2, on this CTA's 16 KB) =====================
-        const int tt = threadIdx.x - 128;
-        uint32_t stage = 0, phase = 0;
-        for (int t = pair; t < a.num_tiles; t += num_pairs) {
-            for (int kb = 0; kb < num_k; ++kb) {
-                mbar_wait(&raw_full[stage], phase);
-                const uint32_t raw = smem_u32(smem + stage * P_STAGE_BYTES) + tt * 16;
-                const uint32_t lo = raw + P_RAW_BYTES;
-#pragma unroll 4
-                for (int i = 0; i < P_RAW_BYTES / 16 / 128; ++i) {
-                    const float4 v = lds128(raw + i * 2048);
-                    float4 l;
-                    if (a.unbiased) {
-                        float4 h;
-                        h.x = rna_tf32(v.x); h.y = rna_tf32(v.y); h.z = rna_tf32(v.z); h.w = rna_tf32(v.w);
-                        l.x = rna_tf32(v.x - h.x); l.y = rna_tf32(v.y - h.y); l.z = rna_tf32(v.z - h.z); l.w = rna_tf32(v.w - h.w);
-                        sts128(raw + i * 2048, h);
-                    } else {
-                        l.x = rna_tf32(v.x - trunc_tf32(v.x)); l.y = rna_tf32(v.y - trunc_tf32(v.y));
-                        l.z = rna_tf32(v.z - trunc_tf32(v.z)); l.w = rna_tf32(v.w - trunc_tf32(v.w));
-                    }
-                    sts128(lo + i * 2048, l);
-                }
-                asm volatile("fence.proxy.async;" ::: "memory");
-                mbar_arrive(&xf_done[stage]);
-                if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
-            }
-        }
-    } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 176;" ::: "memory");
-        // ===================== epilogue (as variant 2; rows of this CTA's half of the 256 x 256 tile) =====================
-        const int q = warp & 3;
-        const int half = (warp - 8) >> 2;
-        uint32_t buf = 0, buf_phase = 0;
-        const int num_chunks = (num_k + KC_STAGES - 1) / KC_STAGES;
-        for (int t = pair; t < a.num_tiles; t += num_pairs) {
-            const int2 tile = a.tiles[t];
-            const int i = tile.x * 256 + (int)rank * 128 + q * 32 + lane;
-            const int j0 = tile.y * 256 + half * 128;
-            float acc[128];
-#pragma unroll
-            for (int v = 0; v < 128; ++v) acc[v] = 0.f;
-            for (int c = 0; c < num_chunks; ++c) {
-                mbar_wait(&tmem_full[buf], buf_phase);
-                tcgen05_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + half * 128;
-#pragma unroll
-                for (int c0 = 0; c0 < 128; c0 += 32) {
-                    uint32_t r[32];
-                    tmem_ld_32x32b_x32(taddr + c0, r);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int v = 0; v < 32; ++v) acc[c0 + v] = __fadd_rn(acc[c0 + v], __uint_as_float(r[v]));
-                }
-                tcgen05_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_remote(&tmem_empty[buf], 0);
-                if (++buf == 2) { buf = 0; buf_phase ^= 1; }
-            }
-            if (a.tma_c) {
-                unsigned char* box = smem + P_STAGES * P_STAGE_BYTES + 1024 + (warp - 8) * CBOX_BYTES;
-                const uint32_t box_u32 = smem_u32(box);
-#pragma unroll
-                for (int c0 = 0; c0 < 128; c0 += 32) {
-                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                    __syncwarp();
-#pragma unroll
-                    for (int v = 0; v < 8; ++v) {
-                        const float4 o = make_float4(a.alpha * acc[c0 + 4 * v + 0], a.alpha * acc[c0 + 4 * v + 1],
-                                                     a.alpha * acc[c0 + 4 * v + 2], a.alpha * acc[c0 + 4 * v + 3]);
-                        sts128(box_u32 + lane * 128 + ((v ^ (lane & 7)) << 4), o);
-                    }
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) {
-                        const int cx = j0 + c0, cy = tile.x * 256 + (int)rank * 128 + q * 32;
-                        if (a.tma_c == 2)
-                            asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2}], [%3];"
-                                         ::"l"(&map_c), "r"(cx), "r"(cy), "r"(box_u32) : "memory");
-                        else
-                            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];"
-                                         ::"l"(&map_c), "r"(cx), "r"(cy), "r"(box_u32) : "memory");
-                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                    }
-                }
-            } else if (i < a.MI) {
-                float* crow = a.C + (long long)i * a.ldc;
-#pragma unroll 4
-                for (int v = 0; v < 128; ++v) {
-                    if (j0 + v < a.NJ) {
-                        float o = a.alpha * acc[v];
-                        if (a.beta != 0.f) o = fmaf(a.beta, crow[j0 + v], o);
-                        crow[j0 + v] = o;
-                    }
-                }
-            }
-        }
-    }
-
-    if (warp >= 8 && lane == 0 && a.tma_c) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-    tcgen05_fence_before();
-    cluster_sync_all();                                // both CTAs are done with the pair's tensor memory
-    if (warp == 1) {
-        tcgen05_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
-    }
-}
-#endif  // SD_EXPERIMENTAL_2CTA
-
 // C (rows x cols, pitch ld) as 32 x 32 boxes, 128B-swizzled in shared memory
 int make_map_c(sd_ctx* ctx, CUtensorMap* map, float* base, int64_t ld, int rows, int cols)
 {
@@ -1009,43 +514,36 @@ bool sd_syrk_tc_supported(const float* d_S, int64_t lds, int K, int MI, int NJ, 
     return K >= 1 && (reinterpret_cast<uintptr_t>(d_S) & 15) == 0 && (lds % 4) == 0;
 }
 
-int sd_syrk_tc(sd_ctx* ctx, const float* d_S, int64_t lds, int K, int MI, int NJ, float* d_C, int64_t ldc,
-               float alpha, float beta, int passes, bool unbiased_split)
+// C[i,j] = beta*C[i,j] + alpha * sum_{k<K} SA[k,i] * SB[k,j],  i < MI, j < NJ.   SA: K x MI (lda), SB: K x NJ (ldb), both row-major,
+// i.e. both operands MN-major.  upper_only keeps the tiles that intersect j >= i (SYRK: SA == SB).  `rows` (optional) keeps the
+// tiles whose C rows belong to this rank's block rows (distributed trailing update).  C may alias SB when every CTA's column
+// range of SB is read completely before its tile is written: true for MI <= 128 (one tile row; each tile's operand columns are
+// its own output columns) -- the in-place block-row solve of the Cholesky relies on that.
+int sd_gemm_tn_tc(sd_ctx* ctx, const float* d_SA, int64_t lda, const float* d_SB, int64_t ldb, int K, int MI, int NJ,
+                  float* d_C, int64_t ldc, float alpha, float beta, int passes, bool unbiased_split, bool upper_only,
+                  const sd_row_filter* rows)
 {
     if (MI <= 0 || NJ <= 0 || K <= 0) return SD_OK;
     SD_REQUIRE(ctx, passes == 1 || passes == 3, "passes must be 1 or 3");
-    const float* hi = d_S;
-    const float* lo = d_S;
-    int64_t ldw = lds;
-    const bool variant2 = ctx->tc_variant != 1;          // default: raw tiles + in-kernel split
-    if (passes == 3 && !variant2) {
-        ldw = ((int64_t)NJ + 3) / 4 * 4;
-        float* whi = (float*)sd_workspace(ctx, SD_WS_SPLIT_HI, (size_t)K * ldw * sizeof(float));
-        float* wlo = (float*)sd_workspace(ctx, SD_WS_SPLIT_LO, (size_t)K * ldw * sizeof(float));
-        if (!whi || !wlo) return SD_ERR_CUDA;
-        const int64_t work = (int64_t)K * (ldw / 4);
-        const int blocks = sd_div_up(work, 256) > 8 * ctx->sm_count ? 8 * ctx->sm_count : sd_div_up(work, 256);
-        split_tf32_kernel<<<blocks, 256, 0, ctx->stream>>>(d_S, lds, K, NJ, whi, wlo, ldw);
-        SD_LAUNCH_CHECK(ctx, "split_tf32_kernel");
-        hi = whi;
-        lo = wlo;
-    }
-    CUtensorMap map_hi, map_lo;
-    int rc = make_map(ctx, &map_hi, hi, ldw, K, NJ);
+    CUtensorMap map_a, map_b;
+    int rc = make_map(ctx, &map_a, d_SA, lda, K, MI);
     if (rc) return rc;
-    rc = make_map(ctx, &map_lo, lo, ldw, K, NJ);
+    rc = make_map(ctx, &map_b, d_SB, ldb, K, NJ);
     if (rc) return rc;
 
     // tile list, ordered by super-tiles so that concurrently running tiles share operand columns in L2
     const int TI = sd_div_up(MI, BM), TJ = sd_div_up(NJ, BN);
-    std::vector<int2> tiles;
-    tiles.reserve((size_t)TI * TJ / 2 + TI + TJ);
+    std::vector<int2>& tiles = ctx->tile_scratch;
+    tiles.clear();
     for (int si = 0; si < TI; si += GI)
         for (int sj = 0; sj < TJ; sj += GJ)
-            for (int ti = si; ti < si + GI && ti < TI; ++ti)
+            for (int ti = si; ti < si + GI && ti < TI; ++ti) {
+                if (rows && rows->nranks > 1 && ((rows->first_row + (int64_t)ti * BM) / rows->block) % rows->nranks != rows->rank) continue;
                 for (int tj = sj; tj < sj + GJ && tj < TJ; ++tj)
-                    if (tj * BN + BN - 1 >= ti * BM) tiles.push_back(make_int2(ti, tj));
+                    if (!upper_only || tj * BN + BN - 1 >= ti * BM) tiles.push_back(make_int2(ti, tj));
+            }
     if (tiles.empty()) return SD_OK;
+    // the list travels through a small pinned ring so that the copy never blocks the host behind running kernels
     int2* d_tiles = (int2*)sd_workspace(ctx, SD_WS_DIAGINV, tiles.size() * sizeof(int2));
     if (!d_tiles) return SD_ERR_CUDA;
     SD_CUDA(ctx, cudaMemcpyAsync(d_tiles, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
@@ -1053,75 +551,25 @@ int sd_syrk_tc(sd_ctx* ctx, const float* d_S, int64_t lds, int K, int MI, int NJ
     TcArgs a;
     a.K = K; a.MI = MI; a.NJ = NJ; a.C = d_C; a.ldc = ldc; a.alpha = alpha; a.beta = beta; a.passes = passes;
     a.unbiased = (ctx->gram_mode == 3 || unbiased_split) ? 1 : 0;
-    a.tma_c = 0;
     a.tiles = d_tiles; a.num_tiles = (int)tiles.size();
     const int sms = ctx->sm_count - ctx->syrk_sm_reserve > 0 ? ctx->sm_count - ctx->syrk_sm_reserve : 1;
     const int grid = a.num_tiles < sms ? a.num_tiles : sms;
-    if (variant2) {
-        // C goes back through the TMA when it can be described by a tensor map (16-byte aligned base and pitch)
-        CUtensorMap map_c = map_hi;
-        a.tma_c = 0;
-        if ((beta == 0.f || beta == 1.f) && (ldc % 4) == 0 && (reinterpret_cast<uintptr_t>(d_C) & 15) == 0 && !getenv("SD_B200_NO_TMA_C")) {
-            rc = make_map_c(ctx, &map_c, d_C, ldc, MI, NJ);
-            if (rc) return rc;
-            a.tma_c = beta == 1.f ? 2 : 1;
-        }
-        SD_CUDA(ctx, cudaFuncSetAttribute(syrk_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
-        syrk_tc2_kernel<<<grid, T2_THREADS, SMEM2_BYTES, ctx->stream>>>(map_hi, map_c, a);
-        SD_LAUNCH_CHECK(ctx, "syrk_tc2_kernel");
-    } else {
-        SD_CUDA(ctx, cudaFuncSetAttribute(syrk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        syrk_tc_kernel<<<grid, TC_THREADS, SMEM_BYTES, ctx->stream>>>(map_hi, map_lo, a);
-        SD_LAUNCH_CHECK(ctx, "syrk_tc_kernel");
-    }
-    return SD_OK;
-}
-
-#ifdef SD_EXPERIMENTAL_2CTA
-// DRAFT host side of the CTA-pair variant (see the kernel's header comment): 256 x 256 tiles, one CTA pair per tile,
-// cluster launch.  Not reachable from the C ABI.
-int sd_syrk_tc_pair_draft(sd_ctx* ctx, const float* d_S, int64_t lds, int K, int MI, int NJ, float* d_C, int64_t ldc,
-                          float alpha, float beta, bool unbiased_split)
-{
-    if (MI <= 0 || NJ <= 0 || K <= 0) return SD_OK;
-    CUtensorMap map_raw, map_c;
-    int rc = make_map(ctx, &map_raw, d_S, lds, K, NJ);
-    if (rc) return rc;
-    const int TI = sd_div_up(MI, 256), TJ = sd_div_up(NJ, 256);
-    std::vector<int2> tiles;
-    for (int si = 0; si < TI; si += 6)
-        for (int sj = 0; sj < TJ; sj += 12)
-            for (int ti = si; ti < si + 6 && ti < TI; ++ti)
-                for (int tj = sj; tj < sj + 12 && tj < TJ; ++tj)
-                    if (tj * 256 + 255 >= ti * 256) tiles.push_back(make_int2(ti, tj));
-    if (tiles.empty()) return SD_OK;
-    int2* d_tiles = (int2*)sd_workspace(ctx, SD_WS_DIAGINV, tiles.size() * sizeof(int2));
-    if (!d_tiles) return SD_ERR_CUDA;
-    SD_CUDA(ctx, cudaMemcpyAsync(d_tiles, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
-    TcArgs a;
-    a.K = K; a.MI = MI; a.NJ = NJ; a.C = d_C; a.ldc = ldc; a.alpha = alpha; a.beta = beta; a.passes = 3;
-    a.unbiased = unbiased_split ? 1 : 0;
-    a.tiles = d_tiles; a.num_tiles = (int)tiles.size();
+    // C goes back through the TMA when it can be described by a tensor map (16-byte aligned base and pitch)
+    CUtensorMap map_c = map_b;
     a.tma_c = 0;
-    map_c = map_raw;
-    if ((beta == 0.f || beta == 1.f) && (ldc % 4) == 0 && (reinterpret_cast<uintptr_t>(d_C) & 15) == 0) {
+    if ((beta == 0.f || beta == 1.f) && (ldc % 4) == 0 && (reinterpret_cast<uintptr_t>(d_C) & 15) == 0 && !getenv("SD_B200_NO_TMA_C")) {
         rc = make_map_c(ctx, &map_c, d_C, ldc, MI, NJ);
         if (rc) return rc;
         a.tma_c = beta == 1.f ? 2 : 1;
     }
-    const int pairs = a.num_tiles < ctx->sm_count / 2 ? a.num_tiles : ctx->sm_count / 2;
-    SD_CUDA(ctx, cudaFuncSetAttribute(syrk_tc3_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES));
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(2 * pairs);
-    cfg.blockDim = dim3(T2_THREADS);
-    cfg.dynamicSmemBytes = P_SMEM_BYTES;
-    cfg.stream = ctx->stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    SD_CUDA(ctx, cudaLaunchKernelEx(&cfg, syrk_tc3_pair_kernel, map_raw, map_c, a));
+    SD_CUDA(ctx, cudaFuncSetAttribute(syrk_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+    syrk_tc2_kernel<<<grid, T2_THREADS, SMEM2_BYTES, ctx->stream>>>(map_a, map_b, map_c, a);
+    SD_LAUNCH_CHECK(ctx, "syrk_tc2_kernel");
     return SD_OK;
 }
-#endif
 
+int sd_syrk_tc(sd_ctx* ctx, const float* d_S, int64_t lds, int K, int MI, int NJ, float* d_C, int64_t ldc,
+               float alpha, float beta, int passes, bool unbiased_split, const sd_row_filter* rows)
+{
+    return sd_gemm_tn_tc(ctx, d_S, lds, d_S, lds, K, MI, NJ, d_C, ldc, alpha, beta, passes, unbiased_split, true, rows);
+}

@@ -293,7 +293,9 @@ __global__ void __launch_bounds__(kHogThreads) hog_patch_kernel(const HogArgs a)
     {
         const int x0 = cx - half, y0 = cy - half;
         const int W = a.width, H = a.height;
-        const bool resident = x0 >= rx && y0 >= ry && x0 + P <= rx + rw && y0 + P <= ry + rh;
+        // the fast paths need the window inside the resident region AND inside the frame (an ROI is rounded up to 16-byte
+        // rows and may include row padding right of the frame: those bytes are zero padding, not pixels)
+        const bool resident = x0 >= rx && y0 >= ry && x0 + P <= rx + rw && y0 + P <= ry + rh && x0 >= 0 && y0 >= 0 && x0 + P <= W && y0 + P <= H;
         const uintptr_t align_bits = reinterpret_cast<uintptr_t>(img) | (uintptr_t)rs;
         const bool vec16 = resident && (align_bits & 15) == 0;      // rows can be fetched as aligned 16-byte vectors
         const bool words = resident && (align_bits & 3) == 0;
@@ -648,7 +650,7 @@ int launch_hog(sd_ctx* ctx, const sd_image_batch* images, const int32_t* d_image
     a.A = d_A; a.ld = ld;
     if (d_A) SD_REQUIRE(ctx, ld >= (int64_t)L * a.nc * a.nc * a.dd + 1, "ld < feature length");
     a.geometry = d_geometry; a.patches = d_patches; a.bins = d_bins;
-    a.status = reinterpret_cast<int*>(ctx->d_scratch);   // bit 0: empty patch, bit 1: bad image index
+    a.status = reinterpret_cast<int*>(ctx->d_scratch) + 1;   // the projection's own status word: bit 0 empty patch, bit 1 bad image index
 
     // orientation table for this K, built once per context (hog.c:195-204: host libm cos/sin, as the reference)
     if (!ctx->hog_lut[a.K]) {

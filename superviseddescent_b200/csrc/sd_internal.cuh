@@ -15,8 +15,18 @@
 #define SD_MAX_EYES 4
 #define SD_MAX_BINS 16   // undirected orientations K supported by the HOG kernel
 
-enum { SD_WS_GRAM_EXT = 0, SD_WS_SPLIT_HI, SD_WS_SPLIT_LO, SD_WS_FEATURES, SD_WS_SCRATCH, SD_WS_DIAGINV,
-       SD_WS_PARTIAL, SD_WS_GEOM, SD_WS_GEMM_PARTIAL, SD_WS_DIAGINV2, SD_WS_PANEL, SD_WS_COUNT };
+enum { SD_WS_GRAM_EXT = 0, SD_WS_FEATURES, SD_WS_SCRATCH, SD_WS_DIAGINV,
+       SD_WS_PARTIAL, SD_WS_GEOM, SD_WS_GEMM_PARTIAL, SD_WS_DIAGINV2, SD_WS_PANEL, SD_WS_BIAS, SD_WS_COUNT };
+
+// Block-row ownership of a distributed factorisation: global row r of the matrix belongs to rank (r / block) % nranks.
+// first_row = global row of the first row of the C sub-matrix a kernel is launched on.
+struct sd_row_filter {
+    int block;
+    int nranks, rank;
+    int64_t first_row;
+};
+
+struct sd_comm;   // sd_comm.cu
 
 struct sd_ctx {
     int device = 0;
@@ -27,10 +37,10 @@ struct sd_ctx {
     cudaEvent_t chain_ev[2] = {nullptr, nullptr};
     int syrk_sm_reserve = 0;              // SMs the persistent SYRK leaves free (1 while a look-ahead chain runs beside it)
     std::string err;
+    std::vector<int2> tile_scratch;       // host side of the tensor-core tile lists
     int64_t launches = 0;
     int sm_count = 148;
     int gram_mode = 0;
-    int tc_variant = 2;            // tensor-core SYRK: 2 = raw tiles + in-kernel hi/lo split (default), 1 = operands pre-split in HBM
     bool disable_roi = false;      // sd_detect_batch_host: always upload whole frames
     int64_t roi_fallbacks = 0;     // faces repeated from the full frame because a patch left its ROI
     float timings[4] = {0, 0, 0, 0};
@@ -82,12 +92,30 @@ static inline int sd_div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b
 // passes the same choice for every piece of one rank-k update (mixing the two kernels inside one update was measured
 // to double the error of the solved weights).  unbiased_split: round the hi operand (gram mode 3) for this call.
 int sd_syrk_update(sd_ctx* ctx, const float* d_S, int64_t lds, int K, int MI, int NJ,
-                   float* d_C, int64_t ldc, float alpha, float beta, int path = 0, bool unbiased_split = false);
+                   float* d_C, int64_t ldc, float alpha, float beta, int path = 0, bool unbiased_split = false,
+                   const sd_row_filter* rows = nullptr);
 int sd_syrk_simt(sd_ctx* ctx, const float* d_S, int64_t lds, int K, int MI, int NJ,
                  float* d_C, int64_t ldc, float alpha, float beta);
 int sd_syrk_tc(sd_ctx* ctx, const float* d_S, int64_t lds, int K, int MI, int NJ,
-               float* d_C, int64_t ldc, float alpha, float beta, int passes, bool unbiased_split = false);
+               float* d_C, int64_t ldc, float alpha, float beta, int passes, bool unbiased_split = false,
+               const sd_row_filter* rows = nullptr);
+// C = beta*C + alpha * SA^T SB on the tensor cores (SA: K x MI, SB: K x NJ, row-major); see sd_gram_tc.cu
+int sd_gemm_tn_tc(sd_ctx* ctx, const float* d_SA, int64_t lda, const float* d_SB, int64_t ldb, int K, int MI, int NJ,
+                  float* d_C, int64_t ldc, float alpha, float beta, int passes, bool unbiased_split, bool upper_only,
+                  const sd_row_filter* rows = nullptr);
 bool sd_syrk_tc_supported(const float* d_S, int64_t lds, int K, int MI, int NJ, const float* d_C, int64_t ldc);
+
+int sd_check_hog_status(sd_ctx* ctx, const char* what);   // sd_api.cu: synchronises, reports and clears the projection's flags
+
+// multi-GPU helpers (sd_comm.cu); a null communicator is a single rank
+int sd_comm_rank_of(const sd_comm* c);
+int sd_comm_size_of(const sd_comm* c);
+int sd_comm_bcast(sd_ctx* ctx, sd_comm* c, float* d_buf, size_t count, int root, cudaStream_t stream);
+int sd_comm_group_start(sd_ctx* ctx);
+int sd_comm_group_end(sd_ctx* ctx);
+int sd_comm_allreduce_f64(sd_ctx* ctx, sd_comm* c, double* d_buf, size_t count, cudaStream_t stream);
+// true when sd_reduce_scatter_gram leaves the rows block-row-cyclic (large, 16-byte aligned systems); smaller ones are all-reduced
+bool sd_gram_is_scattered(int D, int64_t ldg, const float* d_G);
 
 // device-side normalisation factors, shared by the HOG and cascade kernels
 struct sd_eyes_dev {

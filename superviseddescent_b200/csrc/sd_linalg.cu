@@ -315,10 +315,14 @@ __global__ void subtract_kernel(float* __restrict__ A, long long lda, const floa
 // sum of squares of the full symmetric D x D matrix from its upper triangle, in double (cv::norm)
 // Rows are dealt round-robin to the blocks (balanced triangle), a block's 1024 threads stride along the row with
 // four independent loads in flight each; fixed grid and fixed order, so the sum is reproducible.
-__global__ void __launch_bounds__(1024) frob_upper_kernel(const float* __restrict__ G, long long ldg, int D, double* __restrict__ out)
+// own_block/nranks/rank: only the rows of this rank's block rows are summed (distributed solve; the partial sums are then
+// all-reduced).
+__global__ void __launch_bounds__(1024) frob_upper_kernel(const float* __restrict__ G, long long ldg, int D, double* __restrict__ out,
+                                                          int own_block, int nranks, int rank)
 {
     double s0 = 0.0, s1 = 0.0;
     for (int i = blockIdx.x; i < D; i += gridDim.x) {
+        if (nranks > 1 && (i / own_block) % nranks != rank) continue;
         const float* row = G + (long long)i * ldg;
         if (threadIdx.x == 0) { const double v = (double)row[i]; s0 -= 0.5 * v * v; }  // the diagonal counts once, everything is doubled below
         int j = i + threadIdx.x;
@@ -336,6 +340,16 @@ __global__ void __launch_bounds__(1024) frob_upper_kernel(const float* __restric
         __syncthreads();
     }
     if (threadIdx.x == 0) out[blockIdx.x] = red[0];
+}
+
+// partial[0] <- sum of the partials (one double per rank travels through the all-reduce of the distributed solve)
+__global__ void sum_partials_kernel(double* __restrict__ partial, int nparts)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double s = 0.0;
+        for (int i = 0; i < nparts; ++i) s += partial[i];
+        partial[0] = s;
+    }
 }
 
 // scal[0] <- lambda ; then the diagonal gets lambda (0 for the bias row if !regularise_last_row)
@@ -359,6 +373,71 @@ __global__ void add_diag_kernel(float* __restrict__ G, long long ldg, int D, con
     if (i >= D) return;
     const float lambda = (i == D - 1 && !regularise_last_row) ? 0.0f : scal[0];
     G[(long long)i * ldg + i] = __fadd_rn(G[(long long)i * ldg + i], lambda);
+}
+
+
+// ---- last column first --------------------------------------------------------------------------------------------------
+// The last column of the RCR feature matrix is the bias (all ones, adaptive_vlhog.hpp:182-183) and by default gets no lambda
+// (regressors.hpp:143-146).  Eliminated LAST -- where it sits -- its pivot is N - s^T (G_ww + lambda I)^-1 s: a difference of
+// two nearly equal numbers that costs fp32 three digits (the system's condition number is ~7e4 on real HOG features; the
+// reference's own float LU is 2e-3 off the float64 weights there, tests/test_gpu_train.py).  Eliminated FIRST its pivot is
+// the exact integer N, and what remains, G_ww - s s^T / N + lambda I, is the Gram matrix of the CENTRED features: condition
+// number ~4.  Same linear system, same solution, a better pivot order -- symmetric pivoting on the largest diagonal entry
+// would pick that column first as well.
+//   sv[0..D-2] = s (the bias column above the diagonal), sv[D-1] = pivot, sv[D..D+M) = the bias row of the right-hand sides
+__global__ void bias_extract_kernel(const float* __restrict__ G, long long ldg, int D, int M, double* __restrict__ sv,
+                                    int own_block, int nranks, int rank)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= D + M) return;
+    const int row = i < D ? i : D - 1;
+    const bool mine = nranks <= 1 || (row / own_block) % nranks == rank;       // others contribute zero to the all-reduce
+    double v = 0.0;
+    if (mine) v = (double)(i < D ? G[(long long)i * ldg + (D - 1)] : G[(long long)(D - 1) * ldg + i]);
+    sv[i] = v;
+}
+
+// rows i < D-1 (owned ones): G[i][j] -= s_i * t_j / pivot for j in [i, D-1) (t = s) and j in [D, D+M) (t = bias row of the
+// right-hand sides); column D-1 keeps s: it rides through the factorisation as one more right-hand side.
+__global__ void __launch_bounds__(256) bias_downdate_kernel(float* __restrict__ G, long long ldg, int D, int M,
+                                                            const double* __restrict__ sv, int own_block, int nranks, int rank)
+{
+    const double inv_p = 1.0 / sv[D - 1];
+    for (int i = blockIdx.x; i < D - 1; i += gridDim.x) {
+        if (nranks > 1 && (i / own_block) % nranks != rank) continue;
+        const double f = sv[i] * inv_p;
+        float* row = G + (long long)i * ldg;
+        for (int j = i + threadIdx.x; j < D + M; j += 256) {
+            if (j == D - 1) continue;
+            row[j] = (float)((double)row[j] - f * sv[j]);
+        }
+    }
+}
+
+// X[0..D-2] = w (columns 1..M of Xp; column 0 is the solve of the carried bias column), X[D-1] = (rb - s^T w) / pivot
+__global__ void __launch_bounds__(256) bias_finish_kernel(const float* __restrict__ Xp, int D, int M, const double* __restrict__ sv,
+                                                          float* __restrict__ X)
+{
+    const int c = blockIdx.x;
+    if (c < M) {
+        double acc = 0.0;
+        for (int i = threadIdx.x; i < D - 1; i += 256) acc += sv[i] * (double)Xp[(long long)i * (M + 1) + 1 + c];
+        __shared__ double red[256];
+        red[threadIdx.x] = acc;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
+            if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) X[(long long)(D - 1) * M + c] = (float)((sv[D + c] - red[0]) / sv[D - 1]);
+    } else {
+        const long long total = (long long)(D - 1) * M;
+        for (long long idx = (long long)(blockIdx.x - M) * 256 + threadIdx.x; idx < total; idx += (long long)(gridDim.x - M) * 256) {
+            const long long r = idx / M;
+            const int cc = (int)(idx - r * M);
+            X[idx] = Xp[r * (M + 1) + 1 + cc];
+        }
+    }
 }
 
 // ---- LU with partial pivoting, single CTA (regressors.hpp:224-225 for small systems) ---------------
@@ -929,8 +1008,17 @@ bool sd_syrk_is_big(int K, int64_t MI, int64_t NJ)
     return MI * NJ >= tc_min && K >= 64;
 }
 
-int cholesky_solve(sd_ctx* ctx, float* G, int64_t ldg, int D, int M, float* X)
+// comm (optional, more than one rank): DISTRIBUTED factorisation.  Block-row-cyclic ownership in units of one 256-row panel
+// (rank = panel % nranks): on entry every rank holds the summed rows of its own panels (sd_reduce_scatter_gram), the other rows
+// are undefined.  The owner factors its panel (chain + block-row solve), broadcasts the finished panel rows [P1;P2] (and the
+// inverses of the two diagonal blocks) over NVLink, and every rank applies the rank-256 update to the block rows it owns.  The
+// look-ahead is kept: the owner of panel p+1 updates that panel first and factors its diagonal blocks on the second stream while
+// its share of the trailing update runs.  At the end every rank holds all of U and Y, so the (cheap) back substitution runs
+// replicated and every rank ends up with the same X bit for bit.
+int cholesky_solve(sd_ctx* ctx, float* G, int64_t ldg, int D, int M, float* X, sd_comm* comm = nullptr)
 {
+    const int nranks = sd_comm_size_of(comm), me = sd_comm_rank_of(comm);
+    const bool dist = nranks > 1;
     int* status = reinterpret_cast<int*>(ctx->d_scratch);
     const int W_ = D + M;
     const int nblocks = sd_div_up(D, kCholNb);
@@ -982,29 +1070,48 @@ int cholesky_solve(sd_ctx* ctx, float* G, int64_t ldg, int D, int M, float* X)
         }
         return SD_OK;
     };
+    int rc = SD_OK;
     SD_CUDA(ctx, cudaEventRecord(ev_head, main_s));                   // G is ready (regulariser applied) for chain(0)
-    SD_CUDA(ctx, cudaStreamWaitEvent(chain_s, ev_head, 0));
-    int rc = launch_chain(0);
-    if (rc) return rc;
-    SD_CUDA(ctx, cudaEventRecord(ev_chain, chain_s));
+    if (me == 0) {
+        SD_CUDA(ctx, cudaStreamWaitEvent(chain_s, ev_head, 0));
+        rc = launch_chain(0);
+        if (rc) return rc;
+        SD_CUDA(ctx, cudaEventRecord(ev_chain, chain_s));
+    }
     for (int b = 0; b < nblocks; b += 2) {
         int j, nb1, nb2;
         panel_dims(b, j, nb1, nb2);
-        SD_CUDA(ctx, cudaStreamWaitEvent(main_s, ev_chain, 0));       // chain(p) done
+        const int owner = dist ? (b / 2) % nranks : me;
+        const int next_owner = dist ? (b / 2 + 1) % nranks : me;
         const int j3 = j + nb1 + nb2;                                 // first column right of the panel
         const int cols3 = W_ - j3;
-        if (cols3 <= 0) continue;
         float* W1 = inv + (size_t)b * 2 * PB * PB;
         float* row1 = G + (int64_t)j * ldg + j3;
-        rc = launch_trsm_apply(ctx, main_s, row1, ldg, nb1, cols3, W1, nullptr, 0, 0, nullptr, 0);                 // P1
-        if (rc) return rc;
-        if (nb2 > 0) {
-            float* W2 = inv + (size_t)(b + 1) * 2 * PB * PB;
-            float* row2 = G + (int64_t)(j + nb1) * ldg + j3;
-            const float* P1a = G + (int64_t)j * ldg + (j + nb1);
-            rc = launch_trsm_apply(ctx, main_s, row2, ldg, nb2, cols3, W2, P1a, ldg, nb1, row1, ldg);               // P2
-            if (rc) return rc;
+        if (me == owner) {
+            SD_CUDA(ctx, cudaStreamWaitEvent(main_s, ev_chain, 0));   // chain(p) done
+            if (cols3 > 0) {
+                rc = launch_trsm_apply(ctx, main_s, row1, ldg, nb1, cols3, W1, nullptr, 0, 0, nullptr, 0);             // P1
+                if (rc) return rc;
+                if (nb2 > 0) {
+                    float* W2 = inv + (size_t)(b + 1) * 2 * PB * PB;
+                    float* row2 = G + (int64_t)(j + nb1) * ldg + j3;
+                    const float* P1a = G + (int64_t)j * ldg + (j + nb1);
+                    rc = launch_trsm_apply(ctx, main_s, row2, ldg, nb2, cols3, W2, P1a, ldg, nb1, row1, ldg);           // P2
+                    if (rc) return rc;
+                }
+            }
         }
+        if (dist) {
+            // the finished panel rows, from the diagonal column of the first row to the end of the last row (one contiguous
+            // range of G), and U_jj^-1 / U_jj^-T of its diagonal blocks for the back substitution
+            rc = sd_comm_group_start(ctx);
+            if (rc) return rc;
+            rc = sd_comm_bcast(ctx, comm, G + (int64_t)j * ldg + j, (size_t)(nb1 + nb2) * ldg - j, owner, main_s);
+            if (!rc) rc = sd_comm_bcast(ctx, comm, W1, (size_t)(nb2 > 0 ? 2 : 1) * 2 * PB * PB, owner, main_s);
+            const int rc2 = sd_comm_group_end(ctx);
+            if (rc || rc2) return rc ? rc : rc2;
+        }
+        if (cols3 <= 0) continue;
         const int rest = D - j3;                                      // rows (= diagonal columns) below the panel
         if (rest <= 0) continue;
         const int kp = nb1 + nb2;                                     // rows of [P1;P2], contiguous in G
@@ -1015,16 +1122,21 @@ int cholesky_solve(sd_ctx* ctx, float* G, int64_t ldg, int D, int M, float* X)
         // scales [AtA|Atb] almost uniformly) but is amplified by the cancellation inside Schur complements
         static const bool upd_unbiased = getenv("SD_B200_UPDATE_BIASED") == nullptr;
         const int path = sd_syrk_is_big(kp, rest, cols3) ? 1 : 2;
-        rc = sd_syrk_update(ctx, row1, ldg, kp, head, cols3, C3, ldg, -1.0f, 1.0f, path, upd_unbiased);
-        if (rc) return rc;
-        SD_CUDA(ctx, cudaEventRecord(ev_head, main_s));
-        SD_CUDA(ctx, cudaStreamWaitEvent(chain_s, ev_head, 0));
-        rc = launch_chain(b + 2);
-        if (rc) return rc;
-        SD_CUDA(ctx, cudaEventRecord(ev_chain, chain_s));
+        if (me == next_owner) {
+            rc = sd_syrk_update(ctx, row1, ldg, kp, head, cols3, C3, ldg, -1.0f, 1.0f, path, upd_unbiased);
+            if (rc) return rc;
+            SD_CUDA(ctx, cudaEventRecord(ev_head, main_s));
+            SD_CUDA(ctx, cudaStreamWaitEvent(chain_s, ev_head, 0));
+            rc = launch_chain(b + 2);
+            if (rc) return rc;
+            SD_CUDA(ctx, cudaEventRecord(ev_chain, chain_s));
+        }
         if (rest > head) {
-            ctx->syrk_sm_reserve = lookahead ? 1 : 0;                 // leave one SM to the chain running beside it
-            rc = sd_syrk_update(ctx, row1 + head, ldg, kp, rest - head, cols3 - head, C3 + (int64_t)head * ldg + head, ldg, -1.0f, 1.0f, path, upd_unbiased);
+            sd_row_filter own;
+            own.block = 2 * kCholNb; own.nranks = nranks; own.rank = me; own.first_row = j3 + head;
+            ctx->syrk_sm_reserve = (lookahead && me == next_owner) ? 1 : 0;   // leave one SM to the chain running beside it
+            rc = sd_syrk_update(ctx, row1 + head, ldg, kp, rest - head, cols3 - head, C3 + (int64_t)head * ldg + head, ldg, -1.0f, 1.0f, path,
+                                upd_unbiased, dist ? &own : nullptr);
             ctx->syrk_sm_reserve = 0;
             if (rc) return rc;
         }
@@ -1058,8 +1170,6 @@ int check_status(sd_ctx* ctx, const char* what)
         SD_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch, 0, sizeof(int), ctx->stream));
         if (st & 8) return sd_fail(ctx, SD_ERR_NUMERIC, "%s: regularised AtA is not positive definite (increase lambda)", what);
         if (st & 4) return sd_fail(ctx, SD_ERR_NUMERIC, "%s: singular system (zero pivot)", what);
-        if (st & 2) return sd_fail(ctx, SD_ERR_INVALID, "%s: image index out of range", what);
-        if (st & 1) return sd_fail(ctx, SD_ERR_INVALID, "%s: empty HOG patch (inter-eye distance too small)", what);
     }
     return SD_OK;
 }
@@ -1102,11 +1212,12 @@ int sd_syrk_simt(sd_ctx* ctx, const float* d_S, int64_t lds, int K, int MI, int 
 }
 
 int sd_syrk_update(sd_ctx* ctx, const float* d_S, int64_t lds, int K, int MI, int NJ, float* d_C, int64_t ldc,
-                   float alpha, float beta, int path, bool unbiased_split)
+                   float alpha, float beta, int path, bool unbiased_split, const sd_row_filter* rows)
 {
     const bool want_tc = path == 1 || (path == 0 && sd_syrk_is_big(K, MI, NJ));
     if (ctx->gram_mode != 2 && path != 2 && want_tc && sd_syrk_tc_supported(d_S, lds, K, MI, NJ, d_C, ldc))
-        return sd_syrk_tc(ctx, d_S, lds, K, MI, NJ, d_C, ldc, alpha, beta, ctx->gram_mode == 1 ? 1 : 3, unbiased_split);
+        return sd_syrk_tc(ctx, d_S, lds, K, MI, NJ, d_C, ldc, alpha, beta, ctx->gram_mode == 1 ? 1 : 3, unbiased_split, rows);
+    // the SIMT kernel updates every row: rows of other ranks are never read before their owner's broadcast overwrites them
     return sd_syrk_simt(ctx, d_S, lds, K, MI, NJ, d_C, ldc, alpha, beta);
 }
 
@@ -1136,21 +1247,33 @@ int sd_gram(sd_ctx* ctx, const float* d_A, int64_t lda, const float* d_B, int64_
     return sd_syrk_update(ctx, S, lds, N, D, D + M, d_G, ldg, 1.0f, 0.0f);
 }
 
-int sd_solve_gram(sd_ctx* ctx, float* d_G, int64_t ldg, int D, int M, const sd_regulariser* reg, int n_train_global,
-                  float* d_X, float* lambda_out)
+static int solve_gram_impl(sd_ctx* ctx, sd_comm* comm, float* d_G, int64_t ldg, int D, int M, const sd_regulariser* reg,
+                           int n_train_global, float* d_X, float* lambda_out)
 {
     if (!ctx) return SD_ERR_INVALID;
     SD_REQUIRE(ctx, d_G && d_X && reg && D >= 1 && M >= 1 && ldg >= D + M, "bad argument");
     SD_REQUIRE(ctx, reg->type == 0 || reg->type == 1, "unknown regularisation type");
     SD_REQUIRE(ctx, n_train_global >= 1, "n_train_global must be >= 1");
+    // the distributed factorisation needs whole panels per rank; small systems were all-reduced and are solved replicated
+    const int nranks = sd_comm_size_of(comm);
+    const bool dist = nranks > 1 && sd_gram_is_scattered(D, ldg, d_G);
     float* scal = reinterpret_cast<float*>(ctx->d_scratch) + 16;
     double* partial = reinterpret_cast<double*>(reinterpret_cast<char*>(ctx->d_scratch) + 1024);   // up to 384 doubles
+    // errors belong to the call that caused them: HOG status bits raised earlier were reported by their own entry points
+    SD_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch, 0, sizeof(int), ctx->stream));
     SD_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
     int nparts = 0;
     if (reg->type == 1) {
         nparts = D < 296 ? D : 296;                                   // 2 x 148 SMs; at most 384 partials fit the scratch
-        frob_upper_kernel<<<nparts, 1024, 0, ctx->stream>>>(d_G, ldg, D, partial);
+        frob_upper_kernel<<<nparts, 1024, 0, ctx->stream>>>(d_G, ldg, D, partial, 2 * kCholNb, dist ? nranks : 1, sd_comm_rank_of(comm));
         SD_LAUNCH_CHECK(ctx, "frob_upper_kernel");
+        if (dist) {
+            sum_partials_kernel<<<1, 32, 0, ctx->stream>>>(partial, nparts);
+            SD_LAUNCH_CHECK(ctx, "sum_partials_kernel");
+            int rc = sd_comm_allreduce_f64(ctx, comm, partial, 1, ctx->stream);
+            if (rc) return rc;
+            nparts = 1;
+        }
     }
     lambda_kernel<<<1, 32, 0, ctx->stream>>>(partial, nparts, reg->type, reg->param, n_train_global, scal);
     SD_LAUNCH_CHECK(ctx, "lambda_kernel");
@@ -1166,8 +1289,24 @@ int sd_solve_gram(sd_ctx* ctx, float* d_G, int64_t ldg, int D, int M, const sd_r
         copy_block_kernel<<<blocks, 256, 0, ctx->stream>>>(d_G + D, ldg, D, M, d_X, M);
         SD_LAUNCH_CHECK(ctx, "copy_block_kernel");
     } else {
-        rc = cholesky_solve(ctx, d_G, ldg, D, M, d_X);
+        // last column first (see bias_extract_kernel), then the blocked Cholesky of the remaining (D-1) x (D-1) system with the
+        // bias column riding along as right-hand side 0
+        const int me = sd_comm_rank_of(comm), nr = dist ? nranks : 1;
+        double* sv = (double*)sd_workspace(ctx, SD_WS_BIAS, (size_t)(D + M) * sizeof(double) + (size_t)(D - 1) * (M + 1) * sizeof(float));
+        if (!sv) return SD_ERR_CUDA;
+        float* Xp = reinterpret_cast<float*>(sv + D + M);
+        bias_extract_kernel<<<sd_div_up(D + M, 256), 256, 0, ctx->stream>>>(d_G, ldg, D, M, sv, 2 * kCholNb, nr, me);
+        SD_LAUNCH_CHECK(ctx, "bias_extract_kernel");
+        if (dist) {
+            rc = sd_comm_allreduce_f64(ctx, comm, sv, (size_t)(D + M), ctx->stream);
+            if (rc) return rc;
+        }
+        bias_downdate_kernel<<<4 * ctx->sm_count, 256, 0, ctx->stream>>>(d_G, ldg, D, M, sv, 2 * kCholNb, nr, me);
+        SD_LAUNCH_CHECK(ctx, "bias_downdate_kernel");
+        rc = cholesky_solve(ctx, d_G, ldg, D - 1, M + 1, Xp, dist ? comm : nullptr);
         if (rc) return rc;
+        bias_finish_kernel<<<M + 2 * ctx->sm_count, 256, 0, ctx->stream>>>(Xp, D, M, sv, d_X);
+        SD_LAUNCH_CHECK(ctx, "bias_finish_kernel");
     }
     SD_CUDA(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
     if (lambda_out) {
@@ -1177,6 +1316,43 @@ int sd_solve_gram(sd_ctx* ctx, float* d_G, int64_t ldg, int D, int M, const sd_r
         *lambda_out = *h;
     }
     return check_status(ctx, "solve");
+}
+
+int sd_solve_gram(sd_ctx* ctx, float* d_G, int64_t ldg, int D, int M, const sd_regulariser* reg, int n_train_global,
+                  float* d_X, float* lambda_out)
+{
+    return solve_gram_impl(ctx, nullptr, d_G, ldg, D, M, reg, n_train_global, d_X, lambda_out);
+}
+
+int sd_solve_gram_dist(sd_ctx* ctx, sd_comm* comm, float* d_G, int64_t ldg, int D, int M, const sd_regulariser* reg,
+                       int n_train_global, float* d_X, float* lambda_out)
+{
+    if (!ctx) return SD_ERR_INVALID;
+    SD_REQUIRE(ctx, comm != nullptr, "no communicator");
+    return solve_gram_impl(ctx, comm, d_G, ldg, D, M, reg, n_train_global, d_X, lambda_out);
+}
+
+int sd_learn_dist(sd_ctx* ctx, sd_comm* comm, const float* d_A, int64_t lda, const float* d_B, int64_t ldb, int N_local, int D, int M,
+                  const sd_regulariser* reg, int n_train_global, int distributed_solve, float* d_X, float* lambda_out)
+{
+    if (!ctx) return SD_ERR_INVALID;
+    SD_REQUIRE(ctx, comm != nullptr && M >= 1 && N_local >= 0, "bad argument");
+    const int64_t ldg = ((int64_t)(D + M) + 3) / 4 * 4;
+    float* G = (float*)sd_workspace(ctx, SD_WS_SCRATCH, (size_t)D * ldg * sizeof(float));
+    if (!G) return SD_ERR_CUDA;
+    SD_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+    int rc;
+    if (N_local > 0) rc = sd_gram(ctx, d_A, lda, d_B, ldb, N_local, D, M, G, ldg);
+    else rc = sd_check_cuda(ctx, cudaMemsetAsync(G, 0, (size_t)D * ldg * sizeof(float), ctx->stream), "memset(G)");
+    if (rc) return rc;
+    if (distributed_solve) {
+        rc = sd_reduce_scatter_gram(ctx, comm, G, ldg, D, M);
+        if (rc) return rc;
+        return sd_solve_gram_dist(ctx, comm, G, ldg, D, M, reg, n_train_global, d_X, lambda_out);
+    }
+    rc = sd_allreduce_gram(ctx, comm, G, ldg, D, M);
+    if (rc) return rc;
+    return sd_solve_gram(ctx, G, ldg, D, M, reg, n_train_global, d_X, lambda_out);
 }
 
 int sd_learn(sd_ctx* ctx, const float* d_A, int64_t lda, const float* d_B, int64_t ldb, int N, int D, int M,

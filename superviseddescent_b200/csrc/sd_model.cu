@@ -8,6 +8,7 @@
 
 #include <cmath>
 #include <cstring>
+#include <exception>
 #include <fstream>
 #include <string>
 #include <vector>
@@ -69,6 +70,7 @@ struct Cursor {
         const int32_t type = get<int32_t>();
         (void)get<uint8_t>();                               // isContinuous: same bytes either way for a packed Mat
         if (!good || type != 5 /* CV_32FC1 */ || r < 0 || c < 0) { good = false; return false; }
+        if ((uint64_t)r * (uint64_t)c > (buf.size() - pos) / sizeof(float)) { good = false; return false; }   // corrupt header: do not allocate
         data.resize((size_t)r * c);
         return bytes(data.data(), data.size() * sizeof(float));
     }
@@ -307,10 +309,8 @@ int sd_normalised_landmark_errors(sd_ctx* ctx, const float* d_pred, int64_t ldp,
     return SD_OK;
 }
 
-int sd_model_load(sd_ctx* ctx, const char* path, sd_model** out)
+static int model_load_impl(sd_ctx* ctx, const char* path, sd_model** out)
 {
-    if (!ctx || !path || !out) return SD_ERR_INVALID;
-    *out = nullptr;
     std::ifstream f(path, std::ios::binary);
     if (!f) return sd_fail(ctx, SD_ERR_IO, "The given model file could not be opened: %s", path);   // model.hpp:199
     std::vector<unsigned char> buf((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
@@ -354,6 +354,19 @@ int sd_model_load(sd_ctx* ctx, const char* path, sd_model** out)
     if (rc) { sd_model_destroy(m); return rc; }
     *out = m;
     return SD_OK;
+}
+
+int sd_model_load(sd_ctx* ctx, const char* path, sd_model** out)
+{
+    if (!ctx || !path || !out) return SD_ERR_INVALID;
+    *out = nullptr;
+    try {                                                     // nothing may unwind through the C boundary
+        return model_load_impl(ctx, path, out);
+    } catch (const std::exception& e) {
+        return sd_fail(ctx, SD_ERR_IO, "could not read %s: %s", path, e.what());
+    } catch (...) {
+        return sd_fail(ctx, SD_ERR_IO, "could not read %s", path);
+    }
 }
 
 int sd_model_save(sd_ctx* ctx, const sd_model* m, const char* path)
@@ -466,7 +479,11 @@ int sd_detect_batch_device(sd_ctx* ctx, const sd_model* m, const sd_image_batch*
     if (!ctx) return SD_ERR_INVALID;
     SD_REQUIRE(ctx, m && images && d_x0 && d_landmarks && count >= 0, "bad argument");
     SD_REQUIRE(ctx, images->count >= count, "fewer images than faces");
-    return detect_device(ctx, m, images, d_x0, count, d_landmarks);
+    const int rc = detect_device(ctx, m, images, d_x0, count, d_landmarks);
+    if (rc) return rc;
+    // a degenerate face (inter-eye distance too small for a patch) or a bad frame index is an error here, as it is in the
+    // reference (cv::resize on an empty ROI throws); reading the flag synchronises the stream
+    return sd_check_hog_status(ctx, "detect");
 }
 
 static int detect_host_full(sd_ctx* ctx, const sd_model* m, const uint8_t* h_images, int count, int width, int height,
@@ -512,8 +529,7 @@ static int detect_host_full(sd_ctx* ctx, const sd_model* m, const uint8_t* h_ima
         SD_CUDA(ctx, cudaEventRecord(ctx->stage_done[buf], ctx->stream));
     }
     SD_CUDA(ctx, cudaMemcpyAsync(h_landmarks, d_out, (size_t)count * P * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-    SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return SD_OK;
+    return sd_check_hog_status(ctx, "detect");                // synchronises
 }
 
 // ROI route: needs the caller's frames in pinned (device-mapped) host memory
@@ -532,6 +548,8 @@ static int detect_host_roi(sd_ctx* ctx, const sd_model* m, const uint8_t* h_imag
         sd_align_mean(m->mean.data(), L, h_boxes[4 * i], h_boxes[4 * i + 1], h_boxes[4 * i + 2], h_boxes[4 * i + 3], 1.f, 1.f, 0.f, 0.f, &x0[(size_t)i * P]);
         sd_roi r = face_roi(m, &x0[(size_t)i * P], width, height, row_stride);
         const size_t bytes = (size_t)r.row_stride * r.h;
+        if (bytes > chunk_cap)                                // a face window larger than a staging buffer: whole-frame route
+            return detect_host_full(ctx, m, h_images, count, width, height, row_stride, h_boxes, h_landmarks);
         if (chunk_first.empty() || used + bytes > chunk_cap) { chunk_first.push_back(i); used = 0; }
         r.offset = (int64_t)used;
         used += bytes;
@@ -582,7 +600,10 @@ static int detect_host_roi(sd_ctx* ctx, const sd_model* m, const uint8_t* h_imag
     std::vector<uint8_t> miss(count);
     SD_CUDA(ctx, cudaMemcpyAsync(h_landmarks, d_out, xbytes, cudaMemcpyDeviceToHost, ctx->stream));
     SD_CUDA(ctx, cudaMemcpyAsync(miss.data(), d_miss, count, cudaMemcpyDeviceToHost, ctx->stream));
-    SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    {
+        const int rc = sd_check_hog_status(ctx, "detect");    // synchronises
+        if (rc) return rc;
+    }
     // faces whose cascade wandered outside the uploaded region: repeat them from their full frames
     for (int i = 0; i < count; ++i) {
         if (!miss[i]) continue;

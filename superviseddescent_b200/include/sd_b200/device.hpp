@@ -70,9 +70,9 @@ inline void upload(const cv::Mat& m, DeviceBuffer& dst, int64_t ld)
     sd_ctx* ctx = context();
     if (m.isContinuous() && ld == m.cols) {
         check(ctx, sd_memcpy_h2d(ctx, dst.as<float>(), m.ptr<float>(0), static_cast<size_t>(m.rows) * m.cols * sizeof(float)), "upload");
-    } else {
-        for (int r = 0; r < m.rows; ++r)
-            check(ctx, sd_memcpy_h2d(ctx, dst.as<float>() + static_cast<size_t>(r) * ld, m.ptr<float>(r), static_cast<size_t>(m.cols) * sizeof(float)), "upload");
+    } else {   // strided on either side: one 2-D copy
+        check(ctx, sd_memcpy2d_h2d(ctx, dst.as<float>(), static_cast<size_t>(ld) * sizeof(float), m.ptr<float>(0), m.step(),
+                                   static_cast<size_t>(m.cols) * sizeof(float), static_cast<size_t>(m.rows)), "upload");
     }
     check(ctx, sd_sync(ctx), "upload");   // the host Mat may go away after this call
 }
@@ -84,8 +84,8 @@ inline cv::Mat download(const float* d, int rows, int cols, int64_t ld)
     if (ld == cols) {
         check(ctx, sd_memcpy_d2h(ctx, m.ptr<float>(0), d, static_cast<size_t>(rows) * cols * sizeof(float)), "download");
     } else {
-        for (int r = 0; r < rows; ++r)
-            check(ctx, sd_memcpy_d2h(ctx, m.ptr<float>(r), d + static_cast<size_t>(r) * ld, static_cast<size_t>(cols) * sizeof(float)), "download");
+        check(ctx, sd_memcpy2d_d2h(ctx, m.ptr<float>(0), m.step(), d, static_cast<size_t>(ld) * sizeof(float),
+                                   static_cast<size_t>(cols) * sizeof(float), static_cast<size_t>(rows)), "download");
     }
     check(ctx, sd_sync(ctx), "download");
     return m;

@@ -60,10 +60,9 @@ public:
         // one extended operand [A | B] so that A^T B rides along in the same SYRK
         const int64_t ld = (static_cast<int64_t>(D) + M + 3) / 4 * 4;
         sd_b200::DeviceBuffer ext(static_cast<size_t>(N) * ld * sizeof(float)), dX(static_cast<size_t>(D) * M * sizeof(float));
-        for (int r = 0; r < N; ++r) {
-            sd_b200::check(ctx, sd_memcpy_h2d(ctx, ext.as<float>() + r * ld, data.ptr<float>(r), sizeof(float) * D), "solve");
-            sd_b200::check(ctx, sd_memcpy_h2d(ctx, ext.as<float>() + r * ld + D, labels.ptr<float>(r), sizeof(float) * M), "solve");
-        }
+        // [A | B] side by side on the device: two strided copies
+        sd_b200::check(ctx, sd_memcpy2d_h2d(ctx, ext.as<float>(), ld * sizeof(float), data.ptr<float>(0), data.step(), sizeof(float) * D, N), "solve");
+        sd_b200::check(ctx, sd_memcpy2d_h2d(ctx, ext.as<float>() + D, ld * sizeof(float), labels.ptr<float>(0), labels.step(), sizeof(float) * M, N), "solve");
         const sd_regulariser reg = regulariser.c();
         sd_b200::check(ctx, sd_learn(ctx, ext.as<float>(), ld, ext.as<float>() + D, ld, N, D, M, &reg, dX.as<float>(), &last_lambda), "sd_learn");
         return sd_b200::download(dX.as<float>(), D, M, M);

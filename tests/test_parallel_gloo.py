@@ -1,8 +1,11 @@
-"""world_size-2 gloo test (CPU) of the multi-GPU host logic: sample sharding + the one all-reduce of
-[A^T A | A^T b] per level + the global-N lambda rule + replicated solve.
+"""world_size-2 gloo test (CPU) of the multi-GPU protocol: sample sharding, the band-packed exchange of
+[A^T A | A^T b] (all-reduce for the replicated route, per-band reduce to the block-row-cyclic owner for the distributed
+one), the global-N lambda rule, and a numpy model of the distributed blocked Cholesky's ownership / broadcast protocol
+(SURVEY.md 8e, 8f/f3).
 
-No GPU here, so the per-rank Gram is formed with numpy; everything else is the product code in
-superviseddescent_b200/parallel.py that the NCCL path runs unchanged."""
+No GPU here, so the per-rank Gram is formed with numpy and the collectives run over gloo; the layout and ownership
+helpers are the product's (superviseddescent_b200/parallel.py mirrors csrc/sd_comm.cu).  The CUDA implementation of the
+same protocol is checked on hardware by tests/test_gpu_multi.py."""
 import os
 import socket
 import sys
@@ -34,6 +37,35 @@ def _solve(G, D, lam_param, n_global):
     return np.linalg.solve(AtA + reg, G[:, D:].astype(np.float64))
 
 
+def _dist_cholesky_model(G, d, m, lam, rank, world, panel):
+    """numpy model of sd_solve_gram_dist's protocol (csrc/sd_linalg.cu cholesky_solve with a communicator): block-row-cyclic
+    panel ownership, the owner factors its panel and broadcasts the finished rows, every rank updates the rows it owns."""
+    from superviseddescent_b200 import parallel
+    G = G.astype(np.float64).copy()
+    for i in range(d):
+        if parallel.panel_owner(i, world, panel) != rank:
+            G[i, :] = np.nan                                   # rows of other ranks are undefined on entry
+    idx = np.arange(d)
+    G[idx, idx] += np.where(idx == d - 1, 0.0, lam)            # regulariser on every (owned) diagonal entry
+    for j in range(0, d, panel):
+        k = min(panel, d - j)
+        owner = parallel.panel_owner(j, world, panel)
+        rows = torch.from_numpy(G[j:j + k, j:].copy())
+        if rank == owner:
+            blk = np.triu(G[j:j + k, j:j + k])
+            U11 = np.linalg.cholesky(blk + np.triu(blk, 1).T).T
+            P = np.linalg.solve(U11.T, G[j:j + k, j + k:])     # block-row solve, right-hand sides ride along
+            rows = torch.from_numpy(np.hstack([U11, P]))
+        dist.broadcast(rows, src=owner)                        # the panel broadcast
+        G[j:j + k, j:] = rows.numpy()
+        P = G[j:j + k, j + k:]
+        for i in range(j + k, d):                              # trailing update of the rows this rank owns
+            if parallel.panel_owner(i, world, panel) == rank:
+                G[i, i:] -= P[:, i - j - k] @ P[:, i - j - k:]
+    U, Y = np.triu(G[:, :d]), G[:, d:]
+    return np.linalg.solve(U, Y)                               # replicated back substitution
+
+
 def _worker(rank, world, port, n, d, m, out):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -45,18 +77,41 @@ def _worker(rank, world, port, n, d, m, out):
     B = rng.standard_normal((n, m)).astype(np.float32)
     b, e = parallel.shard_range(n, world, rank)
     Al, Bl = A[b:e].astype(np.float64), B[b:e].astype(np.float64)
-    G = torch.from_numpy(np.hstack([Al.T @ Al, Al.T @ Bl]).astype(np.float32))
+    G = np.hstack([Al.T @ Al, Al.T @ Bl]).astype(np.float32)
     n_global = parallel.global_count(e - b)
-    G_full = G.clone()
-    parallel.allreduce_gram(G_full)                          # whole buffer
-    parallel.allreduce_gram(G, None, d, band=5)              # upper row bands only (ragged last band: 24 = 4*5 + 4)
+    G_full = torch.from_numpy(G.copy())
+    dist.all_reduce(G_full)                                  # reference: the whole buffer
+    # the exchange of the product (csrc/sd_comm.cu): only the upper row bands travel, packed back to back
+    band = 5                                                 # ragged last band: 24 = 4*5 + 4
+    W = d + m
+    off = parallel.band_offsets(d, W, band)
+    flat = torch.empty(off[-1], dtype=torch.float32)
+    for p, r0 in enumerate(range(0, d, band)):
+        flat[off[p]:off[p + 1]] = torch.from_numpy(G[r0:r0 + band, r0:].copy()).reshape(-1)
+    # (a) replicated route: all-reduce of the packed bands
+    fa = flat.clone()
+    dist.all_reduce(fa)
+    Ga = G.copy()
+    for p, r0 in enumerate(range(0, d, band)):
+        Ga[r0:r0 + band, r0:] = fa[off[p]:off[p + 1]].reshape(-1, W - r0).numpy()
     iu = np.triu_indices(d)
-    assert np.array_equal(G.numpy()[:, :d][iu], G_full.numpy()[:, :d][iu])       # every element the solve reads ...
-    assert np.array_equal(G.numpy()[:, d:], G_full.numpy()[:, d:])              # ... including the right-hand sides
-    X = _solve(G.numpy(), d, 1.5, n_global)
+    assert np.array_equal(Ga[:, :d][iu], G_full.numpy()[:, :d][iu])             # every element the solve reads ...
+    assert np.array_equal(Ga[:, d:], G_full.numpy()[:, d:])                    # ... including the right-hand sides
+    X = _solve(Ga, d, 1.5, n_global)
+    # (b) distributed route: band p is reduced to rank p % world only, then the distributed factorisation
+    Gs = np.full_like(G, np.nan)
+    for p, r0 in enumerate(range(0, d, band)):
+        piece = flat[off[p]:off[p + 1]].clone()
+        dist.reduce(piece, dst=p % world)
+        if p % world == rank:
+            Gs[r0:r0 + band, r0:] = piece.reshape(-1, W - r0).numpy()
+            assert np.array_equal(Gs[r0:r0 + band, r0:], Ga[r0:r0 + band, r0:])
+    AtA = np.triu(Ga[:, :d].astype(np.float64))
+    lam = 1.5 * np.linalg.norm(AtA + np.triu(AtA, 1).T) / n_global
+    Xd = _dist_cholesky_model(np.where(np.isnan(Gs), 0.0, Gs), d, m, lam, rank, world, band)
     x_local = torch.from_numpy(A[b:e, :4].copy())
     gathered = parallel.gather_rows(x_local)
-    out.put((rank, n_global, X, gathered.numpy()))
+    out.put((rank, n_global, X, gathered.numpy(), Xd))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -74,7 +129,17 @@ def test_shard_range_partitions_rows():
         parallel.shard_range(10, 2, 2)
 
 
-def test_two_rank_gram_allreduce_matches_single_process():
+def test_band_layout_and_ownership():
+    from superviseddescent_b200 import parallel
+    D, W = 1000, 1044
+    off = parallel.band_offsets(D, W)
+    assert len(off) == 5 and off[1] == 256 * W and off[2] - off[1] == 256 * (W - 256)
+    assert off[-1] - off[-2] == (1000 - 768) * (W - 768)
+    assert [parallel.panel_owner(r, 3) for r in (0, 255, 256, 511, 512, 768, 999)] == [0, 0, 1, 1, 2, 0, 0]
+    assert off[-1] < 0.65 * D * W                            # about half of the buffer travels
+
+
+def test_two_rank_gram_exchange_and_distributed_solve_match_single_process():
     n, d, m, world = 301, 24, 6, 2
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
@@ -92,8 +157,10 @@ def test_two_rank_gram_allreduce_matches_single_process():
     B = rng.standard_normal((n, m)).astype(np.float32)
     A64, B64 = A.astype(np.float64), B.astype(np.float64)
     X_ref = _solve(np.hstack([A64.T @ A64, A64.T @ B64]), d, 1.5, n)
-    for rank, n_global, X, gathered in results:
+    for rank, n_global, X, gathered, Xd in results:
         assert n_global == n
         assert np.max(np.abs(X - X_ref)) <= 1e-4 * np.max(np.abs(X_ref))
+        assert np.max(np.abs(Xd - X_ref)) <= 1e-4 * np.max(np.abs(X_ref))      # distributed factorisation, same answer
         assert np.array_equal(gathered, A[:, :4])
     assert np.array_equal(results[0][2], results[1][2])      # replicated solve: bit-identical on every rank
+    assert np.array_equal(results[0][4], results[1][4])      # distributed solve: every rank ends with the same X
