@@ -170,6 +170,14 @@ SD_API int sd_bgr2gray(sd_ctx* ctx, const uint8_t* d_bgr, int width, int height,
  * reference's VerbosePartialPivLUSolver prints them, are available from sd_solver_timings. */
 SD_API int sd_learn(sd_ctx* ctx, const float* d_A, int64_t lda, const float* d_B, int64_t ldb,
                     int N, int D, int M, const sd_regulariser* reg, float* d_X, float* lambda_out);
+/* ColPivHouseholderQRSolver::solve (regressors.hpp:264-305): the same system, plus the one diagnostic that solver exists for --
+ * the numerical rank of the regularised A^T A (regressors.hpp:288-293 prints it and asks for a larger lambda).  A^T A + Lambda is
+ * symmetric positive semi-definite, so the rank comes from a diagonally pivoted Cholesky (threshold eps * D relative to the
+ * largest pivot, Eigen's default rule), D <= 4096; beyond that *rank_out = -1 (not computed).  Like the reference the call goes
+ * on to solve when the matrix is rank deficient; if the solve itself then breaks down the status is SD_ERR_NUMERIC and
+ * sd_last_error carries the reference's message with the rank. */
+SD_API int sd_learn_rank_revealing(sd_ctx* ctx, const float* d_A, int64_t lda, const float* d_B, int64_t ldb,
+                                   int N, int D, int M, const sd_regulariser* reg, float* d_X, float* lambda_out, int* rank_out);
 /* The same, split at the multi-GPU exchange point (superviseddescent.hpp:207 / SURVEY 8e):
  *   1. sd_gram      : d_G[Dx(D+M)] = [A^T A | A^T B] of the local rows (upper triangle of the
  *                     D x D part is valid; row stride ldg >= D+M)

@@ -122,14 +122,27 @@ class Regulariser:
         return RegulariserC(int(self.regularisation_type), self.param, int(self.regularise_last_row))
 
 
-class LinearRegressor:
-    """superviseddescent::LinearRegressor<Solver> (regressors.hpp:318-400); the Solver is the B200 one."""
+class PartialPivLUSolver:
+    """regressors.hpp:180-235 (also VerbosePartialPivLUSolver): the default Solver."""
+    rank_revealing = False
 
-    def __init__(self, regulariser: Optional[Regulariser] = None, ctx: Optional[Context] = None):
+
+class ColPivHouseholderQRSolver:
+    """regressors.hpp:245-306: the Solver that checks invertibility.  Same solve, plus the numerical rank of the regularised
+    AtA (diagonally pivoted Cholesky on the device); a deficient rank prints the reference's message (:290-293)."""
+    rank_revealing = True
+
+
+class LinearRegressor:
+    """superviseddescent::LinearRegressor<Solver> (regressors.hpp:318-400); `solver` plays the template parameter."""
+
+    def __init__(self, regulariser: Optional[Regulariser] = None, ctx: Optional[Context] = None, solver=None):
         self.regulariser = regulariser or Regulariser()
         self.ctx = ctx
+        self.solver = solver or PartialPivLUSolver()
         self.x: Optional[torch.Tensor] = None   # D x M, device
         self.last_lambda: Optional[float] = None
+        self.last_rank: Optional[int] = None    # ColPivHouseholderQRSolver only
 
     def _ctx(self) -> Context:
         if self.ctx is None:
@@ -146,8 +159,21 @@ class LinearRegressor:
         X = torch.empty((D, M), dtype=torch.float32, device=A.device)
         lam = C.c_float(0)
         reg = self.regulariser.c()
-        _check(ctx.h, _capi.lib().sd_learn(ctx.h, ptr(A), C.c_int64(A.stride(0)), ptr(B), C.c_int64(B.stride(0)),
-                                           N, D, M, C.byref(reg), ptr(X), C.byref(lam)))
+        if getattr(self.solver, "rank_revealing", False):
+            rank = C.c_int(-1)
+            rc = _capi.lib().sd_learn_rank_revealing(ctx.h, ptr(A), C.c_int64(A.stride(0)), ptr(B), C.c_int64(B.stride(0)),
+                                                     N, D, M, C.byref(reg), ptr(X), C.byref(lam), C.byref(rank))
+            self.last_rank = rank.value
+            if 0 <= rank.value < D:
+                print("The regularised AtA is not invertible. We continued learning, but Eigen may return garbage (their docu is not "
+                      f"very specific). (The rank is {rank.value}, full rank would be {D}). Increase lambda.")
+                if rc == 5:                       # SD_ERR_NUMERIC: the factorisation of the singular matrix stopped; the reference returns garbage here
+                    X.fill_(float("nan"))
+                    rc = 0
+            _check(ctx.h, rc)
+        else:
+            _check(ctx.h, _capi.lib().sd_learn(ctx.h, ptr(A), C.c_int64(A.stride(0)), ptr(B), C.c_int64(B.stride(0)),
+                                               N, D, M, C.byref(reg), ptr(X), C.byref(lam)))
         self.x = X
         self.last_lambda = lam.value
         return True

@@ -5,9 +5,11 @@
 // One CTA per (sample, landmark) patch.  Everything between the 8-bit source image in HBM and the
 // feature row in HBM lives in shared memory:
 //   geometry (IED -> half patch size, cvRound centre)            adaptive_vlhog.hpp:123,132-133
-//   zero-padded crop + cv::resize INTER_LINEAR (fixed point)     adaptive_vlhog.hpp:135-155
-//   gradient, orientation arg-max (integer result, bit exact)    hog.c:631-672
-//   bilinear spatial vote, gathered per cell (no atomics)        hog.c:697-724
+//   zero-padded crop: ONE TMA tile load per patch (3-D tensor map over the frame batch; out-of-frame
+//     bytes are zero-filled by the TMA = copyMakeBorder(BORDER_CONSTANT 0))   adaptive_vlhog.hpp:135-151
+//   cv::resize INTER_LINEAR (fixed point), tables precomputed once per face   adaptive_vlhog.hpp:154-155
+//   gradient, orientation arg-max and modulus from device-generated tables (integer results, bit exact)  hog.c:631-672
+//   bilinear spatial vote as two separable passes (rows x cell columns, then cell rows; no atomics)      hog.c:697-724
 //   cell energy, 2x2-block normalisation in double, clamp 0.2    hog.c:875-1053
 //   per-dimension transpose + landmark concatenation + bias      adaptive_vlhog.hpp:166-183
 //
@@ -17,6 +19,8 @@
 // reference's value stream is the summation ORDER of the float votes inside a cell histogram
 // (fixed, deterministic tree here; raster order there): ~1e-7 relative.
 #include "sd_internal.cuh"
+
+#include <cuda.h>
 
 #include <cmath>
 
@@ -40,6 +44,10 @@ struct HogArgs {
     int variant, nc, cs, K, fs, dd;
     const int* half;            // per sample: half patch size (hog_geometry_kernel)
     const int8_t* lut;          // (gy+255)*511 + (gx+255) -> directed orientation bin, -1 for a zero gradient
+    const float* mag_lut;       // gx*gx + gy*gy -> sqrtf of it (the exact integer's correctly rounded root)
+    const int* rtab;            // per sample: resize tables [5][fs] (hog_geometry_kernel)
+    const float* btab;          // per launch: spatial binning weights [nc][fs], then lo[nc], hi[nc] (hog_bintab_kernel)
+    int tma_class;              // -1: window staged by load loops; else index of the first usable tensor-map size class
     float* A;
     long long ld;
     int* geometry;
@@ -48,24 +56,91 @@ struct HogArgs {
     int* status;
 };
 
-// ---- per-sample geometry: IED -> half patch size (adaptive_vlhog.hpp:123), once per sample instead of
-//      once per thread of every patch ---------------------------------------------------------------
+// ---- per-sample geometry: IED -> half patch size (adaptive_vlhog.hpp:123) and the interpolation tables of cv::resize
+//      (INTER_LINEAR, 8U, 11-bit fixed point) for a P x P -> fs x fs resize, once per sample instead of once per thread of
+//      every one of its L patches.  One CTA per sample.  rtab[sample][0..4][fs]: x source index, x weights (2 x int16),
+//      y source index 0 / 1 (clamped), y weights. -------------------------------------------------------------------------
+__device__ __forceinline__ int clip_index(int x, int a, int b) { return x >= a ? (x < b ? x : b - 1) : a; }
+__device__ __forceinline__ short sat_short(int v) { return (short)(v > 32767 ? 32767 : (v < -32768 ? -32768 : v)); }
+
 __global__ void hog_geometry_kernel(const float* __restrict__ x, long long ldx, int N, int L, const sd_eyes_dev eyes, float rel,
-                                    int fixed_half, int* __restrict__ half_out, int* __restrict__ status)
+                                    int fixed_half, int fs, int* __restrict__ half_out, int* __restrict__ rtab, int* __restrict__ status)
+{
+    const int i = blockIdx.x;
+    if (i >= N) return;
+    __shared__ int s_half;
+    if (threadIdx.x == 0) {
+        int half = fixed_half;       // > 0: non-adaptive HogTransform of examples/landmark_detection.cpp:213
+        if (fixed_half <= 0) {
+            const double ied = sd_device_ied(x + (long long)i * ldx, L, eyes);
+            half = (int)round(__dmul_rn(__dmul_rn((double)rel, ied), 0.5));   // std::round(float rel * double ied / 2)
+            if (half < 1) {          // cv::resize would throw on the empty ROI; flag it and keep going
+                half = 1;
+                atomicOr(status, 1);
+            }
+        }
+        half_out[i] = half;
+        s_half = half;
+    }
+    __syncthreads();
+    const int P = 2 * s_half;
+    int* rt = rtab + (long long)i * 5 * fs;
+    for (int t = threadIdx.x; t < fs; t += blockDim.x) {
+        const double inv_scale = __ddiv_rn((double)fs, (double)P);
+        const double scale = __ddiv_rn(1.0, inv_scale);
+        float f = (float)__dadd_rn(__dmul_rn((double)t + 0.5, scale), -0.5);
+        const int s = (int)floorf(f);
+        f = __fsub_rn(f, (float)s);
+        int sx = s;
+        float fx = f;
+        if (sx < 0) { fx = 0.f; sx = 0; }
+        if (sx >= P - 1) { fx = 0.f; sx = P - 1; }
+        const short2 xa = make_short2(sat_short(__float2int_rn(__fmul_rn(__fsub_rn(1.f, fx), 2048.f))),
+                                      sat_short(__float2int_rn(__fmul_rn(fx, 2048.f))));
+        const short2 yb = make_short2(sat_short(__float2int_rn(__fmul_rn(__fsub_rn(1.f, f), 2048.f))),
+                                      sat_short(__float2int_rn(__fmul_rn(f, 2048.f))));
+        rt[t] = sx;
+        rt[fs + t] = *reinterpret_cast<const int*>(&xa);
+        rt[2 * fs + t] = clip_index(s, 0, P);
+        rt[3 * fs + t] = clip_index(s + 1, 0, P);
+        rt[4 * fs + t] = *reinterpret_cast<const int*>(&yb);
+    }
+}
+
+// ---- spatial binning tables of vl_hog_put_image (hog.c:697-709), once per launch: btab[c * fs + t] = weight with which pixel
+//      coordinate t votes into cell index c (w1 for its own bin, w2 for the next one, 0 otherwise); then, as ints, the first and
+//      last interior coordinate that votes into cell c (same tables for rows and columns: square patch, square cells) ---------
+__global__ void hog_bintab_kernel(int fs, int nc, int cs, float* __restrict__ btab)
+{
+    __shared__ int s_sbin[256];
+    for (int t = threadIdx.x; t < fs; t += blockDim.x) {
+        const float h = (float)__dadd_rn(__ddiv_rn((double)t + 0.5, (double)cs), -0.5);
+        int b = (int)h;                                   // vl_floor_f, hog.h:52-58
+        if (!(h >= 0.f || (float)b == h)) b -= 1;
+        const float w2 = __fsub_rn(h, (float)b);
+        const float w1 = (float)__dadd_rn(1.0, -(double)w2);
+        s_sbin[t] = b;
+        for (int c = 0; c < nc; ++c) btab[c * fs + t] = (b == c) ? w1 : ((b == c - 1) ? w2 : 0.f);
+    }
+    __syncthreads();
+    int* lohi = reinterpret_cast<int*>(btab + nc * fs);
+    for (int c = threadIdx.x; c < nc; c += blockDim.x) {
+        int lo = fs, hi = -1;
+        for (int t = 1; t <= fs - 2; ++t) {
+            const int b = s_sbin[t];
+            if (b == c || b == c - 1) { if (t < lo) lo = t; hi = t; }
+        }
+        lohi[c] = lo;
+        lohi[nc + c] = hi;
+    }
+}
+
+// sqrtf of every possible squared gradient modulus of an 8-bit patch (gx, gy in [-255, 255]): hog.c:645 takes sqrtf of the
+// float gx*gx + gy*gy, which is an exactly representable integer here
+__global__ void hog_maglut_kernel(float* __restrict__ lut, int n)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
-    if (fixed_half > 0) {    // non-adaptive HogTransform of examples/landmark_detection.cpp:213
-        half_out[i] = fixed_half;
-        return;
-    }
-    const double ied = sd_device_ied(x + (long long)i * ldx, L, eyes);
-    int half = (int)round(__dmul_rn(__dmul_rn((double)rel, ied), 0.5));   // std::round(float rel * double ied / 2)
-    if (half < 1) {          // cv::resize would throw on the empty ROI; flag it and keep going
-        half = 1;
-        atomicOr(status, 1);
-    }
-    half_out[i] = half;
+    if (i < n) lut[i] = __fsqrt_rn((float)i);
 }
 
 // ---- (gx, gy) -> orientation bin table, generated ON THE DEVICE with the reference's float expression
@@ -102,105 +177,60 @@ __global__ void hog_lut_kernel(const LutArgs t, int8_t* __restrict__ lut)
 
 // shared-memory carve-up (same function on host and device)
 struct HogSmem {
-    int patch, bin, r1, xofs, yofs0, yofs1, xa, yb, sbin, sw1, sw2, wcell, lo, hi, hist, energy, fac, priv, feat, total;
+    int patch, bin, r1, xofs, yofs0, yofs1, xa, yb, wcell, lo, hi, hist, energy, fac, vote, feat, mbar, total;
+    int tpad;      // tasks of the horizontal vote pass, padded to a multiple of 32
 };
 
 __host__ __device__ inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
 
-__host__ __device__ inline HogSmem hog_smem_layout(int fs, int nc, int K, int dd, bool pair)
+__host__ __device__ inline HogSmem hog_smem_layout(int fs, int nc, int K, int dd)
 {
     HogSmem s;
     const int cells = nc * nc;
     int o = 0;
-    s.patch = o;  o = align_up(o + fs * fs, 16);
-    s.bin = o;    o = align_up(o + fs * fs, 16);
-    int r1 = fs * fs * 4;                                   // gradient modulus, later the clamped hc values (double)
-    if (cells * K * 32 > r1) r1 = cells * K * 32;
+    s.patch = o;  o = align_up(o + fs * fs, 128);
+    s.bin = o;    o = align_up(o + fs * fs, 16);            // [bin | r1] doubles as the staging area of the source window (128-byte
+    int r1 = fs * fs * 4;                                   //  aligned: TMA destination); r1 = gradient modulus, later the clamped
+    if (cells * K * 32 > r1) r1 = cells * K * 32;           //  hc values (double)
     s.r1 = o;     o = align_up(o + r1, 16);
     s.xofs = o;   o += fs * 4;
     s.yofs0 = o;  o += fs * 4;
     s.yofs1 = o;  o += fs * 4;
     s.xa = o;     o += fs * 4;                              // 2 x int16
     s.yb = o;     o += fs * 4;
-    s.sbin = o;   o += fs * 4;
-    s.sw1 = o;    o += fs * 4;
-    s.sw2 = o;    o += fs * 4;
     s.wcell = o;  o += nc * fs * 4;                         // weight of pixel t for cell index c (0 if it does not vote)
     s.lo = o;     o += nc * 4;
     s.hi = o;     o += nc * 4;
     s.hist = o;   o += cells * 2 * K * 4;
     s.energy = o; o = align_up(o + cells * 4, 16);
     s.fac = o;    o += cells * 4 * 8;
-    s.priv = o;   o += kHogWarps * (pair ? 2 : 1) * 2 * K * 32 * 4;   // private histogram columns (two cells when paired)
+    s.tpad = align_up((fs - 2) * nc, 32);
+    s.vote = o;   o += 2 * K * s.tpad * 4;                  // horizontal pass of the vote: T[bin][(cell column, row)]
     s.feat = o;   o += cells * dd * 4;
+    s.mbar = align_up(o, 8); o = s.mbar + 8;
     s.total = align_up(o, 16);
     return s;
-}
-
-__device__ __forceinline__ int clip_index(int x, int a, int b) { return x >= a ? (x < b ? x : b - 1) : a; }
-
-__device__ __forceinline__ short sat_short(int v) { return (short)(v > 32767 ? 32767 : (v < -32768 ? -32768 : v)); }
-
-
-// Column sums of one warp's private histogram table priv[bin][lane] -> s_hist[bin * cells + c]; the table is
-// cleared for the next cell.  KT > 0: recursive halving (after log2(NB) exchange steps every lane owns one
-// bin, the remaining butterfly steps finish the sum; fixed tree -> deterministic).  KT == 0: transposed read.
-template <int KT>
-__device__ __forceinline__ void hog_reduce_priv(float* priv, int lane, float* s_hist, int cells, int c, int K)
-{
-    if (KT > 0) {
-        constexpr int NB = KT > 0 ? (2 * KT <= 8 ? 8 : (2 * KT <= 16 ? 16 : 32)) : 32;
-        float v[NB];
-#pragma unroll
-        for (int b = 0; b < NB; ++b) {
-            v[b] = b < 2 * KT ? priv[b * 32 + lane] : 0.f;
-            if (b < 2 * KT) priv[b * 32 + lane] = 0.f;
-        }
-        int bin = 0;
-#pragma unroll
-        for (int o = 16, n = NB; n > 1; o >>= 1, n >>= 1) {
-            const bool up = (lane & o) != 0;
-#pragma unroll
-            for (int i = 0; i < n / 2; ++i) {
-                const float send = up ? v[i] : v[i + n / 2];
-                const float keep = up ? v[i + n / 2] : v[i];
-                v[i] = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, o));
-            }
-            bin += up ? n / 2 : 0;
-        }
-        float tot = v[0];
-#pragma unroll
-        for (int o = 32 / NB / 2; o > 0; o >>= 1) tot = __fadd_rn(tot, __shfl_xor_sync(0xffffffffu, tot, o));
-        if ((lane & (32 / NB - 1)) == 0 && bin < 2 * KT) s_hist[bin * cells + c] = tot;
-    } else {
-        // lane b sums row b of the table, starting at column b (skew -> distinct banks)
-        for (int b = lane; b < 2 * K; b += 32) {
-            float sacc = 0.f;
-#pragma unroll 8
-            for (int j = 0; j < 32; ++j) sacc = __fadd_rn(sacc, priv[b * 32 + ((j + b) & 31)]);
-            s_hist[b * cells + c] = sacc;
-        }
-        __syncwarp();
-        for (int i = lane; i < 2 * K * 32; i += 32) priv[i] = 0.f;
-    }
-    __syncwarp();
 }
 
 // KT / NCT / CST > 0 bake the bin count, cells per side and cell size into the kernel (the schedules the
 // reference ships: 5x5 cells of 11/10/8/6 px, K = 4 or 9), which lets the compiler strength-reduce every
 // index computation; 0 = taken from the arguments at run time (any other configuration).
+// tensor maps of the frame batch (u8, dims {W, H, count}), one per square box size: a patch uses the smallest box that covers
+// its P x P source window
+constexpr int kTmaClasses = 8;
+__host__ __device__ constexpr int hog_tma_box(int c) { return c == 0 ? 32 : c == 1 ? 48 : c == 2 ? 64 : c == 3 ? 80 : c == 4 ? 96 : c == 5 ? 112 : c == 6 ? 128 : 160; }
+struct HogMaps { CUtensorMap m[kTmaClasses]; };
+
 template <int KT, int NCT, int CST>
-__global__ void __launch_bounds__(kHogThreads) hog_patch_kernel(const HogArgs a)
+__global__ void __launch_bounds__(kHogThreads) hog_patch_kernel(const HogArgs a, const __grid_constant__ HogMaps maps)
 {
-    extern __shared__ __align__(16) unsigned char smem[];
+    extern __shared__ __align__(128) unsigned char smem[];
     const int K = KT > 0 ? KT : a.K;
-    const int nc = NCT > 0 ? NCT : a.nc, cs = CST > 0 ? CST : a.cs;
+    const int nc = NCT > 0 ? NCT : a.nc;
     const int fs = (NCT > 0 && CST > 0) ? NCT * CST : a.fs;
     const int dd = a.dd;
     const int cells = nc * nc;
-    // two horizontally adjacent cells per warp task when a single cell's window would leave lanes idle (2*cs > 16)
-    constexpr bool PAIR = (KT == 4 && NCT > 0 && CST >= 9);
-    const HogSmem lay = hog_smem_layout(fs, nc, K, dd, PAIR);
+    const HogSmem lay = hog_smem_layout(fs, nc, K, dd);
     uint8_t* s_patch = smem + lay.patch;
     int8_t* s_bin = reinterpret_cast<int8_t*>(smem + lay.bin);
     float* s_gmag = reinterpret_cast<float*>(smem + lay.r1);
@@ -210,17 +240,15 @@ __global__ void __launch_bounds__(kHogThreads) hog_patch_kernel(const HogArgs a)
     int* s_yofs1 = reinterpret_cast<int*>(smem + lay.yofs1);
     short2* s_xa = reinterpret_cast<short2*>(smem + lay.xa);
     short2* s_yb = reinterpret_cast<short2*>(smem + lay.yb);
-    int* s_sbin = reinterpret_cast<int*>(smem + lay.sbin);
-    float* s_sw1 = reinterpret_cast<float*>(smem + lay.sw1);
-    float* s_sw2 = reinterpret_cast<float*>(smem + lay.sw2);
     float* s_wcell = reinterpret_cast<float*>(smem + lay.wcell);
     int* s_lo = reinterpret_cast<int*>(smem + lay.lo);
     int* s_hi = reinterpret_cast<int*>(smem + lay.hi);
     float* s_hist = reinterpret_cast<float*>(smem + lay.hist);
     float* s_energy = reinterpret_cast<float*>(smem + lay.energy);
     double* s_fac = reinterpret_cast<double*>(smem + lay.fac);
-    float* s_priv = reinterpret_cast<float*>(smem + lay.priv);
+    float* s_T = reinterpret_cast<float*>(smem + lay.vote);
     float* s_feat = reinterpret_cast<float*>(smem + lay.feat);
+    uint64_t* s_mbar = reinterpret_cast<uint64_t*>(smem + lay.mbar);
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -253,60 +281,65 @@ __global__ void __launch_bounds__(kHogThreads) hog_patch_kernel(const HogArgs a)
         a.geometry[patch_id * 3 + 2] = half;
     }
 
-    // interpolation tables of cv::resize (INTER_LINEAR, 8U, 11-bit fixed point) and the spatial
-    // binning tables of vl_hog_put_image (hog.c:697-709)
-    for (int t = tid; t < fs; t += kHogThreads) {
-        const double inv_scale = __ddiv_rn((double)fs, (double)P);
-        const double scale = __ddiv_rn(1.0, inv_scale);
-        float f = (float)__dadd_rn(__dmul_rn((double)t + 0.5, scale), -0.5);
-        const int s = (int)floorf(f);
-        f = __fsub_rn(f, (float)s);
-        int sx = s;
-        float fx = f;
-        if (sx < 0) { fx = 0.f; sx = 0; }
-        if (sx >= P - 1) { fx = 0.f; sx = P - 1; }
-        s_xofs[t] = sx;
-        s_xa[t] = make_short2(sat_short(__float2int_rn(__fmul_rn(__fsub_rn(1.f, fx), 2048.f))),
-                              sat_short(__float2int_rn(__fmul_rn(fx, 2048.f))));
-        s_yofs0[t] = clip_index(s, 0, P);
-        s_yofs1[t] = clip_index(s + 1, 0, P);
-        s_yb[t] = make_short2(sat_short(__float2int_rn(__fmul_rn(__fsub_rn(1.f, f), 2048.f))),
-                              sat_short(__float2int_rn(__fmul_rn(f, 2048.f))));
-
-        const float h = (float)__dadd_rn(__ddiv_rn((double)t + 0.5, (double)cs), -0.5);
-        int b = (int)h;                                   // vl_floor_f, hog.h:52-58
-        if (!(h >= 0.f || (float)b == h)) b -= 1;
-        const float w2 = __fsub_rn(h, (float)b);
-        const float w1 = (float)__dadd_rn(1.0, -(double)w2);
-        s_sbin[t] = b;
-        s_sw2[t] = w2;
-        s_sw1[t] = w1;
-        // weight with which pixel t votes into cell index c: w1 for its own bin, w2 for the next one
-        for (int c = 0; c < nc; ++c) s_wcell[c * fs + t] = (b == c) ? w1 : ((b == c - 1) ? w2 : 0.f);
+    // ---- S1: zero-padded crop + fixed-point bilinear resize.  The P x P source window is staged in shared memory with its
+    //      zero padding materialised, then resampled from there: one output row per warp pass, lanes along x.
+    const int x0 = cx - half, y0 = cy - half;
+    const int W = a.width, H = a.height;
+    uint8_t* s_stage = smem + lay.bin;                             // [bin | r1] are dead until S2
+    const int stage_cap = lay.xofs - lay.bin;
+    // TMA route: whole frames resident and describable by a tensor map; the smallest box class that covers the window and
+    // fits the staging area
+    int tma_box = 0;
+    if (a.tma_class >= 0) {
+#pragma unroll
+        for (int c = kTmaClasses - 1; c >= 0; --c)
+            if (c >= a.tma_class && hog_tma_box(c) >= P && hog_tma_box(c) * hog_tma_box(c) <= stage_cap) tma_box = hog_tma_box(c);
     }
-    for (int i = tid; i < kHogWarps * (PAIR ? 2 : 1) * 2 * K * 32; i += kHogThreads) s_priv[i] = 0.f;
-    __syncthreads();
+    if (tma_box > 0 && tid == 0) {
+        // one elected thread: the box lands densely (pitch = box width); bytes outside the frame are zero-filled by the TMA,
+        // which is exactly copyMakeBorder(..., BORDER_CONSTANT, 0) (adaptive_vlhog.hpp:136-147)
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(s_mbar);
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(tma_box * tma_box) : "memory");
+        int cls = 0;
+#pragma unroll
+        for (int c = 0; c < kTmaClasses; ++c) if (hog_tma_box(c) == tma_box) cls = c;
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                     ::"r"((uint32_t)__cvta_generic_to_shared(s_stage)), "l"(&maps.m[cls]), "r"(bar), "r"(x0), "r"(y0), "r"(img_idx)
+                     : "memory");
+    }
 
-    // ---- S1: zero-padded crop + fixed-point bilinear resize.  The P x P source window is first staged in
-    //      shared memory (zero padding materialised, aligned 32-bit loads when the window is resident), then
-    //      resampled from there: one output row per warp pass, lanes along x, no predicates, no division.
+    // tables: cv::resize taps of this sample (hog_geometry_kernel), spatial binning weights of this launch (hog_bintab_kernel)
     {
-        const int x0 = cx - half, y0 = cy - half;
-        const int W = a.width, H = a.height;
-        // the fast paths need the window inside the resident region AND inside the frame (an ROI is rounded up to 16-byte
-        // rows and may include row padding right of the frame: those bytes are zero padding, not pixels)
+        const int* __restrict__ rt = a.rtab + (long long)sample * 5 * fs;
+        for (int t = tid; t < fs; t += kHogThreads) {
+            s_xofs[t] = __ldg(rt + t);
+            const int xa = __ldg(rt + fs + t), yb = __ldg(rt + 4 * fs + t);
+            s_xa[t] = *reinterpret_cast<const short2*>(&xa);
+            s_yofs0[t] = __ldg(rt + 2 * fs + t);
+            s_yofs1[t] = __ldg(rt + 3 * fs + t);
+            s_yb[t] = *reinterpret_cast<const short2*>(&yb);
+        }
+        for (int i = tid; i < nc * fs; i += kHogThreads) s_wcell[i] = __ldg(a.btab + i);
+        const int* __restrict__ lohi = reinterpret_cast<const int*>(a.btab + nc * fs);
+        if (tid < nc) { s_lo[tid] = __ldg(lohi + tid); s_hi[tid] = __ldg(lohi + nc + tid); }
+        for (int i = tid; i < 2 * K * lay.tpad; i += kHogThreads) s_T[i] = 0.f;
+    }
+    {
         const bool resident = x0 >= rx && y0 >= ry && x0 + P <= rx + rw && y0 + P <= ry + rh && x0 >= 0 && y0 >= 0 && x0 + P <= W && y0 + P <= H;
         const uintptr_t align_bits = reinterpret_cast<uintptr_t>(img) | (uintptr_t)rs;
-        const bool vec16 = resident && (align_bits & 15) == 0;      // rows can be fetched as aligned 16-byte vectors
-        const bool words = resident && (align_bits & 3) == 0;
+        const bool vec16 = !tma_box && resident && (align_bits & 15) == 0;      // rows can be fetched as aligned 16-byte vectors
+        const bool words = !tma_box && resident && (align_bits & 3) == 0;
         // column c of the staged window sits at byte shiftb + c of its row
         const int shiftb = vec16 ? ((x0 - rx) & 15) : (words ? ((x0 - rx) & 3) : 0);
-        const int pitch = (P + 15 + 15) & ~15;
-        uint8_t* s_stage = smem + lay.bin;                         // [bin | r1] are dead until S2
-        const bool staged = pitch * P <= lay.xofs - lay.bin;
+        const int pitch = tma_box ? tma_box : ((P + 15 + 15) & ~15);
+        const bool staged = pitch * P <= stage_cap;
         bool miss = false;
         if (staged) {
-            if (vec16) {
+            if (tma_box) {
+                // nothing to do: the tile is in flight
+            } else if (vec16) {
                 // 8 / 16 / 32 lanes per source row, one aligned uint4 each: ~P * nvec / 32 warp loads in total
                 const int nvec = (shiftb + P + 15) >> 4;
                 const int gs = nvec <= 8 ? 3 : (nvec <= 16 ? 4 : 5);
@@ -339,7 +372,17 @@ __global__ void __launch_bounds__(kHogThreads) hog_patch_kernel(const HogArgs a)
                     }
                 }
             }
-            __syncthreads();
+            __syncthreads();                                       // tables (and the load loops' stores) visible
+            if (tma_box) {
+                const uint32_t bar = (uint32_t)__cvta_generic_to_shared(s_mbar);
+                uint32_t ok = 0;
+                const long long t0 = clock64();
+                while (!ok) {                                      // bounded: a protocol bug must trap, never hang the GPU
+                    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                                 : "=r"(ok) : "r"(bar) : "memory");
+                    if (!ok && clock64() - t0 > 4000000000LL) __trap();
+                }
+            }
             for (int dy = warp; dy < fs; dy += kHogWarps) {
                 const short2 yb = s_yb[dy];
                 const uint8_t* r0 = s_stage + s_yofs0[dy] * pitch + shiftb;
@@ -387,28 +430,17 @@ __global__ void __launch_bounds__(kHogThreads) hog_patch_kernel(const HogArgs a)
             for (int i = tid; i < fs * fs; i += kHogThreads) a.patches[patch_id * fs * fs + i] = s_patch[i];
         }
     }
-    // per cell-column pixel ranges that vote into it (same for rows: square patch, square cells)
-    if (tid < nc) {
-        int lo = fs, hi = -1;
-        for (int t = 1; t <= fs - 2; ++t) {
-            const int b = s_sbin[t];
-            if (b == tid || b == tid - 1) { if (t < lo) lo = t; hi = t; }
-        }
-        s_lo[tid] = lo;
-        s_hi[tid] = hi;
-    }
     __syncthreads();
 
-    // ---- S2: gradient + orientation arg-max per interior pixel (hog.c:631-672): the arg-max comes from the
-    //      device-generated table, the modulus is sqrtf of the exact integer g2 ---------------------------
+    // ---- S2: gradient + orientation arg-max per interior pixel (hog.c:631-672): arg-max and modulus come from the
+    //      device-generated tables (the gradient of an 8-bit patch is a pair of integers in [-255, 255]) ---------
     for (int y = 1 + warp; y <= fs - 2; y += kHogWarps) {
         for (int x = 1 + lane; x <= fs - 2; x += 32) {
             const int idx = y * fs + x;
             const int gx = (int)s_patch[idx + 1] - (int)s_patch[idx - 1];
             const int gy = (int)s_patch[idx + fs] - (int)s_patch[idx - fs];
-            const int bin = __ldg(a.lut + (gy + 255) * kLutDim + (gx + 255));
-            s_bin[idx] = (int8_t)bin;
-            s_gmag[idx] = __fsqrt_rn((float)(gx * gx + gy * gy));
+            s_bin[idx] = __ldg(a.lut + (gy + 255) * kLutDim + (gx + 255));
+            s_gmag[idx] = __ldg(a.mag_lut + (gx * gx + gy * gy));
         }
     }
     if (a.bins) {
@@ -421,100 +453,37 @@ __global__ void __launch_bounds__(kHogThreads) hog_patch_kernel(const HogArgs a)
     }
     __syncthreads();
 
-    // ---- S3: spatial vote, gathered per cell by one warp (hog.c:697-724).  Lanes run along x inside the
-    //      cell's window; every lane owns a private column of the histogram (bank == lane: conflict free).
-    if (PAIR) {
-        // two adjacent cells (ci, ci+1) per task: their windows overlap by half, the union is <= 3*cs columns;
-        // bin / modulus / row weight are loaded once and voted into both cells
-        const int groups = (nc + 1) / 2;
-        float* privA = s_priv + warp * (2 * 2 * K * 32);
-        float* privB = privA + 2 * K * 32;
-        for (int task = warp; task < nc * groups; task += kHogWarps) {
-            const int cj = task / groups, g = task - cj * groups;
-            const int ciA = 2 * g, ciB = ciA + 1;
-            const bool hasB = ciB < nc;
-            const int xlo = s_lo[ciA], xhi = hasB ? s_hi[ciB] : s_hi[ciA], ylo = s_lo[cj], yhi = s_hi[cj];
-            const int hh = yhi - ylo + 1;
-            const float* wyt = s_wcell + cj * fs;
-            if (xhi >= xlo && hh > 0) {
-                const int px = xlo + lane;
-                if (px <= xhi) {
-                    const float wA = s_wcell[ciA * fs + px];
-                    const float wB = hasB ? s_wcell[ciB * fs + px] : 0.f;
-                    const int8_t* bp = s_bin + ylo * fs + px;
-                    const float* gp = s_gmag + ylo * fs + px;
-                    float* plA = privA + lane;
-                    float* plB = privB + lane;
+    // ---- S3: bilinear spatial vote (hog.c:697-724), separable:  hist[b][cj][ci] = sum_y wy[cj][y] * ( sum_x wx[ci][x] * g[y][x] * [bin[y][x] == b] ).
+    //      Pass 1: one thread per (cell column ci, interior row y) walks the <= 2*cs pixels of that row that vote into ci and adds
+    //      g * wx into ITS OWN column of T[bin][task] (bank == task mod 32: conflict free, no atomics, fixed order).
+    //      Pass 2: one thread per (bin, cell) folds the rows with wy.  The reference adds (g * wx) * wy per pixel in raster
+    //      order; this is the same sum associated differently (~1e-7 relative), deterministic.
+    {
+        const int nrow = fs - 2, ntask = nrow * nc, tpad = lay.tpad;
+        for (int task = tid; task < ntask; task += kHogThreads) {
+            const int ci = task / nrow, y = 1 + task - ci * nrow;
+            const int xlo = s_lo[ci], xhi = s_hi[ci];
+            const int8_t* bp = s_bin + y * fs + xlo;
+            const float* gp = s_gmag + y * fs + xlo;
+            const float* wp = s_wcell + ci * fs + xlo;
+            float* T = s_T + task;
 #pragma unroll 2
-                    for (int ry = 0; ry < hh; ++ry) {
-                        const int b = max((int)*bp, 0) << 5;          // zero gradient: bin -1, modulus 0 -> votes +0 into bin 0
-                        const float gm = *gp, wy = wyt[ylo + ry];
-                        plA[b] = __fadd_rn(plA[b], __fmul_rn(__fmul_rn(gm, wA), wy));     // grad * wx * wy
-                        plB[b] = __fadd_rn(plB[b], __fmul_rn(__fmul_rn(gm, wB), wy));
-                        bp += fs; gp += fs;
-                    }
-                }
-                // columns beyond the 32nd of the union (3*cs = 33 for cs = 11): lanes run along y instead
-                for (int px2 = xlo + 32; px2 <= xhi; ++px2) {
-                    const float wA = s_wcell[ciA * fs + px2];
-                    const float wB = hasB ? s_wcell[ciB * fs + px2] : 0.f;
-                    for (int ry = lane; ry < hh; ry += 32) {
-                        const int idx = (ylo + ry) * fs + px2;
-                        const int b = max((int)s_bin[idx], 0) << 5;
-                        const float gm = s_gmag[idx], wy = wyt[ylo + ry];
-                        privA[b + lane] = __fadd_rn(privA[b + lane], __fmul_rn(__fmul_rn(gm, wA), wy));
-                        privB[b + lane] = __fadd_rn(privB[b + lane], __fmul_rn(__fmul_rn(gm, wB), wy));
-                    }
-                }
+            for (int x = xlo; x <= xhi; ++x) {
+                const int b = max((int)*bp++, 0);                     // zero gradient: bin -1, modulus 0 -> adds +0 to bin 0
+                float* q = T + b * tpad;
+                *q = __fadd_rn(*q, __fmul_rn(*gp++, *wp++));
             }
-            __syncwarp();
-            hog_reduce_priv<KT>(privA, lane, s_hist, cells, cj * nc + ciA, K);
-            if (hasB) hog_reduce_priv<KT>(privB, lane, s_hist, cells, cj * nc + ciB, K);
         }
-    } else {
-        float* priv = s_priv + warp * (2 * K * 32);
-        for (int c = warp; c < cells; c += kHogWarps) {
-            const int cj = c / nc, ci = c - cj * nc;      // cell row (y), cell column (x)
-            const int xlo = s_lo[ci], xhi = s_hi[ci], ylo = s_lo[cj], yhi = s_hi[cj];
-            const int ww = xhi - xlo + 1, hh = yhi - ylo + 1;
-            if (ww > 0 && hh > 0) {
-                const float* wyt = s_wcell + cj * fs;
-                if (ww <= 32) {
-                    // 8 / 16 / 32 lanes per row, 32 >> shift rows per pass
-                    const int shift = ww <= 8 ? 3 : (ww <= 16 ? 4 : 5);
-                    const int lx = lane & ((1 << shift) - 1), lr = lane >> shift, rpi = 32 >> shift;
-                    if (lx < ww) {
-                        const int px = xlo + lx;
-                        const float wx = s_wcell[ci * fs + px];
-                        const int8_t* bp = s_bin + (ylo + lr) * fs + px;
-                        const float* gp = s_gmag + (ylo + lr) * fs + px;
-                        const float* wp = wyt + ylo + lr;
-                        const int step = rpi * fs;
-                        float* pl = priv + lane;
-#pragma unroll 2
-                        for (int ry = lr; ry < hh; ry += rpi) {
-                            // a zero gradient has bin -1 and modulus 0: it votes +0 into bin 0 (no branch)
-                            const int b = max((int)*bp, 0);
-                            const float v = __fmul_rn(__fmul_rn(*gp, wx), *wp);   // grad * wx * wy
-                            float* q = pl + (b << 5);
-                            *q = __fadd_rn(*q, v);
-                            bp += step; gp += step; wp += rpi;
-                        }
-                    }
-                } else {                                   // very wide cells: lanes stride along x
-                    for (int py = ylo; py <= yhi; ++py)
-                        for (int px = xlo + lane; px <= xhi; px += 32) {
-                            const int idx = py * fs + px;
-                            const int b = s_bin[idx];
-                            if (b >= 0) {
-                                const float v = __fmul_rn(__fmul_rn(s_gmag[idx], s_wcell[ci * fs + px]), wyt[py]);
-                                priv[b * 32 + lane] = __fadd_rn(priv[b * 32 + lane], v);
-                            }
-                        }
-                }
-            }
-            __syncwarp();
-            hog_reduce_priv<KT>(priv, lane, s_hist, cells, c, K);
+        __syncthreads();
+        for (int i = tid; i < 2 * K * cells; i += kHogThreads) {
+            const int b = i / cells, c = i - b * cells;
+            const int cj = c / nc, ci = c - cj * nc;                  // cell row (y), cell column (x)
+            const int ylo = s_lo[cj], yhi = s_hi[cj];
+            const float* Tp = s_T + b * tpad + ci * nrow + (ylo - 1);
+            const float* wy = s_wcell + cj * fs + ylo;
+            float acc = 0.f;
+            for (int y = ylo; y <= yhi; ++y) acc = __fadd_rn(acc, __fmul_rn(*Tp++, *wy++));
+            s_hist[b * cells + c] = acc;
         }
     }
     __syncthreads();
@@ -605,6 +574,22 @@ __global__ void __launch_bounds__(kHogThreads) hog_patch_kernel(const HogArgs a)
     }
 }
 
+typedef CUresult (*PFN_hogEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                       const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                       CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_hogEncodeTiled hog_encode_fn()
+{
+    static PFN_hogEncodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_hogEncodeTiled>(p);
+    }
+    return fn;
+}
+
 int launch_hog(sd_ctx* ctx, const sd_image_batch* images, const int32_t* d_image_index, const float* d_x,
                int64_t ldx, int N, int L, const sd_normalisation* eyes, const sd_hog_param* p, float* d_A,
                int64_t ld, int32_t* d_geometry, uint8_t* d_patches, int8_t* d_bins)
@@ -669,15 +654,54 @@ int launch_hog(sd_ctx* ctx, const sd_image_batch* images, const int32_t* d_image
         ctx->hog_lut[a.K] = lut;
     }
     a.lut = (const int8_t*)ctx->hog_lut[a.K];
+    if (!ctx->hog_lut[0]) {              // slot 0 (K >= 1 always): modulus table, shared by every K
+        const int n = 2 * 255 * 255 + 1;
+        void* lut = nullptr;
+        SD_CUDA(ctx, cudaMalloc(&lut, (size_t)n * sizeof(float)));
+        hog_maglut_kernel<<<sd_div_up(n, 256), 256, 0, ctx->stream>>>((float*)lut, n);
+        SD_LAUNCH_CHECK(ctx, "hog_maglut_kernel");
+        ctx->hog_lut[0] = lut;
+    }
+    a.mag_lut = (const float*)ctx->hog_lut[0];
 
-    int* d_half = (int*)sd_workspace(ctx, SD_WS_GEOM, (size_t)N * sizeof(int));
+    // per-sample tables (half size, cv::resize taps) and the per-launch spatial binning table
+    const size_t geom_bytes = (size_t)N * sizeof(int) + (size_t)N * 5 * fs * sizeof(int) + (size_t)(a.nc * fs + 2 * a.nc) * sizeof(float);
+    int* d_half = (int*)sd_workspace(ctx, SD_WS_GEOM, geom_bytes);
     if (!d_half) return SD_ERR_CUDA;
-    hog_geometry_kernel<<<sd_div_up(N, 128), 128, 0, ctx->stream>>>(d_x, ldx, N, L, eyes_dev, p->relative_patch_size, fixed_half, d_half, a.status);
+    int* d_rtab = d_half + N;
+    float* d_btab = reinterpret_cast<float*>(d_rtab + (size_t)N * 5 * fs);
+    hog_geometry_kernel<<<N, 64, 0, ctx->stream>>>(d_x, ldx, N, L, eyes_dev, p->relative_patch_size, fixed_half, fs, d_half, d_rtab, a.status);
     SD_LAUNCH_CHECK(ctx, "hog_geometry_kernel");
+    hog_bintab_kernel<<<1, 256, 0, ctx->stream>>>(fs, a.nc, a.cs, d_btab);
+    SD_LAUNCH_CHECK(ctx, "hog_bintab_kernel");
     a.half = d_half;
+    a.rtab = d_rtab;
+    a.btab = d_btab;
 
-    const bool pair = a.nc == 5 && a.K == 4 && a.cs >= 9;     // must match PAIR of the kernel that gets picked below
-    const HogSmem lay = hog_smem_layout(fs, a.nc, a.K, a.dd, pair);
+    // tensor maps of the frame batch for the TMA staging route: whole frames resident, 16-byte aligned base and pitches
+    HogMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    a.tma_class = -1;
+    if (!images->d_roi && (reinterpret_cast<uintptr_t>(images->d_data) & 15) == 0 && (images->row_stride % 16) == 0 &&
+        (images->image_stride % 16) == 0 && (images->count == 1 || images->image_stride > 0) && !getenv("SD_B200_HOG_NO_TMA")) {
+        PFN_hogEncodeTiled enc = hog_encode_fn();
+        if (enc) {
+            bool ok = true;
+            for (int c = 0; c < kTmaClasses && ok; ++c) {
+                cuuint64_t gdim[3] = {(cuuint64_t)images->width, (cuuint64_t)images->height, (cuuint64_t)images->count};
+                cuuint64_t gstride[2] = {(cuuint64_t)images->row_stride, (cuuint64_t)(images->count > 1 ? images->image_stride : (int64_t)images->row_stride * images->height)};
+                if (gstride[1] % 16) gstride[1] = (gstride[1] + 15) / 16 * 16;
+                cuuint32_t box[3] = {(cuuint32_t)hog_tma_box(c), (cuuint32_t)hog_tma_box(c), 1};
+                cuuint32_t estr[3] = {1, 1, 1};
+                ok = enc(&maps.m[c], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(images->d_data), gdim, gstride, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+            }
+            if (ok) a.tma_class = 0;
+        }
+    }
+
+    const HogSmem lay = hog_smem_layout(fs, a.nc, a.K, a.dd);
     SD_REQUIRE(ctx, lay.total <= 227 * 1024, "HOG configuration needs more than 227 KB of shared memory");
     const long long blocks = (long long)N * L;
     SD_REQUIRE(ctx, blocks < 2147483647LL, "too many patches for one launch");
@@ -691,7 +715,7 @@ int launch_hog(sd_ctx* ctx, const sd_image_batch* images, const int32_t* d_image
 #undef SD_HOG_PICK
     }
     SD_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, lay.total));
-    kern<<<(unsigned)blocks, kHogThreads, lay.total, ctx->stream>>>(a);
+    kern<<<(unsigned)blocks, kHogThreads, lay.total, ctx->stream>>>(a, maps);
     SD_LAUNCH_CHECK(ctx, "hog_patch_kernel");
     return SD_OK;
 }

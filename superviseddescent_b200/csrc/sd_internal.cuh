@@ -107,6 +107,9 @@ bool sd_syrk_tc_supported(const float* d_S, int64_t lds, int K, int MI, int NJ, 
 
 int sd_check_hog_status(sd_ctx* ctx, const char* what);   // sd_api.cu: synchronises, reports and clears the projection's flags
 
+// numerical rank of the symmetric matrix whose upper triangle is in d_G (pivoted Cholesky, sd_rank.cu); rank -1: not computed
+int sd_gram_rank(sd_ctx* ctx, const float* d_G, int64_t ldg, int D, int* rank_out, float* first_pivot, float* last_pivot);
+
 // multi-GPU helpers (sd_comm.cu); a null communicator is a single rank
 int sd_comm_rank_of(const sd_comm* c);
 int sd_comm_size_of(const sd_comm* c);

@@ -216,6 +216,82 @@ __global__ void __launch_bounds__(256) gemm_nn_kernel(const float* __restrict__ 
     }
 }
 
+
+// ---- skinny-output GEMM of the cascade (LinearRegressor::predict, regressors.hpp:377-381: values * x with 2L output columns) ----
+// One THREAD per sample row: it streams its own feature row from HBM (128-bit loads, each 128-byte line is consumed by the
+// same thread over 8 loads) and keeps up to 48 output columns in registers; the weight chunk [32 x 48] sits in shared memory
+// and every read of it is a broadcast (all lanes the same address: one wavefront), so the inner loop is FFMA-bound: 48 FFMA
+// per 12 LDS.128 + 0.25 LDG.128.  (The 64 x 64 smem-tiled kernel below spends its time on shared-memory traffic when only 44
+// of its 64 tile columns exist.)  Split over D across blockIdx.y; products are summed in fp32 inside a 32-deep chunk and the
+// chunk sums in double -- cv::gemm accumulates float products in double -- then gemm_finalize_kernel adds the splits in a
+// fixed order.  blockIdx.z walks column groups of 48 (2L = 136 for the 68-point model).
+constexpr int PR_ROWS = 256, PR_KC = 32, PR_COLS = 48;
+
+__global__ void __launch_bounds__(PR_ROWS, 1) predict_rows_kernel(const float* __restrict__ A, long long lda, int N, int D,
+                                                                  const float* __restrict__ X, long long ldb, int M,
+                                                                  double* __restrict__ partial, int k_per_split)
+{
+    __shared__ __align__(16) float Xs[PR_KC][PR_COLS];
+    const int tid = threadIdx.x;
+    const int row = blockIdx.x * PR_ROWS + tid;
+    const int c0 = blockIdx.z * PR_COLS;
+    const int kbeg = blockIdx.y * k_per_split;
+    const int kend = min(D, kbeg + k_per_split);
+    const bool live = row < N;
+    const float* __restrict__ arow = A + (long long)(live ? row : 0) * lda;
+    double dacc[PR_COLS];
+#pragma unroll
+    for (int c = 0; c < PR_COLS; ++c) dacc[c] = 0.0;
+    for (int k0 = kbeg; k0 < kend; k0 += PR_KC) {
+        // this thread's 32 feature values of the chunk (columns at or beyond kend may hold anything: masked to zero)
+        float4 av[PR_KC / 4];
+#pragma unroll
+        for (int q = 0; q < PR_KC / 4; ++q) {
+            const int k = k0 + 4 * q;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (live && k < kend) {
+                v = __ldg(reinterpret_cast<const float4*>(arow + k));       // lda and kbeg are multiples of 4, the base is 16-byte aligned
+                if (k + 1 >= kend) v.y = 0.f;
+                if (k + 2 >= kend) v.z = 0.f;
+                if (k + 3 >= kend) v.w = 0.f;
+            }
+            av[q] = v;
+        }
+        __syncthreads();                                                    // the previous chunk's weights are no longer read
+        for (int i = tid; i < PR_KC * PR_COLS; i += PR_ROWS) {
+            const int kk = i / PR_COLS, c = i - kk * PR_COLS;
+            const int k = k0 + kk;
+            Xs[kk][c] = (k < kend && c0 + c < M) ? __ldg(X + (long long)k * ldb + c0 + c) : 0.f;
+        }
+        __syncthreads();
+        float acc[PR_COLS];
+#pragma unroll
+        for (int c = 0; c < PR_COLS; ++c) acc[c] = 0.f;
+#pragma unroll
+        for (int q = 0; q < PR_KC / 4; ++q) {
+            const float a4[4] = {av[q].x, av[q].y, av[q].z, av[q].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float a = a4[e];
+#pragma unroll
+                for (int c = 0; c < PR_COLS; c += 4) {
+                    const float4 w = *reinterpret_cast<const float4*>(&Xs[4 * q + e][c]);
+                    acc[c] = fmaf(a, w.x, acc[c]); acc[c + 1] = fmaf(a, w.y, acc[c + 1]);
+                    acc[c + 2] = fmaf(a, w.z, acc[c + 2]); acc[c + 3] = fmaf(a, w.w, acc[c + 3]);
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < PR_COLS; ++c) dacc[c] += (double)acc[c];
+    }
+    if (live) {
+        double* out = partial + ((long long)blockIdx.y * N + row) * M + c0;
+#pragma unroll
+        for (int c = 0; c < PR_COLS; ++c)
+            if (c0 + c < M) out[c] = dacc[c];
+    }
+}
+
 // sums the split partials in a fixed order (double) and applies the epilogue
 __global__ void gemm_finalize_kernel(const double* __restrict__ partial, int splits, int N, int M,
                                      float* __restrict__ C, long long ldc, float alpha, float beta, const GemmEpilogue ep)
@@ -244,6 +320,26 @@ int launch_gemm_nn(sd_ctx* ctx, const float* A, int64_t lda, int N, int D, const
                    float* C, int64_t ldc, float alpha, float beta, const GemmEpilogue& ep)
 {
     if (N <= 0 || M <= 0) return SD_OK;
+    // the cascade's shape -- many rows, a long contraction, 2L output columns -- goes to the row-per-thread kernel
+    if (N >= 1024 && D >= 1024 && M <= 4 * PR_COLS && (lda % 4) == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0 &&
+        !getenv("SD_B200_OLD_PREDICT")) {
+        const int row_blocks = sd_div_up(N, PR_ROWS), col_groups = sd_div_up(M, PR_COLS);
+        int splits = (int)(2LL * ctx->sm_count / ((long long)row_blocks * col_groups));     // two CTAs' worth of work per SM, whole waves
+        const int maxs = sd_div_up(D, 4 * PR_KC);
+        if (splits > maxs) splits = maxs;
+        if (splits < 1) splits = 1;
+        const int kps = sd_div_up(sd_div_up(D, splits), PR_KC) * PR_KC;
+        splits = sd_div_up(D, kps);
+        double* partial = (double*)sd_workspace(ctx, SD_WS_GEMM_PARTIAL, (size_t)splits * N * M * sizeof(double));
+        if (!partial) return SD_ERR_CUDA;
+        const dim3 pgrid(row_blocks, splits, col_groups);
+        predict_rows_kernel<<<pgrid, PR_ROWS, 0, ctx->stream>>>(A, lda, N, D, B, ldb, M, partial, kps);
+        SD_LAUNCH_CHECK(ctx, "predict_rows_kernel");
+        dim3 fblock(32, 8);
+        gemm_finalize_kernel<<<sd_div_up(N, 8), fblock, 0, ctx->stream>>>(partial, splits, N, M, C, ldc, alpha, beta, ep);
+        SD_LAUNCH_CHECK(ctx, "gemm_finalize_kernel");
+        return SD_OK;
+    }
     dim3 grid(sd_div_up(M, GT), sd_div_up(N, GT), 1);
     SD_REQUIRE(ctx, grid.y <= 65535, "too many rows for one GEMM launch");
     // skinny outputs (M = 2L columns) leave most SMs idle: split the contraction dimension
@@ -1248,7 +1344,7 @@ int sd_gram(sd_ctx* ctx, const float* d_A, int64_t lda, const float* d_B, int64_
 }
 
 static int solve_gram_impl(sd_ctx* ctx, sd_comm* comm, float* d_G, int64_t ldg, int D, int M, const sd_regulariser* reg,
-                           int n_train_global, float* d_X, float* lambda_out)
+                           int n_train_global, float* d_X, float* lambda_out, int* rank_out = nullptr)
 {
     if (!ctx) return SD_ERR_INVALID;
     SD_REQUIRE(ctx, d_G && d_X && reg && D >= 1 && M >= 1 && ldg >= D + M, "bad argument");
@@ -1281,6 +1377,12 @@ static int solve_gram_impl(sd_ctx* ctx, sd_comm* comm, float* d_G, int64_t ldg, 
     SD_LAUNCH_CHECK(ctx, "add_diag_kernel");
     SD_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
     int rc = SD_OK;
+    int rank = -1;
+    if (rank_out) {                                                   // ColPivHouseholderQRSolver's diagnostic (regressors.hpp:288-293)
+        rc = sd_gram_rank(ctx, d_G, ldg, D, &rank, nullptr, nullptr);
+        if (rc) return rc;
+        *rank_out = rank;
+    }
     if (D <= kLuMaxDim) {
         lu_small_kernel<<<1, 1024, 0, ctx->stream>>>(d_G, ldg, D, M, reinterpret_cast<int*>(ctx->d_scratch));
         SD_LAUNCH_CHECK(ctx, "lu_small_kernel");
@@ -1315,7 +1417,10 @@ static int solve_gram_impl(sd_ctx* ctx, sd_comm* comm, float* d_G, int64_t ldg, 
         SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         *lambda_out = *h;
     }
-    return check_status(ctx, "solve");
+    rc = check_status(ctx, "solve");
+    if (rc && rank >= 0 && rank < D)
+        return sd_fail(ctx, rc, "The regularised AtA is not invertible. (The rank is %d, full rank would be %d). Increase lambda.", rank, D);
+    return rc;
 }
 
 int sd_solve_gram(sd_ctx* ctx, float* d_G, int64_t ldg, int D, int M, const sd_regulariser* reg, int n_train_global,
@@ -1353,6 +1458,20 @@ int sd_learn_dist(sd_ctx* ctx, sd_comm* comm, const float* d_A, int64_t lda, con
     rc = sd_allreduce_gram(ctx, comm, G, ldg, D, M);
     if (rc) return rc;
     return sd_solve_gram(ctx, G, ldg, D, M, reg, n_train_global, d_X, lambda_out);
+}
+
+int sd_learn_rank_revealing(sd_ctx* ctx, const float* d_A, int64_t lda, const float* d_B, int64_t ldb, int N, int D, int M,
+                            const sd_regulariser* reg, float* d_X, float* lambda_out, int* rank_out)
+{
+    if (!ctx) return SD_ERR_INVALID;
+    SD_REQUIRE(ctx, M >= 1 && rank_out, "bad argument");
+    const int64_t ldg = ((int64_t)(D + M) + 3) / 4 * 4;
+    float* G = (float*)sd_workspace(ctx, SD_WS_SCRATCH, (size_t)D * ldg * sizeof(float));
+    if (!G) return SD_ERR_CUDA;
+    SD_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+    int rc = sd_gram(ctx, d_A, lda, d_B, ldb, N, D, M, G, ldg);
+    if (rc) return rc;
+    return solve_gram_impl(ctx, nullptr, G, ldg, D, M, reg, N, d_X, lambda_out, rank_out);
 }
 
 int sd_learn(sd_ctx* ctx, const float* d_A, int64_t lda, const float* d_B, int64_t ldb, int N, int D, int M,

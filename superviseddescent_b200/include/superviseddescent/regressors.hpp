@@ -8,6 +8,8 @@
 #pragma once
 
 #include <iostream>
+#include <limits>
+#include <stdexcept>
 #include <string>
 
 #include "sd_b200/device.hpp"
@@ -73,7 +75,40 @@ public:
 };
 
 using PartialPivLUSolver = B200Solver;          // regressors.hpp:180-235
-using ColPivHouseholderQRSolver = B200Solver;   // regressors.hpp:245-306 (same system; rank diagnostics: SD_ERR_NUMERIC)
+
+// regressors.hpp:245-306: the solver that "can check for invertibility".  Same system and solve as above, plus the numerical
+// rank of the regularised AtA from a diagonally pivoted Cholesky on the device (sd_learn_rank_revealing); a deficient rank is
+// reported with the reference's message (regressors.hpp:290-293) and learning continues, as there.
+class ColPivHouseholderQRSolver {
+public:
+    cv::Mat solve(cv::Mat data, cv::Mat labels, Regulariser regulariser)
+    {
+        if (data.empty() || labels.empty() || data.rows != labels.rows) throw std::runtime_error("solve: data/labels shape mismatch");
+        sd_ctx* ctx = sd_b200::context();
+        const int N = data.rows, D = data.cols, M = labels.cols;
+        const int64_t ld = (static_cast<int64_t>(D) + M + 3) / 4 * 4;
+        sd_b200::DeviceBuffer ext(static_cast<size_t>(N) * ld * sizeof(float)), dX(static_cast<size_t>(D) * M * sizeof(float));
+        sd_b200::check(ctx, sd_memcpy2d_h2d(ctx, ext.as<float>(), ld * sizeof(float), data.ptr<float>(0), data.step(), sizeof(float) * D, N), "solve");
+        sd_b200::check(ctx, sd_memcpy2d_h2d(ctx, ext.as<float>() + D, ld * sizeof(float), labels.ptr<float>(0), labels.step(), sizeof(float) * M, N), "solve");
+        const sd_regulariser reg = regulariser.c();
+        last_rank = -1;
+        const int rc = sd_learn_rank_revealing(ctx, ext.as<float>(), ld, ext.as<float>() + D, ld, N, D, M, &reg, dX.as<float>(), &last_lambda, &last_rank);
+        if (last_rank >= 0 && last_rank < D)
+            std::cout << "The regularised AtA is not invertible. We continued learning, but Eigen may return garbage (their docu is not very specific). (The rank is "
+                      << std::to_string(last_rank) << ", full rank would be " << std::to_string(D) << "). Increase lambda." << std::endl;
+        if (rc == SD_ERR_NUMERIC && last_rank >= 0 && last_rank < D) {
+            // the reference would hand back whatever Eigen's inverse of a singular matrix contains; here the factorisation stops
+            cv::Mat nan_x(D, M, CV_32FC1);
+            for (int r = 0; r < D; ++r) for (int c = 0; c < M; ++c) nan_x.at<float>(r, c) = std::numeric_limits<float>::quiet_NaN();
+            return nan_x;
+        }
+        sd_b200::check(ctx, rc, "sd_learn_rank_revealing");
+        return sd_b200::download(dX.as<float>(), D, M, M);
+    }
+    void report() const {}
+    float last_lambda = 0.0f;
+    int last_rank = -1;       // numerical rank of the last system (-1: not computed, D > 4096)
+};
 
 template <class Solver = PartialPivLUSolver>
 class LinearRegressor : public Regressor {

@@ -66,6 +66,26 @@ static void test_regressors()
     EXPECT_REL(-0.174922630, lrb.x.at<float>(0, 1), 1e-4);
     EXPECT_REL(1.82635951, lrb.x.at<float>(3, 1), 1e-4);
 
+    // ColPivHouseholderQRSolver (regressors.hpp:245-306): same weights as the LU solver on a regular system, full rank reported
+    {
+        LinearRegressor<ColPivHouseholderQRSolver> lq;
+        lq.learn(data, labels);
+        EXPECT_REL(0.489539, lq.x.at<float>(0, 0), 1e-4);
+        EXPECT_REL(0.744218946, lq.x.at<float>(2, 1), 1e-4);
+        // a duplicated column without regularisation: rank 3 of 4, the reference's warning is printed (:290-293), learn() still
+        // returns true (:349)
+        Mat dup;
+        cv::hconcat(data, data.colRange(1, 2), dup);
+        LinearRegressor<ColPivHouseholderQRSolver> ld;
+        std::printf("-- expecting the rank warning of regressors.hpp:290-293 --\n");
+        const bool okd = ld.learn(dup, labels);
+        if (!okd) { std::printf("FAIL QR learn returned false\n"); ++failures; }
+        // with lambda > 0 the same data is regular again
+        LinearRegressor<ColPivHouseholderQRSolver> lreg(Regulariser(Regulariser::RegularisationType::Manual, 1.0f, true));
+        lreg.learn(dup, labels);
+        if (!(lreg.x.rows == 4 && std::isfinite(lreg.x.at<float>(3, 1)))) { std::printf("FAIL regularised QR solve\n"); ++failures; }
+    }
+
     // OneDimOneExampleTestingResidual (test_LinearRegressor1D.cpp:84-103)
     LinearRegressor<> l1;
     l1.learn(Mat::ones(1, 1, CV_32FC1), Mat::ones(1, 1, CV_32FC1));

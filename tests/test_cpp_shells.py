@@ -60,3 +60,4 @@ def test_shells_reference_literals_train_and_detect(shells_binary, golden, tmp_p
     assert out_model.read_bytes() == open(golden.model_path, "rb").read()
     assert "The given model file could not be opened" in r.stdout        # model.hpp:199 message
     assert "At * A (ms)" in r.stdout and "Decomposition (ms)" in r.stdout  # verbose_solver.hpp:66-103 lines
+    assert "(The rank is 3, full rank would be 4). Increase lambda." in r.stdout   # regressors.hpp:290-293 through ColPivHouseholderQRSolver

@@ -206,3 +206,36 @@ def test_blocked_cholesky_shapes(sd, D, M, pad):
     err = rel_err(X.cpu().numpy(), Xo)
     print(f"D={D} M={M} ldg={ldg}: X rel err {err:.2e}")
     assert err <= 2e-5
+
+
+def test_colpiv_qr_solver_rank_diagnostic(sd, capsys):
+    """ColPivHouseholderQRSolver (regressors.hpp:245-306): same solution as the LU solver on regular systems; the numerical rank
+    of the regularised AtA (the diagnostic that solver exists for, :288-293) comes from a diagonally pivoted Cholesky."""
+    rng = np.random.default_rng(3)
+    n, d, m = 600, 300, 5
+    A = rng.random((n, d)).astype(np.float32)
+    A[:, -1] = 1.0
+    B = rng.standard_normal((n, m)).astype(np.float32)
+    lu = sd.LinearRegressor(sd.Regulariser(sd.RegularisationType.Manual, 0.5, True))
+    qr = sd.LinearRegressor(sd.Regulariser(sd.RegularisationType.Manual, 0.5, True), solver=sd.ColPivHouseholderQRSolver())
+    lu.learn(A, B)
+    qr.learn(A, B)
+    assert qr.last_rank == d
+    assert np.array_equal(qr.x.cpu().numpy(), lu.x.cpu().numpy())
+    # rank-deficient: 40 duplicated columns, lambda = 0
+    A2 = A.copy()
+    A2[:, 10:50] = A2[:, 100:140]
+    q0 = sd.LinearRegressor(sd.Regulariser(sd.RegularisationType.Manual, 0.0, True), solver=sd.ColPivHouseholderQRSolver())
+    assert q0.learn(A2, B) is True                      # learn() always returns true (regressors.hpp:349)
+    assert q0.last_rank == d - 40
+    assert f"(The rank is {d - 40}, full rank would be {d}). Increase lambda." in capsys.readouterr().out
+    # ... and regular again once lambda > 0
+    q1 = sd.LinearRegressor(sd.Regulariser(sd.RegularisationType.Manual, 1.0, True), solver=sd.ColPivHouseholderQRSolver())
+    q1.learn(A2, B)
+    assert q1.last_rank == d and np.isfinite(q1.x.cpu().numpy()).all()
+    # small systems (the LU route, D <= 256) report their rank too
+    A3 = rng.random((50, 6)).astype(np.float32)
+    A3[:, 5] = A3[:, 0] + A3[:, 1]
+    q2 = sd.LinearRegressor(sd.Regulariser(), solver=sd.ColPivHouseholderQRSolver())
+    q2.learn(A3, rng.standard_normal((50, 2)).astype(np.float32))
+    assert q2.last_rank == 5
