@@ -257,12 +257,14 @@ def syrk_executed_flops(n, D, M, passes=3):
     return passes * 2.0 * n * tiles * 128 * 256
 
 
-def run_train(sd, ctx, model, world, rank, dev, barrier, max_over_ranks, comm, cfg=None, steps=1, warmup=1, e2e=False, distributed_solve=None):
+def run_train(sd, ctx, model, world, rank, dev, barrier, max_over_ranks, comm, cfg=None, steps=1, warmup=1, e2e=False, distributed_solve=None,
+              solver="cholesky"):
     """Regressor-train seconds (all S levels: HOG + targets + Gram + exchange + solve + update), strong scaling: the SAME global
     training set for every number of ranks (samples are generated by global index)."""
     import torch
     from superviseddescent_b200 import parallel
     cfg = cfg or TRAIN_CFG
+    ctx.set_solver(solver)
     mean, ids, right, left = train_shape_model(cfg, model)
     L = cfg["landmarks"]
     b, e = parallel.shard_range(cfg["n"], world, rank)
@@ -272,7 +274,7 @@ def run_train(sd, ctx, model, world, rank, dev, barrier, max_over_ranks, comm, c
     ht = sd.HogTransform(imgs, hps, ids, right, left, ctx)
     D = ht.feature_length(0)
     S = len(hps)
-    ds = (D >= parallel.DIST_SOLVE_MIN_D) if distributed_solve is None else bool(distributed_solve)
+    ds = ((D >= parallel.DIST_SOLVE_MIN_D) if distributed_solve is None else distributed_solve) if world > 1 else None
     gram_ms = []
 
     def one_run(levels=None):
@@ -309,8 +311,11 @@ def run_train(sd, ctx, model, world, rank, dev, barrier, max_over_ranks, comm, c
                       "landmarks": L, "l2": f"per-level operands ({(e - b) * D * 4 / 1e9:.2f} GB of features, {D * (D + 2 * L) * 4 / 1e9:.2f} GB Gram) exceed the 126 MB L2",
                       "parallelism": (f"samples sharded over {world} GPU(s); per level one exchange of the upper row bands of [AtA|Atb] "
                                       f"({parallel.band_offsets(D, (D + 2 * L + 3) // 4 * 4)[-1] * 4 / 1e9:.2f} of {D * (D + 2 * L) * 4 / 1e9:.2f} GB): "
-                                      + ("reduce to the block-row-cyclic owners + distributed blocked Cholesky (panel broadcast)" if (ds and world > 1)
-                                         else "all-reduce + replicated solve" if world > 1 else "single GPU"))},
+                                      + ("all-reduce + conjugate gradients shared by the ranks (one all-reduce of 2L x D floats per iteration)" if ds == "cg"
+                                         else "reduce to the block-row-cyclic owners + distributed blocked Cholesky (panel broadcast)" if ds
+                                         else "all-reduce + replicated solve" if world > 1 else "single GPU")),
+                      "solver": ("conjugate gradients (tcgen05 3xTF32 products)" if (ds == "cg" or solver == "cg") else "blocked Cholesky"),
+                      "solver_iterations_last_level": ctx.solver_iterations()},
            "gpu_launches": launches,
            "train_residual": {"before": res0, "after": res1},
            "weights_checksum_abs_sum_per_level": checksum,
@@ -357,6 +362,7 @@ def run_train(sd, ctx, model, world, rank, dev, barrier, max_over_ranks, comm, c
         out["e2e"] = {"value": secs2, "unit": "s", "h2d_bytes_per_step": int(h_imgs.numel() + x0.nbytes + x_gt.nbytes),
                       "d2h_bytes_per_step": int(sum(w.numel() * 4 for w in w_host)),
                       "api": "SupervisedDescentOptimiser.train with HogTransform over crops uploaded from pinned host memory; trained weights copied back"}
+    ctx.set_solver("cholesky")
     return out
 
 
@@ -426,9 +432,9 @@ def run_train_workload(args, sd, ctx, model, world, rank, local, dev, barrier, m
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ds = {"auto": None, "replicated": False, "distributed": True}[args.solve]
+    ds = {"auto": None, "replicated": False, "distributed": True, "cg": "cg"}[args.solve]
     line = run_train(sd, ctx, model, world, rank, dev, barrier, max_over_ranks, comm, cfg, steps=args.steps, warmup=args.warmup, e2e=True,
-                     distributed_solve=ds)
+                     distributed_solve=ds, solver="cg" if args.solve == "cg" else "cholesky")
     clocks = sampler.stop() if rank == 0 else None
     if rank != 0:
         return
@@ -638,7 +644,8 @@ def main():
     ap.add_argument("--workload", default="detect", choices=["detect", "train", "train5"],
                     help="detect = configs[2] (the default headline line); train = configs[3] and train5 = configs[4]: regressor-train "
                          "seconds as a first-class line (strong scaling over --gpus)")
-    ap.add_argument("--solve", default="auto", choices=["auto", "replicated", "distributed"], help="multi-GPU solve route of the train workloads")
+    ap.add_argument("--solve", default="auto", choices=["auto", "replicated", "distributed", "cg"],
+                    help="solve route of the train workloads: replicated / distributed blocked Cholesky, or conjugate gradients (cg)")
     ap.add_argument("--batch", type=int, default=4096, help="frames per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

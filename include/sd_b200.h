@@ -234,11 +234,23 @@ SD_API int sd_reduce_scatter_gram(sd_ctx* ctx, sd_comm* comm, float* d_G, int64_
 /* sd_solve_gram on a reduce-scattered d_G; collective, every rank receives X (and the same lambda) */
 SD_API int sd_solve_gram_dist(sd_ctx* ctx, sd_comm* comm, float* d_G, int64_t ldg, int D, int M,
                               const sd_regulariser* reg, int n_train_global, float* d_X, float* lambda_out);
-/* LinearRegressor::learn on sharded rows: local Gram, exchange, solve.  distributed_solve != 0 selects the distributed
- * factorisation (pays from D of a few ten thousand), 0 the replicated one.  N_local may be 0. */
+/* LinearRegressor::learn on sharded rows: local Gram, exchange, solve.  distributed_solve: 0 = all-reduce, every rank solves
+ * alone; 1 = reduce to the panel owners + distributed factorisation; 2 = all-reduce + conjugate gradients shared by the ranks
+ * (see sd_set_solver).  N_local may be 0. */
 SD_API int sd_learn_dist(sd_ctx* ctx, sd_comm* comm, const float* d_A, int64_t lda, const float* d_B, int64_t ldb,
                          int N_local, int D, int M, const sd_regulariser* reg, int n_train_global, int distributed_solve,
                          float* d_X, float* lambda_out);
+
+/* Solver of the systems with D > 256 (smaller ones always take the reference-order partial-pivot LU):
+ *   0 = blocked Cholesky (default): the direct solve that stands in for Eigen::PartialPivLU (regressors.hpp:224-225);
+ *   1 = conjugate gradients on the tensor cores: after the bias column has been eliminated the regularised Gram matrix of the
+ *       centred features is very well conditioned under the MatrixNorm rule (condition number ~ N / 350 for RCR features), so a
+ *       few dozen products with the D x D matrix replace the D^3 / 3 factorisation; it stops at a relative residual of 5e-7 and
+ *       falls back to the Cholesky if the recurrence breaks down or stalls (ill-conditioned systems, tiny lambda).
+ * sd_learn_dist: distributed_solve 2 = the ranks share the CG iterations (rows of the matrix sharded, one all-reduce of
+ * 2L x D floats per iteration).  sd_solver_iterations: CG iterations of the last solve (0 = the factorisation ran). */
+SD_API int sd_set_solver(sd_ctx* ctx, int mode);
+SD_API int sd_solver_iterations(const sd_ctx* ctx);
 
 /* ---- cascade steps: SupervisedDescentOptimiser (superviseddescent.hpp:165-344) ---------- */
 /* b_i = (x_i - x_gt_i) (.) norm(x_i)     (superviseddescent.hpp:199-205) */

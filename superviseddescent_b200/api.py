@@ -63,6 +63,16 @@ class Context:
         """0 = 3xTF32 tensor-core Gram (default), 3 = unbiased 3xTF32, 1 = single-pass TF32, 2 = fp32 SIMT."""
         _check(self._h, _capi.lib().sd_set_gram_mode(self._h, int(mode)))
 
+    def set_solver(self, mode) -> None:
+        """Solver of systems with D > 256: 0 / "cholesky" = blocked Cholesky (default), 1 / "cg" = conjugate gradients on the
+        tensor cores (falls back to the Cholesky if they stall)."""
+        m = {"cholesky": 0, "cg": 1}.get(mode, mode)
+        _check(self._h, _capi.lib().sd_set_solver(self._h, int(m)))
+
+    def solver_iterations(self) -> int:
+        """CG iterations of the last solve (0: the factorisation ran)."""
+        return int(_capi.lib().sd_solver_iterations(self._h))
+
     def solver_timings(self):
         out = (C.c_float * 4)()
         _check(self._h, _capi.lib().sd_solver_timings(self._h, out))
@@ -440,7 +450,8 @@ class SupervisedDescentOptimiser:
         """superviseddescent.hpp:165-219.  Multi-GPU: pass `comm` (a parallel.Communicator) or a torch.distributed `group`
         (a communicator is then made from it) -- each rank passes its own shard of rows; per level the C ABI does ONE exchange of
         [AtA | Atb] and the solve.  distributed_solve: None = by size (parallel.DIST_SOLVE_MIN_D), True = reduce-scatter +
-        distributed blocked Cholesky, False = all-reduce + replicated solve."""
+        distributed blocked Cholesky, False = all-reduce + replicated solve, "cg" = all-reduce + conjugate gradients shared by the
+        ranks."""
         from . import parallel
         ctx = self._ctx()
         lib = _capi.lib()
@@ -464,7 +475,10 @@ class SupervisedDescentOptimiser:
             lam = C.c_float(0)
             rc_ = reg.regulariser.c()
             if distributed:
-                ds = (D >= parallel.DIST_SOLVE_MIN_D) if distributed_solve is None else bool(distributed_solve)
+                if distributed_solve is None:
+                    ds = 1 if D >= parallel.DIST_SOLVE_MIN_D else 0
+                else:
+                    ds = 2 if distributed_solve == "cg" else int(bool(distributed_solve))
                 _check(ctx.h, lib.sd_learn_dist(ctx.h, comm.h, ptr(A), C.c_int64(A.stride(0)), ptr(Bv), C.c_int64(A.stride(0)), n, D, P,
                                                 C.byref(rc_), n_global, int(ds), ptr(X), C.byref(lam)))
             else:

@@ -128,6 +128,7 @@ int sd_ctx_create(int device, void* stream, sd_ctx** out)
          cudaMemset(ctx->d_scratch, 0, 4096) == cudaSuccess;
     if (!ok) { sd_ctx_destroy(ctx); return SD_ERR_CUDA; }
     { const char* e = getenv("SD_B200_NO_ROI"); ctx->disable_roi = e && e[0] == '1'; }
+    { const char* e = getenv("SD_B200_SOLVER"); if (e && e[0] == 'c' && e[1] == 'g') ctx->solver_mode = 1; }
     *out = ctx;
     return SD_OK;
 }
@@ -238,6 +239,15 @@ int sd_set_gram_mode(sd_ctx* ctx, int mode)
     ctx->gram_mode = mode;
     return SD_OK;
 }
+
+int sd_set_solver(sd_ctx* ctx, int mode)
+{
+    if (!ctx || mode < 0 || mode > 1) return SD_ERR_INVALID;
+    ctx->solver_mode = mode;
+    return SD_OK;
+}
+
+int sd_solver_iterations(const sd_ctx* ctx) { return ctx ? ctx->cg_iterations : 0; }
 
 int sd_solver_timings(sd_ctx* ctx, float ms_out[4])
 {

@@ -1,0 +1,258 @@
+// Conjugate-gradient solve of the regularised normal equations on the tensor cores (optional route of sd_solve_gram).
+//
+// After the bias column has been eliminated first (sd_linalg.cu, bias_extract_kernel) the system matrix is the Gram matrix of
+// the CENTRED features plus lambda I.  With the reference's MatrixNorm rule lambda = 1.5 ||A^T A||_F / N is of the size of the
+// largest eigenvalues, so the matrix is very well conditioned: measured condition number 3.5 at N = 900 samples, 10.5 at 3,600
+// (it grows like N: ~30 for config 4, a few hundred for config 5).  CG then needs a few dozen iterations of
+//     Q = S P   (one skinny product with the D x D matrix: 2 D^2 2L flops, the tcgen05 TN-GEMM of sd_gram_tc.cu)
+// instead of the D^3/3 factorisation whose chain of D dependent pivots does not parallelise -- and the product shards over
+// GPUs by rows of S with one small all-reduce (2L x D floats) per iteration, which the factorisation cannot.
+//
+// All 2L right-hand sides advance in lockstep (independent CG recurrences sharing the product).  Reductions are two-stage with a
+// fixed order, so the result is reproducible.  If the recurrence breaks down (p^T S p <= 0: not positive definite) or does not
+// reach the tolerance, the caller falls back to the blocked Cholesky: the upper triangle of S and the right-hand sides are never
+// modified here (only the unused lower triangle is filled with the mirror image).
+#include "sd_internal.cuh"
+
+#include <cstdlib>
+
+namespace {
+
+constexpr int CG_BX = 64, CG_BY = 4;           // block: 64 column lanes x 4 row lanes
+constexpr int CG_G = 3;                        // column groups per thread: up to 192 right-hand sides (2L = 136 for 68 landmarks)
+constexpr int CG_MAXCOLS = CG_BX * CG_G;
+
+// G[k][j] = G[j][k] for j < k, rows k in [k0, k1): the product needs whole rows of the symmetric matrix
+__global__ void __launch_bounds__(256) cg_mirror_kernel(float* __restrict__ G, long long ldg, int n, int k0, int k1)
+{
+    __shared__ float tile[32][33];
+    const int tk = k0 / 32 * 32 + blockIdx.y * 32;      // tile of destination rows
+    const int tj = blockIdx.x * 32;                     // tile of destination columns
+    if (tj > tk + 31 || tk >= k1) return;               // entirely above the diagonal / outside the slab
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < 32; r += 8) {                  // read G[tj + r][tk + tx] (upper triangle), coalesced along tk
+        const int j = tj + r, k = tk + tx;
+        tile[r][tx] = (j < n && k < n && j <= k) ? G[(long long)j * ldg + k] : 0.f;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {                  // write G[tk + r][tj + tx]
+        const int k = tk + r, j = tj + tx;
+        if (k >= k0 && k < k1 && k < n && j < k) G[(long long)k * ldg + j] = tile[tx][r];
+    }
+}
+
+struct CgBuf {
+    float *X, *R, *P, *Qt;
+    double *part;          // [2][nblk][CG_MAXCOLS]
+    float *rs;             // [2][CG_MAXCOLS] ping-pong r.r
+    float *bb;             // [CG_MAXCOLS]   b.b
+    float *conv;           // [0] max_c sqrt(rs / bb) of the latest iteration; [1] breakdown flag
+    int nblk;
+};
+
+// folds the CG_BY row lanes of a block and stores the block's partial sums
+__device__ __forceinline__ void cg_store_partials(const double (&acc)[CG_G], double* __restrict__ dst)
+{
+    __shared__ double red[CG_BY][CG_MAXCOLS];
+#pragma unroll
+    for (int g = 0; g < CG_G; ++g) red[threadIdx.y][threadIdx.x + g * CG_BX] = acc[g];
+    __syncthreads();
+    if (threadIdx.y == 0)
+#pragma unroll
+        for (int g = 0; g < CG_G; ++g) {
+            const int c = threadIdx.x + g * CG_BX;
+            dst[c] = red[0][c] + red[1][c] + red[2][c] + red[3][c];
+        }
+}
+
+// R = P = B (the right-hand-side columns of G), X = 0, partial sums of b.b
+__global__ void __launch_bounds__(CG_BX * CG_BY) cg_init_kernel(const float* __restrict__ G, long long ldg, int n, int col0, int M, int Mp, CgBuf b)
+{
+    double acc[CG_G] = {};
+    for (int i = blockIdx.x * CG_BY + threadIdx.y; i < n; i += gridDim.x * CG_BY)
+#pragma unroll
+        for (int g = 0; g < CG_G; ++g) {
+            const int c = threadIdx.x + g * CG_BX;
+            if (c < Mp) {
+                const float v = c < M ? G[(long long)i * ldg + col0 + c] : 0.f;
+                b.R[(long long)i * Mp + c] = v;
+                b.P[(long long)i * Mp + c] = v;
+                b.X[(long long)i * Mp + c] = 0.f;
+                acc[g] += (double)v * (double)v;
+            }
+        }
+    cg_store_partials(acc, b.part + (long long)blockIdx.x * CG_MAXCOLS);
+}
+
+// rs[0] = bb = sum of the partials (one block)
+__global__ void cg_init_finish_kernel(CgBuf b, int M)
+{
+    const int c = threadIdx.x;
+    if (c >= CG_MAXCOLS) return;
+    double s = 0.0;
+    for (int k = 0; k < b.nblk; ++k) s += b.part[(long long)k * CG_MAXCOLS + c];
+    b.rs[c] = c < M ? (float)s : 0.f;
+    b.bb[c] = c < M ? (float)s : 0.f;
+    if (c == 0) { b.conv[0] = 1.f; b.conv[1] = 0.f; }
+}
+
+// partial[blk][c] = sum_i P[i][c] * Qt[c][i]
+__global__ void __launch_bounds__(CG_BX * CG_BY) cg_dot_kernel(CgBuf b, int n, int M, int Mp, long long ldq)
+{
+    double acc[CG_G] = {};
+    for (int i = blockIdx.x * CG_BY + threadIdx.y; i < n; i += gridDim.x * CG_BY)
+#pragma unroll
+        for (int g = 0; g < CG_G; ++g) {
+            const int c = threadIdx.x + g * CG_BX;
+            if (c < M) acc[g] += (double)b.P[(long long)i * Mp + c] * (double)b.Qt[(long long)c * ldq + i];
+        }
+    cg_store_partials(acc, b.part + (long long)blockIdx.x * CG_MAXCOLS);
+}
+
+// alpha = rs / (p.q) (every block sums the partials in the same order); X += alpha P; R -= alpha Q; partials of r.r
+__global__ void __launch_bounds__(CG_BX * CG_BY) cg_update_xr_kernel(CgBuf b, int n, int M, int Mp, long long ldq, int parity)
+{
+    __shared__ float s_alpha[CG_MAXCOLS];
+    for (int c = threadIdx.y * CG_BX + threadIdx.x; c < CG_MAXCOLS; c += CG_BX * CG_BY) {
+        double pq = 0.0;
+        for (int k = 0; k < b.nblk; ++k) pq += b.part[(long long)k * CG_MAXCOLS + c];
+        const float rs = b.rs[parity * CG_MAXCOLS + c];
+        float alpha = 0.f;
+        if (c < M && rs > 0.f) {
+            if (pq > 0.0) alpha = (float)((double)rs / pq);
+            else if (blockIdx.x == 0) b.conv[1] = 1.f;                    // p^T S p <= 0: the matrix is not positive definite
+        }
+        s_alpha[c] = alpha;
+    }
+    __syncthreads();
+    double acc[CG_G] = {};
+    for (int i = blockIdx.x * CG_BY + threadIdx.y; i < n; i += gridDim.x * CG_BY)
+#pragma unroll
+        for (int g = 0; g < CG_G; ++g) {
+            const int c = threadIdx.x + g * CG_BX;
+            if (c < M) {
+                const float alpha = s_alpha[c];
+                const long long o = (long long)i * Mp + c;
+                b.X[o] = fmaf(alpha, b.P[o], b.X[o]);
+                const float r = fmaf(-alpha, b.Qt[(long long)c * ldq + i], b.R[o]);
+                b.R[o] = r;
+                acc[g] += (double)r * (double)r;
+            }
+        }
+    cg_store_partials(acc, b.part + ((long long)b.nblk + blockIdx.x) * CG_MAXCOLS);
+}
+
+// beta = rs_new / rs; P = R + beta P; block 0 publishes rs_new and the convergence measure
+__global__ void __launch_bounds__(CG_BX * CG_BY) cg_update_p_kernel(CgBuf b, int n, int M, int Mp, int parity)
+{
+    __shared__ float s_beta[CG_MAXCOLS];
+    __shared__ float s_rel[CG_MAXCOLS];
+    for (int c = threadIdx.y * CG_BX + threadIdx.x; c < CG_MAXCOLS; c += CG_BX * CG_BY) {
+        double rn = 0.0;
+        for (int k = 0; k < b.nblk; ++k) rn += b.part[((long long)b.nblk + k) * CG_MAXCOLS + c];
+        const float rs = b.rs[parity * CG_MAXCOLS + c];
+        s_beta[c] = (c < M && rs > 0.f) ? (float)(rn / (double)rs) : 0.f;
+        const float bbv = b.bb[c];
+        s_rel[c] = (c < M && bbv > 0.f) ? sqrtf((float)rn / bbv) : 0.f;
+        if (blockIdx.x == 0) b.rs[(parity ^ 1) * CG_MAXCOLS + c] = c < M ? (float)rn : 0.f;
+    }
+    __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.y == 0 && threadIdx.x == 0) {
+        float m = 0.f;
+        for (int k = 0; k < CG_MAXCOLS; ++k) m = fmaxf(m, s_rel[k]);
+        b.conv[0] = m;
+    }
+    for (int i = blockIdx.x * CG_BY + threadIdx.y; i < n; i += gridDim.x * CG_BY)
+#pragma unroll
+        for (int g = 0; g < CG_G; ++g) {
+            const int c = threadIdx.x + g * CG_BX;
+            if (c < Mp) {
+                const long long o = (long long)i * Mp + c;
+                b.P[o] = fmaf(s_beta[c], b.P[o], b.R[o]);
+            }
+        }
+}
+
+}  // namespace
+
+// Solves S W = B for the n x n symmetric matrix whose upper triangle sits in G (pitch ldg) and whose M right-hand sides are the
+// columns [col0, col0 + M) of the same rows.  W: n x Mp row-major (Mp = M rounded up to 4) in *W_out (workspace owned by ctx).
+// Returns SD_OK when converged (iterations in *iters), SD_ERR_NUMERIC when the caller should fall back to the factorisation.
+int sd_cg_solve(sd_ctx* ctx, sd_comm* comm, float* G, int64_t ldg, int n, int col0, int M, float** W_out, int* ldw_out, int* iters)
+{
+    SD_REQUIRE(ctx, M >= 1 && M <= CG_MAXCOLS && n >= 1, "CG route: 1..192 right-hand sides");
+    const int Mp = (M + 3) / 4 * 4;
+    const int64_t ldq = ((int64_t)n + 3) / 4 * 4;
+    const int nranks = sd_comm_size_of(comm), me = sd_comm_rank_of(comm);
+    CgBuf b;
+    b.nblk = 2 * ctx->sm_count;
+    const size_t vec = (size_t)n * Mp;
+    const size_t floats = 3 * vec + (size_t)M * ldq + 4 * CG_MAXCOLS + 64;
+    const size_t bytes = floats * sizeof(float) + (size_t)2 * b.nblk * CG_MAXCOLS * sizeof(double) + 256;
+    char* ws = (char*)sd_workspace(ctx, SD_WS_CG, bytes);
+    if (!ws) return SD_ERR_CUDA;
+    b.part = reinterpret_cast<double*>(ws);
+    float* f = reinterpret_cast<float*>(ws + (size_t)2 * b.nblk * CG_MAXCOLS * sizeof(double));
+    b.X = f; b.R = f + vec; b.P = f + 2 * vec; b.Qt = f + 3 * vec;
+    float* tail = b.Qt + (size_t)M * ldq;
+    tail = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tail) + 15) & ~(uintptr_t)15);
+    b.rs = tail; b.bb = tail + 2 * CG_MAXCOLS; b.conv = tail + 3 * CG_MAXCOLS;
+
+    // this rank's slab of the contraction (rows of S), multiples of 16 rows
+    int k0 = 0, k1 = n;
+    if (nranks > 1) {
+        const int per = (sd_div_up(n, nranks) + 15) / 16 * 16;
+        k0 = me * per < n ? me * per : n;
+        k1 = (me + 1) * per < n ? (me + 1) * per : n;
+    }
+    const dim3 blk(CG_BX, CG_BY);
+    if (k1 > k0) {
+        const dim3 mg(sd_div_up(n, 32), sd_div_up(k1 - k0 / 32 * 32, 32));
+        cg_mirror_kernel<<<mg, 256, 0, ctx->stream>>>(G, ldg, n, k0, k1);
+        SD_LAUNCH_CHECK(ctx, "cg_mirror_kernel");
+    }
+    cg_init_kernel<<<b.nblk, blk, 0, ctx->stream>>>(G, ldg, n, col0, M, Mp, b);
+    SD_LAUNCH_CHECK(ctx, "cg_init_kernel");
+    cg_init_finish_kernel<<<1, 256, 0, ctx->stream>>>(b, M);
+    SD_LAUNCH_CHECK(ctx, "cg_init_finish_kernel");
+
+    static const float tol = getenv("SD_B200_CG_TOL") ? (float)atof(getenv("SD_B200_CG_TOL")) : 5e-7f;
+    static const int max_iter = getenv("SD_B200_CG_MAXIT") ? atoi(getenv("SD_B200_CG_MAXIT")) : 600;
+    // split the contraction in two when one pass of tiles would leave more than half of the SMs idle
+    const int tiles = sd_div_up(n, 256) * sd_div_up(M, 128);
+    const int ksplit = (nranks == 1 && 2 * tiles <= ctx->sm_count) ? 2 : 1;
+    float* h_conv = reinterpret_cast<float*>(reinterpret_cast<char*>(ctx->h_scratch) + 192);
+    int it = 0, rc = SD_OK;
+    bool converged = false;
+    for (; it < max_iter && !converged; ++it) {
+        const int parity = it & 1;
+        if (ksplit > 1 || k1 <= k0) SD_CUDA(ctx, cudaMemsetAsync(b.Qt, 0, (size_t)M * ldq * sizeof(float), ctx->stream));
+        if (k1 > k0) {
+            // Qt[M x n] = P[k0:k1, :]^T S[k0:k1, :]   ( = (S P)^T summed over the ranks' slabs: S is symmetric )
+            rc = sd_gemm_tn_tc(ctx, b.P + (size_t)k0 * Mp, Mp, G + (size_t)k0 * ldg, ldg, k1 - k0, M, n, b.Qt, ldq, 1.0f,
+                               ksplit > 1 ? 1.0f : 0.0f, 3, true, false, nullptr, ksplit);
+            if (rc) return rc;
+        }
+        if (nranks > 1) {
+            rc = sd_comm_allreduce_f32(ctx, comm, b.Qt, (size_t)M * ldq, ctx->stream);
+            if (rc) return rc;
+        }
+        cg_dot_kernel<<<b.nblk, blk, 0, ctx->stream>>>(b, n, M, Mp, ldq);
+        SD_LAUNCH_CHECK(ctx, "cg_dot_kernel");
+        cg_update_xr_kernel<<<b.nblk, blk, 0, ctx->stream>>>(b, n, M, Mp, ldq, parity);
+        SD_LAUNCH_CHECK(ctx, "cg_update_xr_kernel");
+        cg_update_p_kernel<<<b.nblk, blk, 0, ctx->stream>>>(b, n, M, Mp, parity);
+        SD_LAUNCH_CHECK(ctx, "cg_update_p_kernel");
+        if (it >= 5 && (it % 3) == 2) {                  // look at the residual every third iteration
+            SD_CUDA(ctx, cudaMemcpyAsync(h_conv, b.conv, 2 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+            SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            if (h_conv[1] != 0.f || !(h_conv[0] == h_conv[0])) { if (iters) *iters = it + 1; return SD_ERR_NUMERIC; }
+            converged = h_conv[0] <= tol;
+        }
+    }
+    if (iters) *iters = it;
+    if (!converged) return SD_ERR_NUMERIC;
+    *W_out = b.X;
+    *ldw_out = Mp;
+    return SD_OK;
+}

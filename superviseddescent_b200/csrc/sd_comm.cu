@@ -134,6 +134,13 @@ int sd_comm_allreduce_f64(sd_ctx* ctx, sd_comm* c, double* d_buf, size_t count, 
     return SD_OK;
 }
 
+int sd_comm_allreduce_f32(sd_ctx* ctx, sd_comm* c, float* d_buf, size_t count, cudaStream_t stream)
+{
+    if (!c || c->nranks == 1 || count == 0) return SD_OK;
+    SD_NCCL(ctx, nccl().AllReduce(d_buf, d_buf, count, ncclFloat32, ncclSum, c->comm, stream));
+    return SD_OK;
+}
+
 namespace {
 
 constexpr int kBand = 256;   // == one Cholesky panel (two 128-blocks): the ownership unit of sd_solve_gram_dist

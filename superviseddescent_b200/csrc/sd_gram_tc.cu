@@ -164,7 +164,9 @@ struct TcArgs {
     int passes;          // 1 or 3
     int unbiased;        // round hi in place (slower, unbiased) instead of using the truncated raw tile
     const int2* tiles;   // (ti, tj) per tile
-    int num_tiles;
+    int num_tiles;       // work items = tiles x ksplit
+    int ksplit, kps;     // the K loop of every tile is cut into ksplit ranges of kps pipeline stages (work item t: tile t / ksplit,
+                         // range t % ksplit); ksplit > 1 needs the reduce-add write-back onto a zeroed C
     int tma_c;           // 0 = register epilogue, 1 = TMA store (beta == 0), 2 = TMA reduce-add (beta == 1)
 };
 
@@ -248,9 +250,10 @@ syrk_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             if (elect_one_sync()) {
                 uint32_t stage = 0, phase = 0;
                 for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
-                    const int2 tile = a.tiles[t];
+                    const int2 tile = a.tiles[t / a.ksplit];
                     const int i0 = tile.x * BM, j0 = tile.y * BN;
-                    for (int kb = 0; kb < num_k; ++kb) {
+                    const int kb0 = (t % a.ksplit) * a.kps, kb1 = min(num_k, kb0 + a.kps);
+                    for (int kb = kb0; kb < kb1; ++kb) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         mbar_arrive_expect_tx(&raw_full[stage], RAW_BYTES);
                         unsigned char* sa = smem + stage * STAGE_BYTES;
@@ -269,9 +272,10 @@ syrk_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             uint32_t stage = 0, phase = 0;
             uint32_t buf = 0, buf_phase = 0;
             for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
-                for (int kb = 0; kb < num_k; ++kb) {
-                    const bool chunk_first = (kb % KC_STAGES) == 0;
-                    const bool chunk_last = (kb % KC_STAGES) == KC_STAGES - 1 || kb == num_k - 1;
+                const int kb0 = (t % a.ksplit) * a.kps, kb1 = min(num_k, kb0 + a.kps);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    const bool chunk_first = ((kb - kb0) % KC_STAGES) == 0;
+                    const bool chunk_last = ((kb - kb0) % KC_STAGES) == KC_STAGES - 1 || kb == kb1 - 1;
                     if (chunk_first) {
                         mbar_wait(&tmem_empty[buf], buf_phase ^ 1);
                         tcgen05_fence_after();
@@ -312,7 +316,8 @@ syrk_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             const int tt = threadIdx.x - 128;                 // 0..127
             uint32_t stage = 0, phase = 0;
             for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
-                for (int kb = 0; kb < num_k; ++kb) {
+                const int kb0 = (t % a.ksplit) * a.kps, kb1 = min(num_k, kb0 + a.kps);
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&raw_full[stage], phase);
                     const uint32_t raw = smem_u32(smem + stage * STAGE_BYTES) + tt * 16;
                     const uint32_t lo = raw + RAW_BYTES;
@@ -354,9 +359,10 @@ syrk_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         const int half = (warp - 8) >> 2;
         uint32_t buf = 0, buf_phase = 0;
         const bool vec_ok = (a.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.C) & 15) == 0);
-        const int num_chunks = (num_k + KC_STAGES - 1) / KC_STAGES;
         for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
-            const int2 tile = a.tiles[t];
+            const int2 tile = a.tiles[t / a.ksplit];
+            const int kb0 = (t % a.ksplit) * a.kps, kb1 = min(num_k, kb0 + a.kps);
+            const int num_chunks = (kb1 - kb0 + KC_STAGES - 1) / KC_STAGES;
             const int i = tile.x * BM + q * 32 + lane;
             const int j0 = tile.y * BN + half * 128;
             float acc[128];
@@ -521,7 +527,7 @@ bool sd_syrk_tc_supported(const float* d_S, int64_t lds, int K, int MI, int NJ, 
 // its own output columns) -- the in-place block-row solve of the Cholesky relies on that.
 int sd_gemm_tn_tc(sd_ctx* ctx, const float* d_SA, int64_t lda, const float* d_SB, int64_t ldb, int K, int MI, int NJ,
                   float* d_C, int64_t ldc, float alpha, float beta, int passes, bool unbiased_split, bool upper_only,
-                  const sd_row_filter* rows)
+                  const sd_row_filter* rows, int ksplit)
 {
     if (MI <= 0 || NJ <= 0 || K <= 0) return SD_OK;
     SD_REQUIRE(ctx, passes == 1 || passes == 3, "passes must be 1 or 3");
@@ -551,7 +557,12 @@ int sd_gemm_tn_tc(sd_ctx* ctx, const float* d_SA, int64_t lda, const float* d_SB
     TcArgs a;
     a.K = K; a.MI = MI; a.NJ = NJ; a.C = d_C; a.ldc = ldc; a.alpha = alpha; a.beta = beta; a.passes = passes;
     a.unbiased = (ctx->gram_mode == 3 || unbiased_split) ? 1 : 0;
-    a.tiles = d_tiles; a.num_tiles = (int)tiles.size();
+    const int num_k = sd_div_up(K, BK);
+    if (ksplit < 1) ksplit = 1;
+    if (ksplit > num_k) ksplit = num_k;
+    a.kps = sd_div_up(num_k, ksplit);
+    a.ksplit = sd_div_up(num_k, a.kps);                   // every range non-empty
+    a.tiles = d_tiles; a.num_tiles = (int)tiles.size() * a.ksplit;
     const int sms = ctx->sm_count - ctx->syrk_sm_reserve > 0 ? ctx->sm_count - ctx->syrk_sm_reserve : 1;
     const int grid = a.num_tiles < sms ? a.num_tiles : sms;
     // C goes back through the TMA when it can be described by a tensor map (16-byte aligned base and pitch)
@@ -562,6 +573,8 @@ int sd_gemm_tn_tc(sd_ctx* ctx, const float* d_SA, int64_t lda, const float* d_SB
         if (rc) return rc;
         a.tma_c = beta == 1.f ? 2 : 1;
     }
+    // split K: the ranges of one tile add into C in any order, which is only reproducible for two of them (a + b == b + a)
+    SD_REQUIRE(ctx, a.ksplit == 1 || (a.tma_c == 2 && a.ksplit == 2), "split-K needs beta == 1, the TMA reduce-add write-back and two ranges");
     SD_CUDA(ctx, cudaFuncSetAttribute(syrk_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
     syrk_tc2_kernel<<<grid, T2_THREADS, SMEM2_BYTES, ctx->stream>>>(map_a, map_b, map_c, a);
     SD_LAUNCH_CHECK(ctx, "syrk_tc2_kernel");

@@ -16,7 +16,7 @@
 #define SD_MAX_BINS 16   // undirected orientations K supported by the HOG kernel
 
 enum { SD_WS_GRAM_EXT = 0, SD_WS_FEATURES, SD_WS_SCRATCH, SD_WS_DIAGINV,
-       SD_WS_PARTIAL, SD_WS_GEOM, SD_WS_GEMM_PARTIAL, SD_WS_DIAGINV2, SD_WS_PANEL, SD_WS_BIAS, SD_WS_COUNT };
+       SD_WS_PARTIAL, SD_WS_GEOM, SD_WS_GEMM_PARTIAL, SD_WS_DIAGINV2, SD_WS_PANEL, SD_WS_BIAS, SD_WS_CG, SD_WS_COUNT };
 
 // Block-row ownership of a distributed factorisation: global row r of the matrix belongs to rank (r / block) % nranks.
 // first_row = global row of the first row of the C sub-matrix a kernel is launched on.
@@ -41,6 +41,8 @@ struct sd_ctx {
     int64_t launches = 0;
     int sm_count = 148;
     int gram_mode = 0;
+    int solver_mode = 0;           // systems with D > 256: 0 = blocked Cholesky, 1 = conjugate gradients (Cholesky if they stall)
+    int cg_iterations = 0;         // of the last solve (0: the factorisation ran)
     bool disable_roi = false;      // sd_detect_batch_host: always upload whole frames
     int64_t roi_fallbacks = 0;     // faces repeated from the full frame because a patch left its ROI
     float timings[4] = {0, 0, 0, 0};
@@ -102,7 +104,7 @@ int sd_syrk_tc(sd_ctx* ctx, const float* d_S, int64_t lds, int K, int MI, int NJ
 // C = beta*C + alpha * SA^T SB on the tensor cores (SA: K x MI, SB: K x NJ, row-major); see sd_gram_tc.cu
 int sd_gemm_tn_tc(sd_ctx* ctx, const float* d_SA, int64_t lda, const float* d_SB, int64_t ldb, int K, int MI, int NJ,
                   float* d_C, int64_t ldc, float alpha, float beta, int passes, bool unbiased_split, bool upper_only,
-                  const sd_row_filter* rows = nullptr);
+                  const sd_row_filter* rows = nullptr, int ksplit = 1);
 bool sd_syrk_tc_supported(const float* d_S, int64_t lds, int K, int MI, int NJ, const float* d_C, int64_t ldc);
 
 int sd_check_hog_status(sd_ctx* ctx, const char* what);   // sd_api.cu: synchronises, reports and clears the projection's flags
@@ -117,6 +119,9 @@ int sd_comm_bcast(sd_ctx* ctx, sd_comm* c, float* d_buf, size_t count, int root,
 int sd_comm_group_start(sd_ctx* ctx);
 int sd_comm_group_end(sd_ctx* ctx);
 int sd_comm_allreduce_f64(sd_ctx* ctx, sd_comm* c, double* d_buf, size_t count, cudaStream_t stream);
+int sd_comm_allreduce_f32(sd_ctx* ctx, sd_comm* c, float* d_buf, size_t count, cudaStream_t stream);
+// conjugate gradients on the tensor cores (sd_cg.cu); SD_ERR_NUMERIC = did not converge, use the factorisation
+int sd_cg_solve(sd_ctx* ctx, sd_comm* comm, float* G, int64_t ldg, int n, int col0, int M, float** W_out, int* ldw_out, int* iters);
 // true when sd_reduce_scatter_gram leaves the rows block-row-cyclic (large, 16-byte aligned systems); smaller ones are all-reduced
 bool sd_gram_is_scattered(int D, int64_t ldg, const float* d_G);
 

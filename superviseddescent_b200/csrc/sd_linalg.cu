@@ -510,14 +510,15 @@ __global__ void __launch_bounds__(256) bias_downdate_kernel(float* __restrict__ 
     }
 }
 
-// X[0..D-2] = w (columns 1..M of Xp; column 0 is the solve of the carried bias column), X[D-1] = (rb - s^T w) / pivot
-__global__ void __launch_bounds__(256) bias_finish_kernel(const float* __restrict__ Xp, int D, int M, const double* __restrict__ sv,
-                                                          float* __restrict__ X)
+// X[0..D-2] = w = columns [wcol0, wcol0 + M) of Xp (pitch ldw; after the factorisation column 0 is the solve of the carried bias
+// column), X[D-1] = (rb - s^T w) / pivot
+__global__ void __launch_bounds__(256) bias_finish_kernel(const float* __restrict__ Xp, int ldw, int wcol0, int D, int M,
+                                                          const double* __restrict__ sv, float* __restrict__ X)
 {
     const int c = blockIdx.x;
     if (c < M) {
         double acc = 0.0;
-        for (int i = threadIdx.x; i < D - 1; i += 256) acc += sv[i] * (double)Xp[(long long)i * (M + 1) + 1 + c];
+        for (int i = threadIdx.x; i < D - 1; i += 256) acc += sv[i] * (double)Xp[(long long)i * ldw + wcol0 + c];
         __shared__ double red[256];
         red[threadIdx.x] = acc;
         __syncthreads();
@@ -531,7 +532,7 @@ __global__ void __launch_bounds__(256) bias_finish_kernel(const float* __restric
         for (long long idx = (long long)(blockIdx.x - M) * 256 + threadIdx.x; idx < total; idx += (long long)(gridDim.x - M) * 256) {
             const long long r = idx / M;
             const int cc = (int)(idx - r * M);
-            X[idx] = Xp[r * (M + 1) + 1 + cc];
+            X[idx] = Xp[r * ldw + wcol0 + cc];
         }
     }
 }
@@ -1343,8 +1344,11 @@ int sd_gram(sd_ctx* ctx, const float* d_A, int64_t lda, const float* d_B, int64_
     return sd_syrk_update(ctx, S, lds, N, D, D + M, d_G, ldg, 1.0f, 0.0f);
 }
 
+// route: 0 = every rank holds the summed G (one GPU, or after sd_allreduce_gram) and solves it alone;
+//        1 = G is reduce-scattered over comm: distributed blocked Cholesky;
+//        2 = every rank holds the summed G and the ranks share the CG iterations (contraction sharded, one small all-reduce each)
 static int solve_gram_impl(sd_ctx* ctx, sd_comm* comm, float* d_G, int64_t ldg, int D, int M, const sd_regulariser* reg,
-                           int n_train_global, float* d_X, float* lambda_out, int* rank_out = nullptr)
+                           int n_train_global, float* d_X, float* lambda_out, int* rank_out = nullptr, int route = 0)
 {
     if (!ctx) return SD_ERR_INVALID;
     SD_REQUIRE(ctx, d_G && d_X && reg && D >= 1 && M >= 1 && ldg >= D + M, "bad argument");
@@ -1352,7 +1356,7 @@ static int solve_gram_impl(sd_ctx* ctx, sd_comm* comm, float* d_G, int64_t ldg, 
     SD_REQUIRE(ctx, n_train_global >= 1, "n_train_global must be >= 1");
     // the distributed factorisation needs whole panels per rank; small systems were all-reduced and are solved replicated
     const int nranks = sd_comm_size_of(comm);
-    const bool dist = nranks > 1 && sd_gram_is_scattered(D, ldg, d_G);
+    const bool dist = route == 1 && nranks > 1 && sd_gram_is_scattered(D, ldg, d_G);
     float* scal = reinterpret_cast<float*>(ctx->d_scratch) + 16;
     double* partial = reinterpret_cast<double*>(reinterpret_cast<char*>(ctx->d_scratch) + 1024);   // up to 384 doubles
     // errors belong to the call that caused them: HOG status bits raised earlier were reported by their own entry points
@@ -1405,10 +1409,29 @@ static int solve_gram_impl(sd_ctx* ctx, sd_comm* comm, float* d_G, int64_t ldg, 
         }
         bias_downdate_kernel<<<4 * ctx->sm_count, 256, 0, ctx->stream>>>(d_G, ldg, D, M, sv, 2 * kCholNb, nr, me);
         SD_LAUNCH_CHECK(ctx, "bias_downdate_kernel");
-        rc = cholesky_solve(ctx, d_G, ldg, D - 1, M + 1, Xp, dist ? comm : nullptr);
-        if (rc) return rc;
-        bias_finish_kernel<<<M + 2 * ctx->sm_count, 256, 0, ctx->stream>>>(Xp, D, M, sv, d_X);
-        SD_LAUNCH_CHECK(ctx, "bias_finish_kernel");
+        bool solved = false;
+        ctx->cg_iterations = 0;
+        if (!dist && (ctx->solver_mode == 1 || route == 2) && M <= 192) {
+            // conjugate gradients on the (well conditioned) centred system; falls back to the factorisation when it stalls
+            float* W = nullptr;
+            int ldw = 0, its = 0;
+            rc = sd_cg_solve(ctx, route == 2 ? comm : nullptr, d_G, ldg, D - 1, D, M, &W, &ldw, &its);
+            ctx->cg_iterations = its;
+            if (rc == SD_OK) {
+                SD_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
+                bias_finish_kernel<<<M + 2 * ctx->sm_count, 256, 0, ctx->stream>>>(W, ldw, 0, D, M, sv, d_X);
+                SD_LAUNCH_CHECK(ctx, "bias_finish_kernel");
+                solved = true;
+            } else if (rc != SD_ERR_NUMERIC) {
+                return rc;
+            }
+        }
+        if (!solved) {
+            rc = cholesky_solve(ctx, d_G, ldg, D - 1, M + 1, Xp, dist ? comm : nullptr);
+            if (rc) return rc;
+            bias_finish_kernel<<<M + 2 * ctx->sm_count, 256, 0, ctx->stream>>>(Xp, M + 1, 1, D, M, sv, d_X);
+            SD_LAUNCH_CHECK(ctx, "bias_finish_kernel");
+        }
     }
     SD_CUDA(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
     if (lambda_out) {
@@ -1434,7 +1457,7 @@ int sd_solve_gram_dist(sd_ctx* ctx, sd_comm* comm, float* d_G, int64_t ldg, int 
 {
     if (!ctx) return SD_ERR_INVALID;
     SD_REQUIRE(ctx, comm != nullptr, "no communicator");
-    return solve_gram_impl(ctx, comm, d_G, ldg, D, M, reg, n_train_global, d_X, lambda_out);
+    return solve_gram_impl(ctx, comm, d_G, ldg, D, M, reg, n_train_global, d_X, lambda_out, nullptr, 1);
 }
 
 int sd_learn_dist(sd_ctx* ctx, sd_comm* comm, const float* d_A, int64_t lda, const float* d_B, int64_t ldb, int N_local, int D, int M,
@@ -1450,14 +1473,15 @@ int sd_learn_dist(sd_ctx* ctx, sd_comm* comm, const float* d_A, int64_t lda, con
     if (N_local > 0) rc = sd_gram(ctx, d_A, lda, d_B, ldb, N_local, D, M, G, ldg);
     else rc = sd_check_cuda(ctx, cudaMemsetAsync(G, 0, (size_t)D * ldg * sizeof(float), ctx->stream), "memset(G)");
     if (rc) return rc;
-    if (distributed_solve) {
+    if (distributed_solve == 1) {
         rc = sd_reduce_scatter_gram(ctx, comm, G, ldg, D, M);
         if (rc) return rc;
         return sd_solve_gram_dist(ctx, comm, G, ldg, D, M, reg, n_train_global, d_X, lambda_out);
     }
     rc = sd_allreduce_gram(ctx, comm, G, ldg, D, M);
     if (rc) return rc;
-    return sd_solve_gram(ctx, G, ldg, D, M, reg, n_train_global, d_X, lambda_out);
+    // 2: the ranks share the CG iterations; 0: every rank solves alone (factorisation, or CG if sd_set_solver chose it)
+    return solve_gram_impl(ctx, comm, G, ldg, D, M, reg, n_train_global, d_X, lambda_out, nullptr, distributed_solve == 2 ? 2 : 0);
 }
 
 int sd_learn_rank_revealing(sd_ctx* ctx, const float* d_A, int64_t lda, const float* d_B, int64_t ldb, int N, int D, int M,

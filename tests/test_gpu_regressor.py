@@ -239,3 +239,52 @@ def test_colpiv_qr_solver_rank_diagnostic(sd, capsys):
     q2 = sd.LinearRegressor(sd.Regulariser(), solver=sd.ColPivHouseholderQRSolver())
     q2.learn(A3, rng.standard_normal((50, 2)).astype(np.float32))
     assert q2.last_rank == 5
+
+
+def test_conjugate_gradient_route_matches_the_factorisation(sd):
+    """sd_set_solver(1): CG on the tensor cores for the centred, MatrixNorm-regularised system (well conditioned) must give the
+    weights of the blocked Cholesky; an ill-conditioned system (tiny manual lambda) must fall back to the factorisation."""
+    ctx = sd.default_context()
+    A = _features_like(np.random.default_rng(31), 2500, 1800)
+    B = (0.05 * np.random.default_rng(32).standard_normal((2500, 44))).astype(np.float32)
+    reg = sd.Regulariser(sd.RegularisationType.MatrixNorm, 1.5, False)
+    chol = sd.LinearRegressor(reg)
+    chol.learn(A, B)
+    assert ctx.solver_iterations() == 0
+    ctx.set_solver("cg")
+    try:
+        cg = sd.LinearRegressor(reg)
+        cg.learn(A, B)
+        its = ctx.solver_iterations()
+        e = rel_err(cg.x.cpu().numpy(), chol.x.cpu().numpy())
+        A64 = A.astype(np.float64)
+        G = A64.T @ A64
+        lam = 1.5 * np.linalg.norm(G) / A.shape[0]
+        R = np.eye(G.shape[0]) * lam
+        R[-1, -1] = 0
+        Xt = np.linalg.solve(G + R, A64.T @ B.astype(np.float64))
+        print(f"CG: {its} iterations; weights vs Cholesky {e:.2e}; vs float64 CG {rel_err(cg.x.cpu().numpy(), Xt):.2e} / Cholesky {rel_err(chol.x.cpu().numpy(), Xt):.2e}; {ctx.solver_timings()}")
+        assert 3 <= its <= 200
+        assert e <= 2e-5
+        assert rel_err(cg.x.cpu().numpy(), Xt) <= 1e-4
+        # 136 right-hand sides (68 landmarks): two tile rows of the product
+        B2 = (0.05 * np.random.default_rng(33).standard_normal((2500, 136))).astype(np.float32)
+        cg2 = sd.LinearRegressor(reg)
+        cg2.learn(A, B2)
+        assert ctx.solver_iterations() >= 3
+        ctx.set_solver("cholesky")
+        ch2 = sd.LinearRegressor(reg)
+        ch2.learn(A, B2)
+        assert rel_err(cg2.x.cpu().numpy(), ch2.x.cpu().numpy()) <= 2e-5
+        # tiny lambda: condition number ~1e6, CG stalls -> the factorisation answers
+        ctx.set_solver("cg")
+        hard = sd.LinearRegressor(sd.Regulariser(sd.RegularisationType.Manual, 1e-4, True))
+        hard.learn(A, B)
+        ctx.set_solver("cholesky")
+        ref = sd.LinearRegressor(sd.Regulariser(sd.RegularisationType.Manual, 1e-4, True))
+        ref.learn(A, B)
+        assert np.isfinite(hard.x.cpu().numpy()).all()
+        pa, pb = A @ hard.x.cpu().numpy(), A @ ref.x.cpu().numpy()
+        assert rel_err(pa, pb) <= 1e-3
+    finally:
+        ctx.set_solver("cholesky")

@@ -4,7 +4,7 @@
 set -e
 cd "$(dirname "$0")/../superviseddescent_b200"
 mkdir -p build_prof lib_prof
-for f in sd_api sd_hog sd_linalg sd_gram_tc sd_model sd_comm sd_rank; do
+for f in sd_api sd_hog sd_linalg sd_gram_tc sd_model sd_comm sd_rank sd_cg; do
   nvcc -gencode arch=compute_100a,code=sm_100a -std=c++17 -O3 -lineinfo -DSD_PROFILE_POTRF \
        -Xcompiler -fPIC,-fvisibility=hidden -I ../include -I csrc -c csrc/$f.cu -o build_prof/$f.o &
 done
