@@ -85,7 +85,17 @@ typedef struct {
     int64_t offset;              /* byte offset of the ROI's first pixel from d_data */
 } sd_roi;
 
-/* A batch of equally sized 8UC1 images resident on the device. */
+/* One frame of a batch whose frames differ in size (the reference's HogTransform takes a std::vector<cv::Mat> of arbitrary
+ * sizes: rcr-train and examples/landmark_detection.cpp train on photographs of different resolutions). */
+typedef struct {
+    int32_t width, height;       /* defines where the zero padding of a patch starts for THIS frame */
+    int32_t row_stride;          /* bytes */
+    int32_t reserved;
+    int64_t offset;              /* byte offset of the frame's first pixel from d_data */
+} sd_frame;
+
+/* A batch of 8UC1 images resident on the device: equally sized (width/height/strides below), or -- d_frames != NULL -- one
+ * descriptor per frame. */
 typedef struct {
     const uint8_t* d_data;
     int32_t width, height;       /* frame size: defines where the zero padding of a patch starts */
@@ -97,6 +107,9 @@ typedef struct {
      * (sd_detect_batch_host then repeats that face from the full frame). */
     const sd_roi* d_roi;
     uint8_t* d_roi_miss;
+    /* Optional (NULL = equally sized frames): per-frame size / pitch / position; width, height, row_stride and image_stride
+     * above are then ignored.  Not combinable with d_roi. */
+    const sd_frame* d_frames;
 } sd_image_batch;
 
 /* ---- context --------------------------------------------------------------------------- */

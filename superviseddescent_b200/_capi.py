@@ -35,7 +35,13 @@ class NormalisationC(C.Structure):
 
 class ImageBatchC(C.Structure):
     _fields_ = [("d_data", C.c_void_p), ("width", C.c_int32), ("height", C.c_int32), ("row_stride", C.c_int32),
-                ("image_stride", C.c_int64), ("count", C.c_int32), ("d_roi", C.c_void_p), ("d_roi_miss", C.c_void_p)]
+                ("image_stride", C.c_int64), ("count", C.c_int32), ("d_roi", C.c_void_p), ("d_roi_miss", C.c_void_p),
+                ("d_frames", C.c_void_p)]
+
+
+class FrameC(C.Structure):
+    """sd_frame: one frame of a batch with differently sized frames."""
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("row_stride", C.c_int32), ("reserved", C.c_int32), ("offset", C.c_int64)]
 
 
 # every symbol declared in include/sd_b200.h (tests/test_abi.py checks the list against the header)

@@ -328,19 +328,46 @@ class HogTransform:
     def __init__(self, images, hog_params: Sequence[HoGParam], model_landmarks_list: Sequence[str],
                  right_eye_identifiers: Sequence[str], left_eye_identifiers: Sequence[str], ctx: Optional[Context] = None):
         self.ctx = ctx or default_context()
-        imgs = images if isinstance(images, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(images))
-        if imgs.dim() == 2:
-            imgs = imgs.unsqueeze(0)
-        if imgs.dtype == torch.uint8 and imgs.dim() == 4 and imgs.shape[3] == 3:
-            imgs = bgr2gray(imgs, self.ctx)
-        if imgs.dtype != torch.uint8 or imgs.dim() != 3:
-            raise ValueError("images must be (count, H, W) uint8 or (count, H, W, 3) uint8")
-        self.images = imgs.to(f"cuda:{self.ctx.device}").contiguous()
+        self.frames = None
+        if isinstance(images, (list, tuple)) and len({np.asarray(im).shape for im in images}) > 1:
+            # frames of different sizes (the reference takes a std::vector<cv::Mat>): packed back to back, rows 16-byte aligned,
+            # with one sd_frame descriptor each
+            recs, chunks, off = [], [], 0
+            for im in images:
+                a = np.ascontiguousarray(im, dtype=np.uint8)
+                if a.ndim == 3 and a.shape[2] == 3:
+                    a = bgr2gray(a[None], self.ctx)[0].cpu().numpy()
+                if a.ndim != 2:
+                    raise ValueError("every image must be (H, W) uint8 or (H, W, 3) uint8")
+                h, w = a.shape
+                stride = (w + 15) // 16 * 16
+                buf = np.zeros((h, stride), dtype=np.uint8)
+                buf[:, :w] = a
+                recs.append((w, h, stride, 0, off))
+                chunks.append(buf.reshape(-1))
+                off += h * stride
+            self.images = torch.from_numpy(np.concatenate(chunks)).to(f"cuda:{self.ctx.device}")
+            table = np.array(recs, dtype=[("w", "<i4"), ("h", "<i4"), ("s", "<i4"), ("r", "<i4"), ("o", "<i8")])
+            self.frames = torch.from_numpy(table.view(np.uint8).copy()).to(f"cuda:{self.ctx.device}")
+            self.frame_count = len(recs)
+        else:
+            if isinstance(images, (list, tuple)):
+                images = np.stack([np.asarray(im) for im in images])
+            imgs = images if isinstance(images, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(images))
+            if imgs.dim() == 2:
+                imgs = imgs.unsqueeze(0)
+            if imgs.dtype == torch.uint8 and imgs.dim() == 4 and imgs.shape[3] == 3:
+                imgs = bgr2gray(imgs, self.ctx)
+            if imgs.dtype != torch.uint8 or imgs.dim() != 3:
+                raise ValueError("images must be (count, H, W) uint8, (count, H, W, 3) uint8, or a list of such frames of any sizes")
+            self.images = imgs.to(f"cuda:{self.ctx.device}").contiguous()
         self.hog_params = list(hog_params)
         self.norm = InterEyeDistanceNormalisation(model_landmarks_list, right_eye_identifiers, left_eye_identifiers)
         self.num_landmarks = len(self.norm.model_landmarks_list)
 
     def batch(self) -> ImageBatchC:
+        if self.frames is not None:
+            return ImageBatchC(C.c_void_p(self.images.data_ptr()), 0, 0, 0, 0, self.frame_count, None, None, C.c_void_p(self.frames.data_ptr()))
         n, h, w = self.images.shape
         return ImageBatchC(C.c_void_p(self.images.data_ptr()), w, h, self.images.stride(1), self.images.stride(0), n)
 

@@ -37,6 +37,7 @@ struct HogArgs {
     int image_count;
     const int* image_index;
     const sd_roi* roi;          // optional: only a region of every frame is resident
+    const sd_frame* frames;     // optional: frames of different sizes
     uint8_t* roi_miss;
     const float* x;
     long long ldx;
@@ -268,8 +269,14 @@ __global__ void __launch_bounds__(kHogThreads) hog_patch_kernel(const HogArgs a,
         if (tid == 0 && a.status) atomicOr(a.status, 2);
     }
     // resident region of this frame: the whole frame, or the ROI that sd_detect_batch_host uploaded
-    int rx = 0, ry = 0, rw = a.width, rh = a.height, rs = a.row_stride;
+    int W = a.width, H = a.height, rs = a.row_stride;
     const uint8_t* __restrict__ img = a.images + (long long)img_idx * a.image_stride;
+    if (a.frames) {
+        const sd_frame f = a.frames[img_idx];
+        W = f.width; H = f.height; rs = f.row_stride;
+        img = a.images + f.offset;
+    }
+    int rx = 0, ry = 0, rw = W, rh = H;
     if (a.roi) {
         const sd_roi r = a.roi[img_idx];
         rx = r.x; ry = r.y; rw = r.w; rh = r.h; rs = r.row_stride;
@@ -284,7 +291,6 @@ __global__ void __launch_bounds__(kHogThreads) hog_patch_kernel(const HogArgs a,
     // ---- S1: zero-padded crop + fixed-point bilinear resize.  The P x P source window is staged in shared memory with its
     //      zero padding materialised, then resampled from there: one output row per warp pass, lanes along x.
     const int x0 = cx - half, y0 = cy - half;
-    const int W = a.width, H = a.height;
     uint8_t* s_stage = smem + lay.bin;                             // [bin | r1] are dead until S2
     const int stage_cap = lay.xofs - lay.bin;
     // TMA route: whole frames resident and describable by a tensor map; the smallest box class that covers the window and
@@ -628,6 +634,8 @@ int launch_hog(sd_ctx* ctx, const sd_image_batch* images, const int32_t* d_image
     a.image_index = d_image_index;
     a.roi = images->d_roi;
     a.roi_miss = images->d_roi_miss;
+    a.frames = images->d_frames;
+    SD_REQUIRE(ctx, !(images->d_roi && images->d_frames), "d_roi and d_frames cannot be combined");
     if (!d_image_index) SD_REQUIRE(ctx, images->count >= N, "fewer images than samples and no image index");
     a.x = d_x; a.ldx = ldx; a.N = N; a.L = L;
     a.variant = p->variant; a.nc = p->num_cells; a.cs = p->cell_size; a.K = p->num_bins; a.fs = fs;
@@ -682,7 +690,7 @@ int launch_hog(sd_ctx* ctx, const sd_image_batch* images, const int32_t* d_image
     HogMaps maps;
     memset(&maps, 0, sizeof(maps));
     a.tma_class = -1;
-    if (!images->d_roi && (reinterpret_cast<uintptr_t>(images->d_data) & 15) == 0 && (images->row_stride % 16) == 0 &&
+    if (!images->d_roi && !images->d_frames && (reinterpret_cast<uintptr_t>(images->d_data) & 15) == 0 && (images->row_stride % 16) == 0 &&
         (images->image_stride % 16) == 0 && (images->count == 1 || images->image_stride > 0) && !getenv("SD_B200_HOG_NO_TMA")) {
         PFN_hogEncodeTiled enc = hog_encode_fn();
         if (enc) {

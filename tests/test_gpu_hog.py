@@ -138,3 +138,28 @@ def test_fixed_patch_hog_transform_vs_oracle(sd, oracle, variant, nc, cs, K):
     assert np.array_equal(one, got[2])
     with pytest.raises(Exception):
         sd.FixedHogTransform(imgs, variant, nc, 11, K)(x, 0)
+
+
+def test_hog_frames_of_different_sizes(sd, oracle, golden):
+    """The reference's HogTransform takes a std::vector<cv::Mat> of arbitrary sizes (rcr-train reads photographs of different
+    resolutions): a list of differently sized frames goes through per-frame descriptors (sd_frame) and must give, frame by
+    frame, what the oracle gives -- including patches that hang over each frame's OWN border."""
+    m = oracle.Model(golden.model_path)
+    sizes = [(120, 160), (97, 131), (200, 150), (64, 64)]
+    frames = [synth.smooth_images(1, h, w, seed=40 + i)[0] for i, (h, w) in enumerate(sizes)]
+    boxes = [(10, 8, 90, 90), (40, 20, 80, 80), (-20, 60, 120, 120), (5, 5, 50, 50)]
+    x = np.stack([oracle.align_mean(m.mean, b) for b in boxes]).astype(np.float32)
+    for cs, rel, K in ((11, 1.0, 4), (6, 0.25, 9)):
+        hp, ohp = sd.HoGParam(1, 5, cs, K, rel), oracle.HogParam(1, 5, cs, K, rel)
+        ht = sd.HogTransform(frames, [hp], m.landmark_ids, m.right_ids, m.left_ids)
+        A = ht(x, 0).cpu().numpy()
+        geo, patches, bins = ht.debug(x, 0)
+        for i, f in enumerate(frames):
+            ref = oracle.hog_transform(f, x[i], ohp, m.right_idx, m.left_idx)
+            assert rel_err(A[i], ref) <= TOL, (i, cs)
+            cxs, cys, half = oracle.patch_geometry(x[i], ohp, m.right_idx, m.left_idx)
+            for l in range(len(m.landmark_ids)):
+                want = oracle.resize_linear_u8(oracle.crop_patch_u8(f, int(cxs[l]), int(cys[l]), int(half[l])), 5 * cs, 5 * cs)
+                assert np.array_equal(patches[i, l].cpu().numpy(), want), (i, l, cs)    # integer result: bit exact
+    with pytest.raises(ValueError):
+        sd.HogTransform([frames[0], np.zeros((3, 4, 5, 6), np.uint8)], [hp], m.landmark_ids, m.right_ids, m.left_ids)
