@@ -48,7 +48,7 @@ struct HogArgs {
     const float* mag_lut;       // gx*gx + gy*gy -> sqrtf of it (the exact integer's correctly rounded root)
     const int* rtab;            // per sample: resize tables [5][fs] (hog_geometry_kernel)
     const float* btab;          // per launch: spatial binning weights [nc][fs], then lo[nc], hi[nc] (hog_bintab_kernel)
-    int tma_class;              // -1: window staged by load loops; else index of the first usable tensor-map size class
+    int tma_count;              // number of usable tensor-map size classes (0: the window is staged by load loops)
     float* A;
     long long ld;
     int* geometry;
@@ -296,11 +296,9 @@ __global__ void __launch_bounds__(kHogThreads) hog_patch_kernel(const HogArgs a,
     // TMA route: whole frames resident and describable by a tensor map; the smallest box class that covers the window and
     // fits the staging area
     int tma_box = 0;
-    if (a.tma_class >= 0) {
 #pragma unroll
-        for (int c = kTmaClasses - 1; c >= 0; --c)
-            if (c >= a.tma_class && hog_tma_box(c) >= P && hog_tma_box(c) * hog_tma_box(c) <= stage_cap) tma_box = hog_tma_box(c);
-    }
+    for (int c = kTmaClasses - 1; c >= 0; --c)
+        if (c < a.tma_count && hog_tma_box(c) >= P && hog_tma_box(c) * hog_tma_box(c) <= stage_cap) tma_box = hog_tma_box(c);
     if (tma_box > 0 && tid == 0) {
         // one elected thread: the box lands densely (pitch = box width); bytes outside the frame are zero-filled by the TMA,
         // which is exactly copyMakeBorder(..., BORDER_CONSTANT, 0) (adaptive_vlhog.hpp:136-147)
@@ -405,6 +403,7 @@ __global__ void __launch_bounds__(kHogThreads) hog_patch_kernel(const HogArgs a,
             }
         } else {
             // window too large for the staging area: sample straight from global memory with full checks
+            __syncthreads();                                       // tables visible
             for (int dy = warp; dy < fs; dy += kHogWarps) {
                 const short2 yb = s_yb[dy];
                 const int iy0 = y0 + s_yofs0[dy], iy1 = y0 + s_yofs1[dy];
@@ -689,13 +688,14 @@ int launch_hog(sd_ctx* ctx, const sd_image_batch* images, const int32_t* d_image
     // tensor maps of the frame batch for the TMA staging route: whole frames resident, 16-byte aligned base and pitches
     HogMaps maps;
     memset(&maps, 0, sizeof(maps));
-    a.tma_class = -1;
+    a.tma_count = 0;
     if (!images->d_roi && !images->d_frames && (reinterpret_cast<uintptr_t>(images->d_data) & 15) == 0 && (images->row_stride % 16) == 0 &&
         (images->image_stride % 16) == 0 && (images->count == 1 || images->image_stride > 0) && !getenv("SD_B200_HOG_NO_TMA")) {
         PFN_hogEncodeTiled enc = hog_encode_fn();
         if (enc) {
             bool ok = true;
             for (int c = 0; c < kTmaClasses && ok; ++c) {
+                if (hog_tma_box(c) > 256) break;
                 cuuint64_t gdim[3] = {(cuuint64_t)images->width, (cuuint64_t)images->height, (cuuint64_t)images->count};
                 cuuint64_t gstride[2] = {(cuuint64_t)images->row_stride, (cuuint64_t)(images->count > 1 ? images->image_stride : (int64_t)images->row_stride * images->height)};
                 if (gstride[1] % 16) gstride[1] = (gstride[1] + 15) / 16 * 16;
@@ -704,8 +704,8 @@ int launch_hog(sd_ctx* ctx, const sd_image_batch* images, const int32_t* d_image
                 ok = enc(&maps.m[c], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(images->d_data), gdim, gstride, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+                if (ok) a.tma_count = c + 1;               // classes are usable up to the first one the driver refuses
             }
-            if (ok) a.tma_class = 0;
         }
     }
 
