@@ -35,6 +35,23 @@ def test_detect_example_frames_match_reference_goldens(sd, oracle, golden):
         assert np.max(np.abs(m.detect(gray, init) - ref)) <= 1e-4 * np.max(np.abs(ref))
 
 
+def _rounding_margin(oracle, om, image, x):
+    """Smallest distance to a rounding tie (crop centres: cvRound; half patch size: std::round of rel * IED / 2) met by the
+    oracle's cascade on this face."""
+    margin = 1.0
+    x = np.asarray(x, dtype=np.float32).copy()
+    for level in range(om.num_levels):
+        hp = om.hog_params[level]
+        margin = min(margin, float(np.min(np.abs(np.abs(x - np.floor(x)) - 0.5))))
+        ied = oracle.get_ied(x, om.right_idx, om.left_idx)
+        h = float(np.float32(hp.relative_patch_size)) * ied / 2.0
+        margin = min(margin, abs(abs(h - np.floor(h)) - 0.5))
+        feat = oracle.hog_transform(image, x, hp, om.right_idx, om.left_idx)
+        upd = oracle.predict(feat.reshape(1, -1), om.weights[level]).ravel()
+        x = (x - upd * np.float32(1.0 / np.float32(1.0 / ied))).astype(np.float32)
+    return margin
+
+
 def test_detect_batch_host_and_device_paths(sd, oracle, golden):
     """End-to-end cascade on seeded synthetic frames (25 % of the boxes hang over the border).
 
@@ -52,7 +69,15 @@ def test_detect_batch_host_and_device_paths(sd, oracle, golden):
     got = m.detect_batch(images, boxes)
     per_face = np.max(np.abs(got - ref), axis=1) / np.max(np.abs(ref))
     print("batch host path: per-face rel err", np.sort(per_face)[::-1][:5], "faces within 1e-4:", int((per_face <= 1e-4).sum()), "of", len(per_face))
-    assert (per_face <= 1e-4).sum() >= 0.8 * len(per_face)
+    # every face must agree to 1e-4 -- unless it is PROVEN to sit on a rounding boundary: replaying the oracle's cascade level by
+    # level, some crop centre (cvRound) or half patch size (std::round) of that face lies within 5e-5 px of a tie, where a
+    # difference in the seventh digit legitimately moves a whole patch by one pixel
+    flipped = [i for i in range(len(per_face)) if per_face[i] > 1e-4]
+    for i in flipped:
+        near = _rounding_margin(oracle, om, images[i], np.asarray(oracle.align_mean(om.mean, boxes[i])))
+        print(f"face {i}: rel err {per_face[i]:.2e}, closest rounding margin over the cascade {near:.2e}")
+        assert near <= 5e-5, f"face {i} differs by {per_face[i]:.2e} without sitting on a rounding boundary"
+    assert len(flipped) <= 2
     assert np.max(np.abs(got - ref)) <= 1.0          # a flipped rounding moves a landmark by well under a pixel
     x0 = np.stack([sd.align_mean(m.get_mean(), b) for b in boxes])
     assert np.array_equal(x0, np.stack([oracle.align_mean(om.mean, b) for b in boxes]))
