@@ -128,6 +128,8 @@ int sd_ctx_create(int device, void* stream, sd_ctx** out)
          cudaMemset(ctx->d_scratch, 0, 4096) == cudaSuccess;
     if (!ok) { sd_ctx_destroy(ctx); return SD_ERR_CUDA; }
     { const char* e = getenv("SD_B200_NO_ROI"); ctx->disable_roi = e && e[0] == '1'; }
+    { const char* e = getenv("SD_B200_HOST_ROUTE"); if (e) ctx->host_route = (e[0] == 'p') ? 1 : 0; }
+    { const char* e = getenv("SD_B200_PACK_THREADS"); if (e && atoi(e) >= 1 && atoi(e) <= 64) ctx->pack_threads = atoi(e); }
     { const char* e = getenv("SD_B200_SOLVER"); if (e && e[0] == 'c' && e[1] == 'g') ctx->solver_mode = 1; }
     *out = ctx;
     return SD_OK;
@@ -147,6 +149,8 @@ void sd_ctx_destroy(sd_ctx* ctx)
         if (ctx->stage_done[i]) cudaEventDestroy(ctx->stage_done[i]);
     }
     for (int i = 0; i < 6; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->pack_pool) sd_pack_pool_destroy(ctx->pack_pool);
+    for (int i = 0; i < 2; ++i) if (ctx->h_stage[i]) cudaFreeHost(ctx->h_stage[i]);
     if (ctx->h_scratch) cudaFreeHost(ctx->h_scratch);
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);

@@ -58,7 +58,13 @@ struct sd_ctx {
     size_t stage_bytes[2] = {0, 0};
     cudaEvent_t stage_ev[2] = {nullptr, nullptr};
     cudaEvent_t stage_done[2] = {nullptr, nullptr};
+    // "pack" staging route of sd_detect_batch_host: pinned buffers + host copy threads (sd_model.cu)
+    int host_route = 0;            // 0 = gather (zero-copy kernel), 1 = pack (host threads + one copy-engine transfer per chunk)
+    int pack_threads = 8;
+    void* h_stage[2] = {nullptr, nullptr};
+    struct sd_pack_pool* pack_pool = nullptr;
 };
+void sd_pack_pool_destroy(struct sd_pack_pool* p);
 
 int sd_fail(sd_ctx* ctx, int code, const char* fmt, ...);
 int sd_check_cuda(sd_ctx* ctx, cudaError_t e, const char* what);
