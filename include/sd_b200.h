@@ -139,6 +139,7 @@ SD_API int sd_memset(sd_ctx* ctx, void* d_dst, int value, size_t bytes);
  * bytes, pitches in bytes; async on the context's stream */
 SD_API int sd_memcpy2d_h2d(sd_ctx* ctx, void* d_dst, size_t dst_pitch, const void* h_src, size_t src_pitch, size_t row_bytes, size_t rows);
 SD_API int sd_memcpy2d_d2h(sd_ctx* ctx, void* h_dst, size_t dst_pitch, const void* d_src, size_t src_pitch, size_t row_bytes, size_t rows);
+SD_API int sd_memcpy2d_d2d(sd_ctx* ctx, void* d_dst, size_t dst_pitch, const void* d_src, size_t src_pitch, size_t row_bytes, size_t rows);
 
 /* ---- projection h: rcr::HogTransform::operator() batched (adaptive_vlhog.hpp:109-185) -- */
 /* D = L * num_cells^2 * (3K+4 | 4K) + 1 */

@@ -230,6 +230,14 @@ int sd_memcpy2d_d2h(sd_ctx* ctx, void* h_dst, size_t dst_pitch, const void* d_sr
     return SD_OK;
 }
 
+int sd_memcpy2d_d2d(sd_ctx* ctx, void* d_dst, size_t dst_pitch, const void* d_src, size_t src_pitch, size_t row_bytes, size_t rows)
+{
+    if (!ctx) return SD_ERR_INVALID;
+    if (rows == 0 || row_bytes == 0) return SD_OK;
+    SD_CUDA(ctx, cudaMemcpy2DAsync(d_dst, dst_pitch, d_src, src_pitch, row_bytes, rows, cudaMemcpyDeviceToDevice, ctx->stream));
+    return SD_OK;
+}
+
 int sd_memset(sd_ctx* ctx, void* d_dst, int value, size_t bytes)
 {
     if (!ctx) return SD_ERR_INVALID;

@@ -88,6 +88,23 @@ public:
         want_callback = true;
     }
 
+    // Multi-GPU (one process per GPU, each passing ITS shard of the rows): the optional communicator of the C ABI.  Per level
+    // the local [AtA | Atb] is exchanged and solved by sd_learn_dist; every rank ends with the same regressors.  route: 0 =
+    // all-reduce + every rank solves, 1 = reduce to the panel owners + distributed Cholesky, 2 = all-reduce + CG shared by the
+    // ranks.  The callback receives the rows of ALL ranks (superviseddescent.hpp:217).
+    template <class ProjectionFunction, class OnTrainingEpochCallback>
+    void train(cv::Mat parameters, cv::Mat initialisations, cv::Mat templates, ProjectionFunction projection,
+               OnTrainingEpochCallback on_training_epoch_callback, sd_comm* communicator, int route = 0)
+    {
+        static_assert(detail::is_device_projection<ProjectionFunction>::value && detail::has_c_normalisation<NormalisationStrategy>::value &&
+                          detail::is_device_regressor<RegressorType>::value,
+                      "multi-GPU training needs the device route (HogTransform projection, device regressors)");
+        comm = communicator;
+        comm_route = route;
+        train_impl(parameters, initialisations, templates, projection, on_training_epoch_callback, std::true_type());
+        comm = nullptr;
+    }
+
     // superviseddescent.hpp:165-219
     template <class ProjectionFunction, class OnTrainingEpochCallback>
     void train(cv::Mat parameters, cv::Mat initialisations, cv::Mat templates, ProjectionFunction projection,
@@ -181,6 +198,9 @@ private:
         return x_k;
     }
 
+    sd_comm* comm = nullptr;     // set for the duration of a multi-GPU train()
+    int comm_route = 0;
+
     // ------------------------------------------------------------------ device route
     template <class P, class CB>
     void train_impl(cv::Mat parameters, cv::Mat initialisations, cv::Mat templates, P projection, CB cb, std::true_type)
@@ -192,6 +212,9 @@ private:
         sd_b200::upload(initialisations, d_cur, Pd);
         const sd_normalisation norm = normalisation_strategy.c_normalisation();
         sd_b200::DeviceBuffer A, G, X;
+        int64_t n_global = n;
+        const int nranks = comm ? sd_comm_size(comm) : 1;
+        if (nranks > 1) sd_b200::check(ctx, sd_comm_sum_int64(ctx, comm, &n_global), "sd_comm_sum_int64");
         for (size_t level = 0; level < regressors.size(); ++level) {
             const int D = projection.feature_length(level);
             const int64_t ld = (static_cast<int64_t>(D) + Pd + 3) / 4 * 4;
@@ -205,12 +228,38 @@ private:
             sd_b200::check(ctx, sd_cascade_targets(ctx, d_cur.as<float>(), d_gt.as<float>(), n, Pd, &norm, B, ld), "sd_cascade_targets");
             X.allocate(static_cast<size_t>(D) * Pd * sizeof(float));                                          // 3) :207
             const sd_regulariser reg = regressors[level].get_regulariser().c();
-            sd_b200::check(ctx, sd_learn(ctx, A.as<float>(), ld, B, ld, n, D, Pd, &reg, X.as<float>(), nullptr), "sd_learn");
+            if (nranks > 1)
+                sd_b200::check(ctx, sd_learn_dist(ctx, comm, A.as<float>(), ld, B, ld, n, D, Pd, &reg, static_cast<int>(n_global), comm_route, X.as<float>(), nullptr), "sd_learn_dist");
+            else
+                sd_b200::check(ctx, sd_learn(ctx, A.as<float>(), ld, B, ld, n, D, Pd, &reg, X.as<float>(), nullptr), "sd_learn");
             regressors[level].set_x(sd_b200::download(X.as<float>(), D, Pd, Pd));
             regressors[level].report_solver();
             sd_b200::check(ctx, sd_cascade_update(ctx, A.as<float>(), ld, n, D, X.as<float>(), Pd, d_cur.as<float>(), &norm, d_next.as<float>()), "sd_cascade_update");   // 4) :209-215
             std::swap(d_cur, d_next);
-            if (want_callback) cb(sd_b200::download(d_cur.as<float>(), n, Pd, Pd));                          // 5) :217
+            if (want_callback) {                                                                             // 5) :217
+                if (nranks > 1) {
+                    // every rank contributes its rows; shards are padded to the largest one for the gather
+                    int64_t most = n;
+                    std::vector<int64_t> counts(nranks, 0);
+                    for (int r = 0; r < nranks; ++r) {
+                        int64_t v = (r == sd_comm_rank(comm)) ? n : 0;
+                        sd_b200::check(ctx, sd_comm_sum_int64(ctx, comm, &v), "sd_comm_sum_int64");
+                        counts[r] = v;
+                        most = v > most ? v : most;
+                    }
+                    const size_t row_bytes = static_cast<size_t>(Pd) * sizeof(float);
+                    sd_b200::DeviceBuffer send(static_cast<size_t>(most) * row_bytes), recv(static_cast<size_t>(most) * row_bytes * nranks);
+                    sd_b200::check(ctx, sd_memset(ctx, send.as<float>(), 0, static_cast<size_t>(most) * row_bytes), "gather");
+                    sd_b200::check(ctx, sd_memcpy2d_d2d(ctx, send.as<float>(), row_bytes, d_cur.as<float>(), row_bytes, row_bytes, n), "gather");
+                    sd_b200::check(ctx, sd_comm_allgather(ctx, comm, send.as<float>(), static_cast<size_t>(most) * row_bytes, recv.as<float>()), "sd_comm_allgather");
+                    cv::Mat all;
+                    for (int r = 0; r < nranks; ++r)
+                        if (counts[r] > 0) all.push_back(sd_b200::download(recv.as<float>() + static_cast<size_t>(r) * most * Pd, static_cast<int>(counts[r]), Pd, Pd));
+                    cb(all);
+                } else {
+                    cb(sd_b200::download(d_cur.as<float>(), n, Pd, Pd));
+                }
+            }
         }
     }
 

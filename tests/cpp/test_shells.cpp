@@ -169,6 +169,20 @@ static void test_rcr_device_route(const char* model_path)
     Mat dev = sdo.test(x0, Mat(), hog);
     Mat host = sdo.test(x0, Mat(), [&](Mat row, size_t level, int idx) { return hog(row, level, idx); });
     EXPECT_REL(0.0, cv::norm(dev, host, cv::NORM_L2) / cv::norm(dev, cv::NORM_L2), 1e-3);   // tol * max(|e|,1e-3) = 1e-6
+    // the multi-GPU overload with a one-rank communicator must give the same model (the exchange degenerates; two and more
+    // ranks are covered by tests/test_gpu_multi.py)
+    {
+        sd_comm* comm = nullptr;
+        sd_b200::check(sd_b200::context(), sd_comm_create(sd_b200::context(), nullptr, 0, 1, &comm), "sd_comm_create");
+        std::vector<LinearRegressor<VerbosePartialPivLUSolver>> regs2{LinearRegressor<VerbosePartialPivLUSolver>(reg), LinearRegressor<VerbosePartialPivLUSolver>(reg)};
+        detection_model::model_type sdo2(regs2, InterEyeDistanceNormalisation(ids, reye, leye));
+        int seen_rows = 0;
+        sdo2.train(x_gt, x0, Mat(), hog, [&](const Mat& cur) { seen_rows = cur.rows; }, comm, 0);
+        sd_comm_destroy(comm);
+        Mat dev2 = sdo2.test(x0, Mat(), hog);
+        EXPECT_REL(0.0, cv::norm(dev, dev2, cv::NORM_L2) / cv::norm(dev, cv::NORM_L2), 1e-3);
+        if (seen_rows != n) { std::printf("FAIL communicator route: callback saw %d rows\n", seen_rows); ++failures; }
+    }
     // assemble a detection_model from the trained parts and run it
     detection_model trained(sdo, mean, ids, hp, reye, leye);
     auto lms = trained.detect(images[0], cv::Rect(20, 18, 110, 110));
