@@ -12,6 +12,6 @@ ncu --set full --clock-control none --import-source on -k regex:predict_rows_ker
     python bench.py --no-cpu --no-train --steps 1 --warmup 1 --batch 2048 > gpurun_out/r02_prof_predict.log 2>&1
 LEVELS=1 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/r02_launches_train.csv \
     python tools/train_once.py > gpurun_out/r02_prof_train.log 2>&1
-LEVELS=1 ncu --set full --clock-control none --import-source on -k regex:syrk_tc2_kernel -s 1 -c 1 -o gpurun_out/r02_syrk \
+LEVELS=1 ncu --set full --clock-control none --import-source on -k regex:syrk_tc2_kernel -s 0 -c 1 -o gpurun_out/r02_syrk \
     python tools/train_once.py > gpurun_out/r02_prof_syrk.log 2>&1
 ls -la gpurun_out | tail -12
