@@ -154,6 +154,21 @@ def run_reference(args):
     if rank != 0:
         return
     cores = host_cores()
+    if args.workload != "detect":
+        # regressor-train seconds of the reference's CPU path: one level on a bounded sample, scaled (see cpu_train_level_seconds)
+        cfg = TRAIN_CFGS[args.workload]
+        n_cpu = min(cfg["n"], 10000) if cfg["landmarks"] == 22 else 1500
+        lvl = cpu_train_level_seconds(n_cpu, cores, cfg)
+        S = len(cfg["cell_sizes"])
+        value = lvl["total_extrapolated_s"] * S
+        sample_txt = (f"ONE level (level 0) on {n_cpu} of the {cfg['n']} samples: HOG {lvl['hog_s']:.2f} s, Gram {lvl['gram_s']:.2f} s, LU+solve {lvl['lu_solve_s']:.2f} s, "
+                      f"update {lvl['update_s']:.2f} s, scaled to the full level and x{S} levels (extrapolated); {lvl['kind']}")
+        print(json.dumps({"impl": "reference", "metric": "regressor train sec (RCR, all cascade levels)", "value": value, "unit": "s", "n_gpus": args.gpus,
+                          "steps": 1, "warmup": 0, "ms_per_step": value * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                          "data": "synthetic", "config": {"workload": cfg["name"]},
+                          "cpu_baseline": {"value": value, "unit": "s", "cores": cores, "kind": "port", "sample": sample_txt},
+                          "e2e": {"value": value, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+        return
     sample = max(cores * 8, 256)
     rates = []
     kind = "port"
