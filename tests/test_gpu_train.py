@@ -57,9 +57,14 @@ def test_training_levels_teacher_forced(sd, oracle, golden, mode):
             print(f"mode {mode} level {level}: D={X.shape[0]} lambda {sdo.regressors[0].last_lambda:.6g} vs {lam_ref:.6g}; weights rel err {e_w:.2e}; updated landmarks rel err {e_x:.2e}; timings {ctx.solver_timings()}")
             assert abs(sdo.regressors[0].last_lambda - lam_ref) <= 2e-5 * lam_ref
             assert e_x <= 1e-4
-            # weights of an ill-conditioned system are looser than the predictions they produce; the plain fp32 SIMT
-            # accumulation (mode 2) is the less accurate of the two Gram kernels
-            assert e_w <= (1e-3 if mode == 0 else 5e-3)
+            # the reference's own float32 arithmetic on the same system (the reference-order oracle, regressors.hpp:199-234 with
+            # Eigen-like partial-pivot LU): ITS distance to the float64 weights is what "matching the reference" can mean
+            b_ref = ((cur - x_gt) * (1.0 / np.array([oracle.get_ied(cur[i], om.right_idx, om.left_idx) for i in range(n)])).astype(np.float32)[:, None]).astype(np.float32)
+            X_f32, _ = oracle.solve(A_ref, b_ref, oracle.Regulariser(1, 1.5, 0), 0)
+            print(f"   float32 reference-order oracle vs float64: weights {rel_err(X_f32, X_ref):.2e}; ours vs that oracle: {rel_err(X, X_f32):.2e}")
+            # last-column-first elimination removes the cancellation that costs the reference three digits: the
+            # tensor-core Gram holds the weights to north_star's 1e-4; the plain fp32 SIMT Gram (mode 2, ~3e-7 per entry) to 5e-4
+            assert e_w <= (1e-4 if mode == 0 else 5e-4)
             cur = nxt_ref
     finally:
         ctx.set_gram_mode(0)
