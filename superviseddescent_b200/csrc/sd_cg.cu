@@ -14,6 +14,7 @@
 // modified here (only the unused lower triangle is filled with the mirror image).
 #include "sd_internal.cuh"
 
+#include <cmath>
 #include <cstdlib>
 
 namespace {
@@ -222,7 +223,8 @@ int sd_cg_solve(sd_ctx* ctx, sd_comm* comm, float* G, int64_t ldg, int n, int co
     const int tiles = sd_div_up(n, 256) * sd_div_up(M, 128);
     const int ksplit = (nranks == 1 && 2 * tiles <= ctx->sm_count) ? 2 : 1;
     float* h_conv = reinterpret_cast<float*>(reinterpret_cast<char*>(ctx->h_scratch) + 192);
-    int it = 0, rc = SD_OK;
+    int it = 0, rc = SD_OK, prev_it = 0;
+    float prev_conv = 0.f;
     bool converged = false;
     for (; it < max_iter && !converged; ++it) {
         const int parity = it & 1;
@@ -248,6 +250,16 @@ int sd_cg_solve(sd_ctx* ctx, sd_comm* comm, float* G, int64_t ldg, int n, int co
             SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
             if (h_conv[1] != 0.f || !(h_conv[0] == h_conv[0])) { if (iters) *iters = it + 1; return SD_ERR_NUMERIC; }
             converged = h_conv[0] <= tol;
+            // a system that would need more than max_iter iterations at the observed rate is the factorisation's job
+            if (!converged && it >= 30 && prev_conv > 0.f) {
+                const double rate = pow((double)h_conv[0] / (double)prev_conv, 1.0 / (double)(it - prev_it));
+                if (rate >= 1.0 || (double)it + log((double)tol / (double)h_conv[0]) / log(rate) > (double)max_iter) {
+                    if (iters) *iters = it + 1;
+                    return SD_ERR_NUMERIC;
+                }
+            }
+            prev_conv = h_conv[0];
+            prev_it = it;
         }
     }
     if (iters) *iters = it;
