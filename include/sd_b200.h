@@ -50,6 +50,7 @@ typedef enum {
 
 typedef struct sd_ctx sd_ctx;       /* one per host thread / stream */
 typedef struct sd_model sd_model;   /* rcr::detection_model resident on the device */
+typedef struct sd_comm sd_comm;     /* multi-GPU communicator (see "multi-GPU training" below) */
 
 /* rcr::HoGParam (adaptive_vlhog.hpp:41-60); same field order as its cereal archive */
 typedef struct {
@@ -184,6 +185,22 @@ SD_API int sd_bgr2gray(sd_ctx* ctx, const uint8_t* d_bgr, int width, int height,
  * reference's VerbosePartialPivLUSolver prints them, are available from sd_solver_timings. */
 SD_API int sd_learn(sd_ctx* ctx, const float* d_A, int64_t lda, const float* d_B, int64_t ldb,
                     int N, int D, int M, const sd_regulariser* reg, float* d_X, float* lambda_out);
+/* The training path on CENTRED feature rows (what the shells' and the Python mirror's train() use for D > 256).
+ * HOG features are non-negative, so A^T A is dominated by n mu mu^T and the covariance that decides the weights sits several
+ * digits down; a float32 Gram matrix -- the reference's as much as this one -- then loses three digits of the weights (the
+ * reference's own arithmetic is 2e-3 away from the float64 solution on RCR features).  Subtracting the column means before the
+ * Gram is the same least-squares problem (A w + c 1 = (A - 1 mu^T) w + (c + mu.w) 1) without that loss:
+ *   sd_centre_features : d_mu[c] = mean of column c over ALL ranks' rows (0 for the last = bias column); d_A[:, c] -= d_mu[c]
+ *                        in place.  Systems with D <= 256 (reference-order LU) are left untouched (d_mu = 0).
+ *   sd_learn_centred   : Gram of the centred rows, exchange (comm may be NULL; route as in sd_learn_dist), lambda from the norm
+ *                        of the UNcentred A^T A (regressors.hpp:135: reconstructed from the centred Gram and mu), solve.
+ *                        d_X  : D x M weights for uncentred features -- the model (bias shifted back: c' - mu.w);
+ *                        d_Xc : (optional) the weights that go with the centred buffer, for sd_cascade_update on it. */
+SD_API int sd_centre_features(sd_ctx* ctx, sd_comm* comm, float* d_A, int64_t lda, int N_local, int D, int n_global, float* d_mu);
+SD_API int sd_learn_centred(sd_ctx* ctx, sd_comm* comm, const float* d_Ac, int64_t lda, const float* d_B, int64_t ldb,
+                            int N_local, int D, int M, const sd_regulariser* reg, int n_train_global, int route,
+                            const float* d_mu, float* d_X, float* d_Xc, float* lambda_out);
+
 /* ColPivHouseholderQRSolver::solve (regressors.hpp:264-305): the same system, plus the one diagnostic that solver exists for --
  * the numerical rank of the regularised A^T A (regressors.hpp:288-293 prints it and asks for a larger lambda).  A^T A + Lambda is
  * symmetric positive semi-definite, so the rank comes from a diagonally pivoted Cholesky (threshold eps * D relative to the
@@ -226,7 +243,6 @@ SD_API int sd_set_gram_mode(sd_ctx* ctx, int mode);
  *                ends with the same X.  sd_learn_dist runs either route from the local rows.
  * Determinism: for a fixed nranks the result is reproducible bit for bit; it differs from the one-GPU result only by the
  * summation order of the partial Gram matrices (~1e-7 relative). */
-typedef struct sd_comm sd_comm;
 #define SD_COMM_ID_BYTES 128
 /* rank 0 obtains an id and hands it to the other ranks by any means the host has (MPI, torch.distributed, a file) */
 SD_API int sd_comm_get_unique_id(uint8_t* id_out /* SD_COMM_ID_BYTES */);

@@ -169,6 +169,17 @@ class LinearRegressor:
         X = torch.empty((D, M), dtype=torch.float32, device=A.device)
         lam = C.c_float(0)
         reg = self.regulariser.c()
+        if D > 256 and not getattr(self.solver, "rank_revealing", False):
+            # the factorisation route works on centred rows (include/sd_b200.h, sd_centre_features): on a private copy
+            if isinstance(data, torch.Tensor) and A.data_ptr() == data.data_ptr():
+                A = A.clone()
+            mu = torch.empty(D, dtype=torch.float32, device=A.device)
+            _check(ctx.h, _capi.lib().sd_centre_features(ctx.h, None, ptr(A), C.c_int64(A.stride(0)), N, D, N, ptr(mu)))
+            _check(ctx.h, _capi.lib().sd_learn_centred(ctx.h, None, ptr(A), C.c_int64(A.stride(0)), ptr(B), C.c_int64(B.stride(0)), N, D, M,
+                                                       C.byref(reg), N, 0, ptr(mu), ptr(X), None, C.byref(lam)))
+            self.x = X
+            self.last_lambda = lam.value
+            return True
         if getattr(self.solver, "rank_revealing", False):
             rank = C.c_int(-1)
             rc = _capi.lib().sd_learn_rank_revealing(ctx.h, ptr(A), C.c_int64(A.stride(0)), ptr(B), C.c_int64(B.stride(0)),
@@ -498,22 +509,24 @@ class SupervisedDescentOptimiser:
                 _check(ctx.h, lib.sd_subtract_templates(ctx.h, ptr(A), C.c_int64(A.stride(0)), ptr(tmpl), C.c_int64(tmpl.stride(0)), n, D))
             Bv = A[:, D:D + P]                                               # 2) b = (x - x_gt) .* norm(x)  (:199-205)
             _check(ctx.h, lib.sd_cascade_targets(ctx.h, ptr(cur), ptr(x_gt), n, P, C.byref(norm), ptr(Bv), C.c_int64(A.stride(0))))
-            X = torch.empty((D, P), dtype=torch.float32, device=cur.device)  # 3) learn (:207)
+            X = torch.empty((D, P), dtype=torch.float32, device=cur.device)  # 3) learn (:207), on centred rows (sd_centre_features)
+            Xc = torch.empty((D, P), dtype=torch.float32, device=cur.device)
+            mu = torch.empty(D, dtype=torch.float32, device=cur.device)
             lam = C.c_float(0)
             rc_ = reg.regulariser.c()
+            ds = 0
             if distributed:
                 if distributed_solve is None:
                     ds = 1 if D >= parallel.DIST_SOLVE_MIN_D else 0
                 else:
                     ds = 2 if distributed_solve == "cg" else int(bool(distributed_solve))
-                _check(ctx.h, lib.sd_learn_dist(ctx.h, comm.h, ptr(A), C.c_int64(A.stride(0)), ptr(Bv), C.c_int64(A.stride(0)), n, D, P,
-                                                C.byref(rc_), n_global, int(ds), ptr(X), C.byref(lam)))
-            else:
-                _check(ctx.h, lib.sd_learn(ctx.h, ptr(A), C.c_int64(A.stride(0)), ptr(Bv), C.c_int64(A.stride(0)), n, D, P, C.byref(rc_),
-                                           ptr(X), C.byref(lam)))
-            reg.x, reg.last_lambda = X, lam.value
-            nxt = torch.empty_like(cur)                                      # 4) x <- x - (A X) .* 1/norm(x) (:209-215)
-            _check(ctx.h, lib.sd_cascade_update(ctx.h, ptr(A), C.c_int64(A.stride(0)), n, D, ptr(X), P, ptr(cur), C.byref(norm), ptr(nxt)))
+            ch = comm.h if distributed else None
+            _check(ctx.h, lib.sd_centre_features(ctx.h, ch, ptr(A), C.c_int64(A.stride(0)), n, D, n_global, ptr(mu)))
+            _check(ctx.h, lib.sd_learn_centred(ctx.h, ch, ptr(A), C.c_int64(A.stride(0)), ptr(Bv), C.c_int64(A.stride(0)), n, D, P,
+                                               C.byref(rc_), n_global, int(ds), ptr(mu), ptr(X), ptr(Xc), C.byref(lam)))
+            reg.x, reg.last_lambda = X, lam.value                            #    X: the model (for uncentred features)
+            nxt = torch.empty_like(cur)                                      # 4) x <- x - (A X) .* 1/norm(x) (:209-215); A is centred now: Xc
+            _check(ctx.h, lib.sd_cascade_update(ctx.h, ptr(A), C.c_int64(A.stride(0)), n, D, ptr(Xc), P, ptr(cur), C.byref(norm), ptr(nxt)))
             cur = nxt
             del A, Bv
             if on_training_epoch_callback is not None:                       # 5) callback (:217)

@@ -296,9 +296,12 @@ __global__ void __launch_bounds__(kHogThreads) hog_patch_kernel(const HogArgs a,
     // TMA route: whole frames resident and describable by a tensor map; the smallest box class that covers the window and
     // fits the staging area
     int tma_box = 0;
+    // The TMA wants the box to start on a 16-byte boundary of the innermost dimension (an unaligned start faults with "illegal
+    // instruction"): the box starts at x0 rounded down to a multiple of 16 and the window sits tma_shift bytes into its rows.
+    const int tma_shift = x0 & 15;
 #pragma unroll
     for (int c = kTmaClasses - 1; c >= 0; --c)
-        if (c < a.tma_count && hog_tma_box(c) >= P && hog_tma_box(c) * hog_tma_box(c) <= stage_cap) tma_box = hog_tma_box(c);
+        if (c < a.tma_count && hog_tma_box(c) >= P + tma_shift && hog_tma_box(c) * hog_tma_box(c) <= stage_cap) tma_box = hog_tma_box(c);
     if (tma_box > 0 && tid == 0) {
         // one elected thread: the box lands densely (pitch = box width); bytes outside the frame are zero-filled by the TMA,
         // which is exactly copyMakeBorder(..., BORDER_CONSTANT, 0) (adaptive_vlhog.hpp:136-147)
@@ -310,7 +313,7 @@ __global__ void __launch_bounds__(kHogThreads) hog_patch_kernel(const HogArgs a,
 #pragma unroll
         for (int c = 0; c < kTmaClasses; ++c) if (hog_tma_box(c) == tma_box) cls = c;
         asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-                     ::"r"((uint32_t)__cvta_generic_to_shared(s_stage)), "l"(&maps.m[cls]), "r"(bar), "r"(x0), "r"(y0), "r"(img_idx)
+                     ::"r"((uint32_t)__cvta_generic_to_shared(s_stage)), "l"(&maps.m[cls]), "r"(bar), "r"(x0 - tma_shift), "r"(y0), "r"(img_idx)
                      : "memory");
     }
 
@@ -336,7 +339,7 @@ __global__ void __launch_bounds__(kHogThreads) hog_patch_kernel(const HogArgs a,
         const bool vec16 = !tma_box && resident && (align_bits & 15) == 0;      // rows can be fetched as aligned 16-byte vectors
         const bool words = !tma_box && resident && (align_bits & 3) == 0;
         // column c of the staged window sits at byte shiftb + c of its row
-        const int shiftb = vec16 ? ((x0 - rx) & 15) : (words ? ((x0 - rx) & 3) : 0);
+        const int shiftb = tma_box ? tma_shift : (vec16 ? ((x0 - rx) & 15) : (words ? ((x0 - rx) & 3) : 0));
         const int pitch = tma_box ? tma_box : ((P + 15 + 15) & ~15);
         const bool staged = pitch * P <= stage_cap;
         bool miss = false;

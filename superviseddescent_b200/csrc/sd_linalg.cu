@@ -320,11 +320,13 @@ int launch_gemm_nn(sd_ctx* ctx, const float* A, int64_t lda, int N, int D, const
                    float* C, int64_t ldc, float alpha, float beta, const GemmEpilogue& ep)
 {
     if (N <= 0 || M <= 0) return SD_OK;
-    // the cascade's shape -- many rows, a long contraction, 2L output columns -- goes to the row-per-thread kernel
-    if (N >= 1024 && D >= 1024 && M <= 4 * PR_COLS && (lda % 4) == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0 &&
+    // the cascade's shape -- a long contraction, 2L output columns -- goes to the row-per-thread kernel for ANY number of rows: its
+    // chunk boundaries are global multiples of 32, so a row's result does not depend on the batch it is computed in
+    if (D >= 1024 && M <= 4 * PR_COLS && (lda % 4) == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0 &&
         !getenv("SD_B200_OLD_PREDICT")) {
         const int row_blocks = sd_div_up(N, PR_ROWS), col_groups = sd_div_up(M, PR_COLS);
         int splits = (int)(2LL * ctx->sm_count / ((long long)row_blocks * col_groups));     // two CTAs' worth of work per SM, whole waves
+        if (N < PR_ROWS) splits = splits * N / PR_ROWS + 1;                                 // few rows: few threads per CTA are live anyway
         const int maxs = sd_div_up(D, 4 * PR_KC);
         if (splits > maxs) splits = maxs;
         if (splits < 1) splits = 1;
@@ -407,12 +409,97 @@ __global__ void subtract_kernel(float* __restrict__ A, long long lda, const floa
     }
 }
 
+
+// ---- centred features -----------------------------------------------------------------------------------------------------
+// HOG features are non-negative with means of the size of their spread, so every entry of A^T A is dominated by N mu_i mu_j and
+// the part that decides the weights -- the covariance -- sits several digits down: a Gram matrix that is accurate to 2e-7 still
+// loses those digits when the bias column is eliminated (measured: weights 2.9e-4 from the float64 solve, the reference's own
+// float32 arithmetic 2.0e-3).  Subtracting a per-column shift mu (the column mean) BEFORE the Gram removes the problem at the
+// source.  It is the same least-squares problem:  A w + c 1 = (A - 1 mu^T) w + (c + mu.w) 1,  so the solve runs on the centred
+// rows and the bias is shifted back at the end (bias = c' - mu.w); the MatrixNorm lambda still needs ||A^T A||_F of the
+// UNcentred matrix, which follows from the centred Gram, its bias column s' and mu (frob_upper_kernel below).
+// Column sums in double: blockIdx.y splits the rows, partials [splits][D] are folded in a fixed order.
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ A, long long lda, int N, int D, double* __restrict__ part)
+{
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int rl = threadIdx.x >> 5;                      // 8 row lanes
+    const int rows_per = (N + gridDim.y - 1) / gridDim.y;
+    const int r0 = blockIdx.y * rows_per, r1 = min(N, r0 + rows_per);
+    double acc = 0.0;
+    if (c < D)
+        for (int r = r0 + rl; r < r1; r += 8) acc += (double)A[(long long)r * lda + c];
+    __shared__ double red[8][33];
+    red[rl][threadIdx.x & 31] = acc;
+    __syncthreads();
+    if (rl == 0 && c < D) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += red[k][threadIdx.x & 31];
+        part[(long long)blockIdx.y * D + c] = s;
+    }
+}
+
+__global__ void colsum_finish_kernel(double* __restrict__ part, int splits, int D)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= D) return;
+    double s = 0.0;
+    for (int k = 0; k < splits; ++k) s += part[(long long)k * D + c];
+    part[c] = s;
+}
+
+// mu[c] = (float)(sum[c] / n) for the feature columns, 0 for the last (bias) column; A[:, c] -= mu[c]
+__global__ void colmean_kernel(const double* __restrict__ sums, int D, int n_global, float* __restrict__ mu)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < D) mu[c] = c < D - 1 ? (float)(sums[c] / (double)n_global) : 0.f;
+}
+
+__global__ void __launch_bounds__(256) centre_kernel(float* __restrict__ A, long long lda, int N, int D, const float* __restrict__ mu)
+{
+    const long long total = (long long)N * (D - 1);
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const long long r = idx / (D - 1);
+        const int c = (int)(idx - r * (D - 1));
+        A[r * lda + c] = __fsub_rn(A[r * lda + c], __ldg(mu + c));
+    }
+}
+
 // ---- regulariser (regressors.hpp:126-148) ---------------------------------------------------------
 // sum of squares of the full symmetric D x D matrix from its upper triangle, in double (cv::norm)
 // Rows are dealt round-robin to the blocks (balanced triangle), a block's 1024 threads stride along the row with
 // four independent loads in flight each; fixed grid and fixed order, so the sum is reproducible.
 // own_block/nranks/rank: only the rows of this rank's block rows are summed (distributed solve; the partial sums are then
 // all-reduced).
+// Centred features (mu != NULL): G is the Gram of the rows shifted by mu (bias column unshifted, so G[:, D-1] = s' = A_c^T 1);
+// the norm is taken of the uncentred matrix it stands for,  G[i][j] + s'_i mu_j + mu_i s'_j + n mu_i mu_j  (bias column:
+// G[i][D-1] + n mu_i), entry by entry in double.  sv = s' (bias_extract_kernel), n = global sample count.
+__global__ void __launch_bounds__(1024) frob_upper_centred_kernel(const float* __restrict__ G, long long ldg, int D, double* __restrict__ out,
+                                                                  int own_block, int nranks, int rank, const float* __restrict__ mu,
+                                                                  const double* __restrict__ sv, double n)
+{
+    double s0 = 0.0;
+    for (int i = blockIdx.x; i < D; i += gridDim.x) {
+        if (nranks > 1 && (i / own_block) % nranks != rank) continue;
+        const float* row = G + (long long)i * ldg;
+        const double mi = (double)mu[i], si = i < D - 1 ? sv[i] : 0.0;
+        for (int j = i + threadIdx.x; j < D; j += 1024) {
+            double v = (double)row[j];
+            if (j == D - 1) v += (i == D - 1) ? 0.0 : n * mi;
+            else v += si * (double)mu[j] + mi * sv[j] + n * mi * (double)mu[j];
+            s0 += (j == i) ? 0.5 * v * v : v * v;                 // the diagonal counts once, everything is doubled below
+        }
+    }
+    __shared__ double red[1024];
+    red[threadIdx.x] = 2.0 * s0;
+    __syncthreads();
+    for (int o = 512; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[blockIdx.x] = red[0];
+}
+
 __global__ void __launch_bounds__(1024) frob_upper_kernel(const float* __restrict__ G, long long ldg, int D, double* __restrict__ out,
                                                           int own_block, int nranks, int rank)
 {
@@ -512,27 +599,41 @@ __global__ void __launch_bounds__(256) bias_downdate_kernel(float* __restrict__ 
 
 // X[0..D-2] = w = columns [wcol0, wcol0 + M) of Xp (pitch ldw; after the factorisation column 0 is the solve of the carried bias
 // column), X[D-1] = (rb - s^T w) / pivot
+// Centred features: mu shifts the bias back (bias = c' - mu.w); Xc (optional) receives the weights that go with the CENTRED rows
+// (same w, bias c'), which is what the cascade update multiplies the centred feature buffer with.
 __global__ void __launch_bounds__(256) bias_finish_kernel(const float* __restrict__ Xp, int ldw, int wcol0, int D, int M,
-                                                          const double* __restrict__ sv, float* __restrict__ X)
+                                                          const double* __restrict__ sv, float* __restrict__ X,
+                                                          const float* __restrict__ mu, float* __restrict__ Xc)
 {
     const int c = blockIdx.x;
     if (c < M) {
-        double acc = 0.0;
-        for (int i = threadIdx.x; i < D - 1; i += 256) acc += sv[i] * (double)Xp[(long long)i * ldw + wcol0 + c];
-        __shared__ double red[256];
+        double acc = 0.0, shift = 0.0;
+        for (int i = threadIdx.x; i < D - 1; i += 256) {
+            const double w = (double)Xp[(long long)i * ldw + wcol0 + c];
+            acc += sv[i] * w;
+            if (mu) shift += (double)mu[i] * w;
+        }
+        __shared__ double red[256], red2[256];
         red[threadIdx.x] = acc;
+        red2[threadIdx.x] = shift;
         __syncthreads();
         for (int o = 128; o > 0; o >>= 1) {
-            if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+            if ((int)threadIdx.x < o) { red[threadIdx.x] += red[threadIdx.x + o]; red2[threadIdx.x] += red2[threadIdx.x + o]; }
             __syncthreads();
         }
-        if (threadIdx.x == 0) X[(long long)(D - 1) * M + c] = (float)((sv[D + c] - red[0]) / sv[D - 1]);
+        if (threadIdx.x == 0) {
+            const double cprime = (sv[D + c] - red[0]) / sv[D - 1];
+            X[(long long)(D - 1) * M + c] = (float)(cprime - red2[0]);
+            if (Xc) Xc[(long long)(D - 1) * M + c] = (float)cprime;
+        }
     } else {
         const long long total = (long long)(D - 1) * M;
         for (long long idx = (long long)(blockIdx.x - M) * 256 + threadIdx.x; idx < total; idx += (long long)(gridDim.x - M) * 256) {
             const long long r = idx / M;
             const int cc = (int)(idx - r * M);
-            X[idx] = Xp[r * ldw + wcol0 + cc];
+            const float w = Xp[r * ldw + wcol0 + cc];
+            X[idx] = w;
+            if (Xc) Xc[idx] = w;
         }
     }
 }
@@ -1348,7 +1449,8 @@ int sd_gram(sd_ctx* ctx, const float* d_A, int64_t lda, const float* d_B, int64_
 //        1 = G is reduce-scattered over comm: distributed blocked Cholesky;
 //        2 = every rank holds the summed G and the ranks share the CG iterations (contraction sharded, one small all-reduce each)
 static int solve_gram_impl(sd_ctx* ctx, sd_comm* comm, float* d_G, int64_t ldg, int D, int M, const sd_regulariser* reg,
-                           int n_train_global, float* d_X, float* lambda_out, int* rank_out = nullptr, int route = 0)
+                           int n_train_global, float* d_X, float* lambda_out, int* rank_out = nullptr, int route = 0,
+                           const float* d_mu = nullptr, float* d_Xc = nullptr)
 {
     if (!ctx) return SD_ERR_INVALID;
     SD_REQUIRE(ctx, d_G && d_X && reg && D >= 1 && M >= 1 && ldg >= D + M, "bad argument");
@@ -1363,10 +1465,26 @@ static int solve_gram_impl(sd_ctx* ctx, sd_comm* comm, float* d_G, int64_t ldg, 
     SD_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch, 0, sizeof(int), ctx->stream));
     SD_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
     int nparts = 0;
+    SD_REQUIRE(ctx, !d_mu || D > kLuMaxDim, "centred features are for the factorisation route (D > 256)");
     if (reg->type == 1) {
         nparts = D < 296 ? D : 296;                                   // 2 x 148 SMs; at most 384 partials fit the scratch
-        frob_upper_kernel<<<nparts, 1024, 0, ctx->stream>>>(d_G, ldg, D, partial, 2 * kCholNb, dist ? nranks : 1, sd_comm_rank_of(comm));
-        SD_LAUNCH_CHECK(ctx, "frob_upper_kernel");
+        if (d_mu) {
+            // s' = bias column of the centred Gram, needed entry by entry for the norm of the uncentred matrix
+            double* sv0 = (double*)sd_workspace(ctx, SD_WS_BIAS, (size_t)(D + M) * sizeof(double) + (size_t)(D - 1) * (M + 1) * sizeof(float));
+            if (!sv0) return SD_ERR_CUDA;
+            bias_extract_kernel<<<sd_div_up(D + M, 256), 256, 0, ctx->stream>>>(d_G, ldg, D, M, sv0, 2 * kCholNb, dist ? nranks : 1, sd_comm_rank_of(comm));
+            SD_LAUNCH_CHECK(ctx, "bias_extract_kernel");
+            if (dist) {
+                int rc0 = sd_comm_allreduce_f64(ctx, comm, sv0, (size_t)(D + M), ctx->stream);
+                if (rc0) return rc0;
+            }
+            frob_upper_centred_kernel<<<nparts, 1024, 0, ctx->stream>>>(d_G, ldg, D, partial, 2 * kCholNb, dist ? nranks : 1, sd_comm_rank_of(comm),
+                                                                        d_mu, sv0, (double)n_train_global);
+            SD_LAUNCH_CHECK(ctx, "frob_upper_centred_kernel");
+        } else {
+            frob_upper_kernel<<<nparts, 1024, 0, ctx->stream>>>(d_G, ldg, D, partial, 2 * kCholNb, dist ? nranks : 1, sd_comm_rank_of(comm));
+            SD_LAUNCH_CHECK(ctx, "frob_upper_kernel");
+        }
         if (dist) {
             sum_partials_kernel<<<1, 32, 0, ctx->stream>>>(partial, nparts);
             SD_LAUNCH_CHECK(ctx, "sum_partials_kernel");
@@ -1419,7 +1537,7 @@ static int solve_gram_impl(sd_ctx* ctx, sd_comm* comm, float* d_G, int64_t ldg, 
             ctx->cg_iterations = its;
             if (rc == SD_OK) {
                 SD_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
-                bias_finish_kernel<<<M + 2 * ctx->sm_count, 256, 0, ctx->stream>>>(W, ldw, 0, D, M, sv, d_X);
+                bias_finish_kernel<<<M + 2 * ctx->sm_count, 256, 0, ctx->stream>>>(W, ldw, 0, D, M, sv, d_X, d_mu, d_Xc);
                 SD_LAUNCH_CHECK(ctx, "bias_finish_kernel");
                 solved = true;
             } else if (rc != SD_ERR_NUMERIC) {
@@ -1429,7 +1547,7 @@ static int solve_gram_impl(sd_ctx* ctx, sd_comm* comm, float* d_G, int64_t ldg, 
         if (!solved) {
             rc = cholesky_solve(ctx, d_G, ldg, D - 1, M + 1, Xp, dist ? comm : nullptr);
             if (rc) return rc;
-            bias_finish_kernel<<<M + 2 * ctx->sm_count, 256, 0, ctx->stream>>>(Xp, M + 1, 1, D, M, sv, d_X);
+            bias_finish_kernel<<<M + 2 * ctx->sm_count, 256, 0, ctx->stream>>>(Xp, M + 1, 1, D, M, sv, d_X, d_mu, d_Xc);
             SD_LAUNCH_CHECK(ctx, "bias_finish_kernel");
         }
     }
@@ -1482,6 +1600,65 @@ int sd_learn_dist(sd_ctx* ctx, sd_comm* comm, const float* d_A, int64_t lda, con
     if (rc) return rc;
     // 2: the ranks share the CG iterations; 0: every rank solves alone (factorisation, or CG if sd_set_solver chose it)
     return solve_gram_impl(ctx, comm, G, ldg, D, M, reg, n_train_global, d_X, lambda_out, nullptr, distributed_solve == 2 ? 2 : 0);
+}
+
+int sd_centre_features(sd_ctx* ctx, sd_comm* comm, float* d_A, int64_t lda, int N_local, int D, int n_global, float* d_mu)
+{
+    if (!ctx) return SD_ERR_INVALID;
+    SD_REQUIRE(ctx, d_mu && D >= 1 && N_local >= 0 && n_global >= 1 && (N_local == 0 || (d_A && lda >= D)), "bad argument");
+    if (D <= kLuMaxDim) {                                   // the small systems keep the reference-order LU on the rows as they are
+        SD_CUDA(ctx, cudaMemsetAsync(d_mu, 0, (size_t)D * sizeof(float), ctx->stream));
+        return SD_OK;
+    }
+    int splits = N_local / 512;
+    splits = splits < 1 ? 1 : (splits > 16 ? 16 : splits);
+    double* part = (double*)sd_workspace(ctx, SD_WS_PARTIAL, (size_t)splits * D * sizeof(double));
+    if (!part) return SD_ERR_CUDA;
+    if (N_local > 0) {
+        const dim3 grid(sd_div_up(D, 32), splits);
+        colsum_kernel<<<grid, 256, 0, ctx->stream>>>(d_A, lda, N_local, D, part);
+        SD_LAUNCH_CHECK(ctx, "colsum_kernel");
+        colsum_finish_kernel<<<sd_div_up(D, 256), 256, 0, ctx->stream>>>(part, splits, D);
+        SD_LAUNCH_CHECK(ctx, "colsum_finish_kernel");
+    } else {
+        SD_CUDA(ctx, cudaMemsetAsync(part, 0, (size_t)D * sizeof(double), ctx->stream));
+    }
+    int rc = sd_comm_allreduce_f64(ctx, comm, part, (size_t)D, ctx->stream);     // no-op without a communicator
+    if (rc) return rc;
+    colmean_kernel<<<sd_div_up(D, 256), 256, 0, ctx->stream>>>(part, D, n_global, d_mu);
+    SD_LAUNCH_CHECK(ctx, "colmean_kernel");
+    if (N_local > 0) {
+        const long long total = (long long)N_local * (D - 1);
+        const int blocks = (int)(sd_div_up(total, 256) < 32LL * ctx->sm_count ? sd_div_up(total, 256) : 32LL * ctx->sm_count);
+        centre_kernel<<<blocks, 256, 0, ctx->stream>>>(d_A, lda, N_local, D, d_mu);
+        SD_LAUNCH_CHECK(ctx, "centre_kernel");
+    }
+    return SD_OK;
+}
+
+int sd_learn_centred(sd_ctx* ctx, sd_comm* comm, const float* d_Ac, int64_t lda, const float* d_B, int64_t ldb, int N_local, int D, int M,
+                     const sd_regulariser* reg, int n_train_global, int route, const float* d_mu, float* d_X, float* d_Xc, float* lambda_out)
+{
+    if (!ctx) return SD_ERR_INVALID;
+    SD_REQUIRE(ctx, M >= 1 && N_local >= 0 && d_mu && d_X, "bad argument");
+    const int64_t ldg = ((int64_t)(D + M) + 3) / 4 * 4;
+    float* G = (float*)sd_workspace(ctx, SD_WS_SCRATCH, (size_t)D * ldg * sizeof(float));
+    if (!G) return SD_ERR_CUDA;
+    SD_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+    int rc;
+    if (N_local > 0) rc = sd_gram(ctx, d_Ac, lda, d_B, ldb, N_local, D, M, G, ldg);
+    else rc = sd_check_cuda(ctx, cudaMemsetAsync(G, 0, (size_t)D * ldg * sizeof(float), ctx->stream), "memset(G)");
+    if (rc) return rc;
+    const bool multi = sd_comm_size_of(comm) > 1;
+    if (multi) {
+        rc = route == 1 ? sd_reduce_scatter_gram(ctx, comm, G, ldg, D, M) : sd_allreduce_gram(ctx, comm, G, ldg, D, M);
+        if (rc) return rc;
+    }
+    const float* mu = D > kLuMaxDim ? d_mu : nullptr;       // sd_centre_features leaves the small systems alone
+    rc = solve_gram_impl(ctx, multi ? comm : nullptr, G, ldg, D, M, reg, n_train_global, d_X, lambda_out, nullptr, multi ? route : 0, mu, d_Xc);
+    if (rc) return rc;
+    if (!mu && d_Xc && d_Xc != d_X) SD_CUDA(ctx, cudaMemcpyAsync(d_Xc, d_X, (size_t)D * M * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+    return SD_OK;
 }
 
 int sd_learn_rank_revealing(sd_ctx* ctx, const float* d_A, int64_t lda, const float* d_B, int64_t ldb, int N, int D, int M,

@@ -211,7 +211,7 @@ private:
         sd_b200::upload(parameters, d_gt, Pd);
         sd_b200::upload(initialisations, d_cur, Pd);
         const sd_normalisation norm = normalisation_strategy.c_normalisation();
-        sd_b200::DeviceBuffer A, G, X;
+        sd_b200::DeviceBuffer A, G, X, Xc, mu;
         int64_t n_global = n;
         const int nranks = comm ? sd_comm_size(comm) : 1;
         if (nranks > 1) sd_b200::check(ctx, sd_comm_sum_int64(ctx, comm, &n_global), "sd_comm_sum_int64");
@@ -228,13 +228,17 @@ private:
             sd_b200::check(ctx, sd_cascade_targets(ctx, d_cur.as<float>(), d_gt.as<float>(), n, Pd, &norm, B, ld), "sd_cascade_targets");
             X.allocate(static_cast<size_t>(D) * Pd * sizeof(float));                                          // 3) :207
             const sd_regulariser reg = regressors[level].get_regulariser().c();
-            if (nranks > 1)
-                sd_b200::check(ctx, sd_learn_dist(ctx, comm, A.as<float>(), ld, B, ld, n, D, Pd, &reg, static_cast<int>(n_global), comm_route, X.as<float>(), nullptr), "sd_learn_dist");
-            else
-                sd_b200::check(ctx, sd_learn(ctx, A.as<float>(), ld, B, ld, n, D, Pd, &reg, X.as<float>(), nullptr), "sd_learn");
+            // learn on centred rows (sd_centre_features: column means over all ranks, subtracted in place; no-op for D <= 256);
+            // X is the model, Xc the weights that go with the centred buffer
+            Xc.allocate(static_cast<size_t>(D) * Pd * sizeof(float));
+            mu.allocate(static_cast<size_t>(D) * sizeof(float));
+            sd_comm* c = nranks > 1 ? comm : nullptr;
+            sd_b200::check(ctx, sd_centre_features(ctx, c, A.as<float>(), ld, n, D, static_cast<int>(n_global), mu.as<float>()), "sd_centre_features");
+            sd_b200::check(ctx, sd_learn_centred(ctx, c, A.as<float>(), ld, B, ld, n, D, Pd, &reg, static_cast<int>(n_global), nranks > 1 ? comm_route : 0,
+                                                 mu.as<float>(), X.as<float>(), Xc.as<float>(), nullptr), "sd_learn_centred");
             regressors[level].set_x(sd_b200::download(X.as<float>(), D, Pd, Pd));
             regressors[level].report_solver();
-            sd_b200::check(ctx, sd_cascade_update(ctx, A.as<float>(), ld, n, D, X.as<float>(), Pd, d_cur.as<float>(), &norm, d_next.as<float>()), "sd_cascade_update");   // 4) :209-215
+            sd_b200::check(ctx, sd_cascade_update(ctx, A.as<float>(), ld, n, D, Xc.as<float>(), Pd, d_cur.as<float>(), &norm, d_next.as<float>()), "sd_cascade_update");   // 4) :209-215
             std::swap(d_cur, d_next);
             if (want_callback) {                                                                             // 5) :217
                 if (nranks > 1) {

@@ -40,6 +40,7 @@ def _truth(A, B, lam_param):
 
 
 def _learn_dist(sd, ctx, comm_h, A_local, B_local, n_global, D, M, distributed_solve):
+    """The training step of the shells / the Python mirror on this rank's rows: centre (global means), Gram, exchange, solve."""
     import torch
     from superviseddescent_b200 import _capi
     dev = f"cuda:{ctx.device}"
@@ -49,12 +50,17 @@ def _learn_dist(sd, ctx, comm_h, A_local, B_local, n_global, D, M, distributed_s
         ext[:A_local.shape[0], :D] = torch.from_numpy(A_local).to(dev)
         ext[:A_local.shape[0], D:D + M] = torch.from_numpy(B_local).to(dev)
     X = torch.empty((D, M), dtype=torch.float32, device=dev)
+    mu = torch.empty(D, dtype=torch.float32, device=dev)
     lam = C.c_float(0)
     reg = sd.Regulariser(sd.RegularisationType.MatrixNorm, 1.5, False).c()
-    rc = _capi.lib().sd_learn_dist(ctx.h, comm_h, C.c_void_p(ext.data_ptr()), C.c_int64(ld), C.c_void_p(ext.data_ptr() + 4 * D), C.c_int64(ld),
-                                   A_local.shape[0], D, M, C.byref(reg), n_global, int(distributed_solve), C.c_void_p(X.data_ptr()), C.byref(lam))
+    lib = _capi.lib()
+    rc = lib.sd_centre_features(ctx.h, comm_h, C.c_void_p(ext.data_ptr()), C.c_int64(ld), A_local.shape[0], D, n_global, C.c_void_p(mu.data_ptr()))
+    if not rc:
+        rc = lib.sd_learn_centred(ctx.h, comm_h, C.c_void_p(ext.data_ptr()), C.c_int64(ld), C.c_void_p(ext.data_ptr() + 4 * D), C.c_int64(ld),
+                                  A_local.shape[0], D, M, C.byref(reg), n_global, int(distributed_solve), C.c_void_p(mu.data_ptr()),
+                                  C.c_void_p(X.data_ptr()), None, C.byref(lam))
     if rc:
-        raise RuntimeError(_capi.lib().sd_last_error(ctx.h).decode())
+        raise RuntimeError(lib.sd_last_error(ctx.h).decode())
     return X.cpu().numpy(), lam.value
 
 
