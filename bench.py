@@ -289,7 +289,7 @@ def run_train(sd, ctx, model, world, rank, dev, barrier, max_over_ranks, comm, c
     ht = sd.HogTransform(imgs, hps, ids, right, left, ctx)
     D = ht.feature_length(0)
     S = len(hps)
-    ds = ((D >= parallel.DIST_SOLVE_MIN_D) if distributed_solve is None else distributed_solve) if world > 1 else None
+    ds = ((True if D >= parallel.DIST_SOLVE_MIN_D else "cg") if distributed_solve is None else distributed_solve) if world > 1 else None
     gram_ms = []
 
     def one_run(levels=None):

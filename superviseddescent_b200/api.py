@@ -487,7 +487,8 @@ class SupervisedDescentOptimiser:
               distributed_solve=None):
         """superviseddescent.hpp:165-219.  Multi-GPU: pass `comm` (a parallel.Communicator) or a torch.distributed `group`
         (a communicator is then made from it) -- each rank passes its own shard of rows; per level the C ABI does ONE exchange of
-        [AtA | Atb] and the solve.  distributed_solve: None = by size (parallel.DIST_SOLVE_MIN_D), True = reduce-scatter +
+        [AtA | Atb] and the solve.  distributed_solve: None = by size (shared CG below parallel.DIST_SOLVE_MIN_D features,
+        the distributed factorisation from there), True = reduce-scatter +
         distributed blocked Cholesky, False = all-reduce + replicated solve, "cg" = all-reduce + conjugate gradients shared by the
         ranks."""
         from . import parallel
@@ -517,7 +518,7 @@ class SupervisedDescentOptimiser:
             ds = 0
             if distributed:
                 if distributed_solve is None:
-                    ds = 1 if D >= parallel.DIST_SOLVE_MIN_D else 0
+                    ds = 1 if D >= parallel.DIST_SOLVE_MIN_D else 2     # big systems: distributed factorisation; else shared CG
                 else:
                     ds = 2 if distributed_solve == "cg" else int(bool(distributed_solve))
             ch = comm.h if distributed else None
