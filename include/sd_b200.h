@@ -191,12 +191,15 @@ SD_API int sd_learn(sd_ctx* ctx, const float* d_A, int64_t lda, const float* d_B
  * reference's own arithmetic is 2e-3 away from the float64 solution on RCR features).  Subtracting the column means before the
  * Gram is the same least-squares problem (A w + c 1 = (A - 1 mu^T) w + (c + mu.w) 1) without that loss:
  *   sd_centre_features : d_mu[c] = mean of column c over ALL ranks' rows (0 for the last = bias column); d_A[:, c] -= d_mu[c]
- *                        in place.  Systems with D <= 256 (reference-order LU) are left untouched (d_mu = 0).
+ *                        in place.  The shift is only the same problem when the last column is exactly all ones and is not
+ *                        regularised (regressors.hpp:143-146): otherwise -- and for D <= 256 (reference-order LU) -- the rows are
+ *                        left untouched and d_mu = 0, with which sd_learn_centred is sd_learn / sd_learn_dist.
  *   sd_learn_centred   : Gram of the centred rows, exchange (comm may be NULL; route as in sd_learn_dist), lambda from the norm
  *                        of the UNcentred A^T A (regressors.hpp:135: reconstructed from the centred Gram and mu), solve.
  *                        d_X  : D x M weights for uncentred features -- the model (bias shifted back: c' - mu.w);
  *                        d_Xc : (optional) the weights that go with the centred buffer, for sd_cascade_update on it. */
-SD_API int sd_centre_features(sd_ctx* ctx, sd_comm* comm, float* d_A, int64_t lda, int N_local, int D, int n_global, float* d_mu);
+SD_API int sd_centre_features(sd_ctx* ctx, sd_comm* comm, float* d_A, int64_t lda, int N_local, int D, int n_global,
+                              const sd_regulariser* reg, float* d_mu);
 SD_API int sd_learn_centred(sd_ctx* ctx, sd_comm* comm, const float* d_Ac, int64_t lda, const float* d_B, int64_t ldb,
                             int N_local, int D, int M, const sd_regulariser* reg, int n_train_global, int route,
                             const float* d_mu, float* d_X, float* d_Xc, float* lambda_out);

@@ -174,7 +174,7 @@ class LinearRegressor:
             if isinstance(data, torch.Tensor) and A.data_ptr() == data.data_ptr():
                 A = A.clone()
             mu = torch.empty(D, dtype=torch.float32, device=A.device)
-            _check(ctx.h, _capi.lib().sd_centre_features(ctx.h, None, ptr(A), C.c_int64(A.stride(0)), N, D, N, ptr(mu)))
+            _check(ctx.h, _capi.lib().sd_centre_features(ctx.h, None, ptr(A), C.c_int64(A.stride(0)), N, D, N, C.byref(reg), ptr(mu)))
             _check(ctx.h, _capi.lib().sd_learn_centred(ctx.h, None, ptr(A), C.c_int64(A.stride(0)), ptr(B), C.c_int64(B.stride(0)), N, D, M,
                                                        C.byref(reg), N, 0, ptr(mu), ptr(X), None, C.byref(lam)))
             self.x = X
@@ -522,7 +522,7 @@ class SupervisedDescentOptimiser:
                 else:
                     ds = 2 if distributed_solve == "cg" else int(bool(distributed_solve))
             ch = comm.h if distributed else None
-            _check(ctx.h, lib.sd_centre_features(ctx.h, ch, ptr(A), C.c_int64(A.stride(0)), n, D, n_global, ptr(mu)))
+            _check(ctx.h, lib.sd_centre_features(ctx.h, ch, ptr(A), C.c_int64(A.stride(0)), n, D, n_global, C.byref(rc_), ptr(mu)))
             _check(ctx.h, lib.sd_learn_centred(ctx.h, ch, ptr(A), C.c_int64(A.stride(0)), ptr(Bv), C.c_int64(A.stride(0)), n, D, P,
                                                C.byref(rc_), n_global, int(ds), ptr(mu), ptr(X), ptr(Xc), C.byref(lam)))
             reg.x, reg.last_lambda = X, lam.value                            #    X: the model (for uncentred features)

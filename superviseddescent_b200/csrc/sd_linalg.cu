@@ -425,34 +425,43 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ A
     const int rl = threadIdx.x >> 5;                      // 8 row lanes
     const int rows_per = (N + gridDim.y - 1) / gridDim.y;
     const int r0 = blockIdx.y * rows_per, r1 = min(N, r0 + rows_per);
-    double acc = 0.0;
+    double acc = 0.0, sq = 0.0;
     if (c < D)
-        for (int r = r0 + rl; r < r1; r += 8) acc += (double)A[(long long)r * lda + c];
-    __shared__ double red[8][33];
+        for (int r = r0 + rl; r < r1; r += 8) {
+            const double v = (double)A[(long long)r * lda + c];
+            acc += v;
+            if (c == D - 1) sq += v * v;
+        }
+    __shared__ double red[8][33], red2[8][33];
     red[rl][threadIdx.x & 31] = acc;
+    red2[rl][threadIdx.x & 31] = sq;
     __syncthreads();
     if (rl == 0 && c < D) {
-        double s = 0.0;
+        double s = 0.0, q = 0.0;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) s += red[k][threadIdx.x & 31];
-        part[(long long)blockIdx.y * D + c] = s;
+        for (int k = 0; k < 8; ++k) { s += red[k][threadIdx.x & 31]; q += red2[k][threadIdx.x & 31]; }
+        part[(long long)blockIdx.y * (D + 1) + c] = s;
+        if (c == D - 1) part[(long long)blockIdx.y * (D + 1) + D] = q;     // sum of squares of the last column
     }
 }
 
 __global__ void colsum_finish_kernel(double* __restrict__ part, int splits, int D)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= D) return;
+    if (c > D) return;
     double s = 0.0;
-    for (int k = 0; k < splits; ++k) s += part[(long long)k * D + c];
+    for (int k = 0; k < splits; ++k) s += part[(long long)k * (D + 1) + c];
     part[c] = s;
 }
 
-// mu[c] = (float)(sum[c] / n) for the feature columns, 0 for the last (bias) column; A[:, c] -= mu[c]
-__global__ void colmean_kernel(const double* __restrict__ sums, int D, int n_global, float* __restrict__ mu)
+// mu[c] = (float)(sum[c] / n) for the feature columns, 0 for the last (bias) column.  The shift is only a reformulation of the
+// same problem when the last column is exactly all ones (sum == n and sum of squares == n) and carries no penalty; otherwise
+// mu = 0 and the rows stay as they are.
+__global__ void colmean_kernel(const double* __restrict__ sums, int D, int n_global, int enabled, float* __restrict__ mu)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c < D) mu[c] = c < D - 1 ? (float)(sums[c] / (double)n_global) : 0.f;
+    const bool ones = enabled && sums[D - 1] == (double)n_global && sums[D] == (double)n_global;
+    if (c < D) mu[c] = (ones && c < D - 1) ? (float)(sums[c] / (double)n_global) : 0.f;
 }
 
 __global__ void __launch_bounds__(256) centre_kernel(float* __restrict__ A, long long lda, int N, int D, const float* __restrict__ mu)
@@ -1602,30 +1611,31 @@ int sd_learn_dist(sd_ctx* ctx, sd_comm* comm, const float* d_A, int64_t lda, con
     return solve_gram_impl(ctx, comm, G, ldg, D, M, reg, n_train_global, d_X, lambda_out, nullptr, distributed_solve == 2 ? 2 : 0);
 }
 
-int sd_centre_features(sd_ctx* ctx, sd_comm* comm, float* d_A, int64_t lda, int N_local, int D, int n_global, float* d_mu)
+int sd_centre_features(sd_ctx* ctx, sd_comm* comm, float* d_A, int64_t lda, int N_local, int D, int n_global,
+                       const sd_regulariser* reg, float* d_mu)
 {
     if (!ctx) return SD_ERR_INVALID;
-    SD_REQUIRE(ctx, d_mu && D >= 1 && N_local >= 0 && n_global >= 1 && (N_local == 0 || (d_A && lda >= D)), "bad argument");
-    if (D <= kLuMaxDim) {                                   // the small systems keep the reference-order LU on the rows as they are
+    SD_REQUIRE(ctx, d_mu && reg && D >= 1 && N_local >= 0 && n_global >= 1 && (N_local == 0 || (d_A && lda >= D)), "bad argument");
+    if (D <= kLuMaxDim || reg->regularise_last_row) {       // a penalised last column cannot absorb the shift                                   // the small systems keep the reference-order LU on the rows as they are
         SD_CUDA(ctx, cudaMemsetAsync(d_mu, 0, (size_t)D * sizeof(float), ctx->stream));
         return SD_OK;
     }
     int splits = N_local / 512;
     splits = splits < 1 ? 1 : (splits > 16 ? 16 : splits);
-    double* part = (double*)sd_workspace(ctx, SD_WS_PARTIAL, (size_t)splits * D * sizeof(double));
+    double* part = (double*)sd_workspace(ctx, SD_WS_PARTIAL, (size_t)splits * (D + 1) * sizeof(double));
     if (!part) return SD_ERR_CUDA;
     if (N_local > 0) {
         const dim3 grid(sd_div_up(D, 32), splits);
         colsum_kernel<<<grid, 256, 0, ctx->stream>>>(d_A, lda, N_local, D, part);
         SD_LAUNCH_CHECK(ctx, "colsum_kernel");
-        colsum_finish_kernel<<<sd_div_up(D, 256), 256, 0, ctx->stream>>>(part, splits, D);
+        colsum_finish_kernel<<<sd_div_up(D + 1, 256), 256, 0, ctx->stream>>>(part, splits, D);
         SD_LAUNCH_CHECK(ctx, "colsum_finish_kernel");
     } else {
-        SD_CUDA(ctx, cudaMemsetAsync(part, 0, (size_t)D * sizeof(double), ctx->stream));
+        SD_CUDA(ctx, cudaMemsetAsync(part, 0, (size_t)(D + 1) * sizeof(double), ctx->stream));
     }
-    int rc = sd_comm_allreduce_f64(ctx, comm, part, (size_t)D, ctx->stream);     // no-op without a communicator
+    int rc = sd_comm_allreduce_f64(ctx, comm, part, (size_t)D + 1, ctx->stream);     // no-op without a communicator
     if (rc) return rc;
-    colmean_kernel<<<sd_div_up(D, 256), 256, 0, ctx->stream>>>(part, D, n_global, d_mu);
+    colmean_kernel<<<sd_div_up(D, 256), 256, 0, ctx->stream>>>(part, D, n_global, 1, d_mu);
     SD_LAUNCH_CHECK(ctx, "colmean_kernel");
     if (N_local > 0) {
         const long long total = (long long)N_local * (D - 1);

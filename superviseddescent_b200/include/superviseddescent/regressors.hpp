@@ -68,7 +68,7 @@ public:
         const sd_regulariser reg = regulariser.c();
         // the private copy is centred in place (no-op for D <= 256): see sd_centre_features in sd_b200.h
         sd_b200::DeviceBuffer mu(static_cast<size_t>(D) * sizeof(float));
-        sd_b200::check(ctx, sd_centre_features(ctx, nullptr, ext.as<float>(), ld, N, D, N, mu.as<float>()), "sd_centre_features");
+        sd_b200::check(ctx, sd_centre_features(ctx, nullptr, ext.as<float>(), ld, N, D, N, &reg, mu.as<float>()), "sd_centre_features");
         sd_b200::check(ctx, sd_learn_centred(ctx, nullptr, ext.as<float>(), ld, ext.as<float>() + D, ld, N, D, M, &reg, N, 0, mu.as<float>(),
                                              dX.as<float>(), nullptr, &last_lambda), "sd_learn_centred");
         return sd_b200::download(dX.as<float>(), D, M, M);

@@ -233,7 +233,7 @@ private:
             Xc.allocate(static_cast<size_t>(D) * Pd * sizeof(float));
             mu.allocate(static_cast<size_t>(D) * sizeof(float));
             sd_comm* c = nranks > 1 ? comm : nullptr;
-            sd_b200::check(ctx, sd_centre_features(ctx, c, A.as<float>(), ld, n, D, static_cast<int>(n_global), mu.as<float>()), "sd_centre_features");
+            sd_b200::check(ctx, sd_centre_features(ctx, c, A.as<float>(), ld, n, D, static_cast<int>(n_global), &reg, mu.as<float>()), "sd_centre_features");
             sd_b200::check(ctx, sd_learn_centred(ctx, c, A.as<float>(), ld, B, ld, n, D, Pd, &reg, static_cast<int>(n_global), nranks > 1 ? comm_route : 0,
                                                  mu.as<float>(), X.as<float>(), Xc.as<float>(), nullptr), "sd_learn_centred");
             regressors[level].set_x(sd_b200::download(X.as<float>(), D, Pd, Pd));

@@ -54,7 +54,7 @@ def _learn_dist(sd, ctx, comm_h, A_local, B_local, n_global, D, M, distributed_s
     lam = C.c_float(0)
     reg = sd.Regulariser(sd.RegularisationType.MatrixNorm, 1.5, False).c()
     lib = _capi.lib()
-    rc = lib.sd_centre_features(ctx.h, comm_h, C.c_void_p(ext.data_ptr()), C.c_int64(ld), A_local.shape[0], D, n_global, C.c_void_p(mu.data_ptr()))
+    rc = lib.sd_centre_features(ctx.h, comm_h, C.c_void_p(ext.data_ptr()), C.c_int64(ld), A_local.shape[0], D, n_global, C.byref(reg), C.c_void_p(mu.data_ptr()))
     if not rc:
         rc = lib.sd_learn_centred(ctx.h, comm_h, C.c_void_p(ext.data_ptr()), C.c_int64(ld), C.c_void_p(ext.data_ptr() + 4 * D), C.c_int64(ld),
                                   A_local.shape[0], D, M, C.byref(reg), n_global, int(distributed_solve), C.c_void_p(mu.data_ptr()),
