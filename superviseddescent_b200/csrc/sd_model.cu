@@ -222,9 +222,13 @@ sd_roi face_roi(const sd_model* m, const float* x0, int width, int height, int r
     for (int i = 0; i < m->norm.n_left; ++i) { lxs += x0[m->norm.left_idx[i]]; lys += x0[m->norm.left_idx[i] + L]; }
     rxs /= m->norm.n_right; rys /= m->norm.n_right; lxs /= m->norm.n_left; lys /= m->norm.n_left;
     const float ied = std::sqrt((rxs - lxs) * (rxs - lxs) + (rys - lys) * (rys - lys));
-    float rel = 0.f;
-    for (const auto& hp : m->hog) rel = hp.relative_patch_size > rel ? hp.relative_patch_size : rel;
-    const float grow = 0.5f * rel * ied * 1.1f + 0.2f * ied + 4.f;        // half patch (IED may grow a little) + drift
+    // per level: half patch (the IED may grow a little) + how far the landmarks may have drifted by then (none at level 0)
+    float grow = 0.f;
+    for (size_t l = 0; l < m->hog.size(); ++l) {
+        const float g = 0.5f * m->hog[l].relative_patch_size * ied * 1.1f + (l > 0 ? 0.2f * ied : 0.f);
+        grow = g > grow ? g : grow;
+    }
+    grow += 4.f;
     int xa = (int)std::floor(minx - grow), xb = (int)std::ceil(maxx + grow);
     int ya = (int)std::floor(miny - grow), yb = (int)std::ceil(maxy + grow);
     xa = xa < 0 ? 0 : xa; ya = ya < 0 ? 0 : ya;

@@ -62,9 +62,9 @@ def test_training_levels_teacher_forced(sd, oracle, golden, mode):
             b_ref = ((cur - x_gt) * (1.0 / np.array([oracle.get_ied(cur[i], om.right_idx, om.left_idx) for i in range(n)])).astype(np.float32)[:, None]).astype(np.float32)
             X_f32, _ = oracle.solve(A_ref, b_ref, oracle.Regulariser(1, 1.5, 0), 0)
             print(f"   float32 reference-order oracle vs float64: weights {rel_err(X_f32, X_ref):.2e}; ours vs that oracle: {rel_err(X, X_f32):.2e}")
-            # last-column-first elimination removes the cancellation that costs the reference three digits: the
-            # tensor-core Gram holds the weights to north_star's 1e-4; the plain fp32 SIMT Gram (mode 2, ~3e-7 per entry) to 5e-4
-            assert e_w <= (1e-4 if mode == 0 else 5e-4)
+            # centred features + last-column-first elimination remove the cancellation that costs the reference three
+            # digits
+            assert e_w <= 2e-5          # achieved ~1e-6 (both Gram kernels): 1000x closer to the float64 weights than the reference
             cur = nxt_ref
     finally:
         ctx.set_gram_mode(0)
