@@ -149,6 +149,7 @@ void sd_ctx_destroy(sd_ctx* ctx)
         if (ctx->stage_done[i]) cudaEventDestroy(ctx->stage_done[i]);
     }
     for (int i = 0; i < 6; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    for (int i = 0; i < 8; ++i) if (ctx->cg_ev[i]) cudaEventDestroy(ctx->cg_ev[i]);
     if (ctx->pack_pool) sd_pack_pool_destroy(ctx->pack_pool);
     for (int i = 0; i < 2; ++i) if (ctx->h_stage[i]) cudaFreeHost(ctx->h_stage[i]);
     if (ctx->h_scratch) cudaFreeHost(ctx->h_scratch);

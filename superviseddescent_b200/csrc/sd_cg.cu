@@ -188,7 +188,8 @@ int sd_cg_solve(sd_ctx* ctx, sd_comm* comm, float* G, int64_t ldg, int n, int co
     CgBuf b;
     b.nblk = 2 * ctx->sm_count;
     const size_t vec = (size_t)n * Mp;
-    const size_t floats = 3 * vec + (size_t)M * ldq + 4 * CG_MAXCOLS + 64;
+    const size_t tile_cap = ((size_t)sd_div_up(n, 256) + 1) * ((size_t)sd_div_up(M, 128) + 1) * 2;       // int2 entries, as floats
+    const size_t floats = 3 * vec + (size_t)M * ldq + 4 * CG_MAXCOLS + 64 + tile_cap + 8;
     const size_t bytes = floats * sizeof(float) + (size_t)2 * b.nblk * CG_MAXCOLS * sizeof(double) + 256;
     char* ws = (char*)sd_workspace(ctx, SD_WS_CG, bytes);
     if (!ws) return SD_ERR_CUDA;
@@ -198,6 +199,7 @@ int sd_cg_solve(sd_ctx* ctx, sd_comm* comm, float* G, int64_t ldg, int n, int co
     float* tail = b.Qt + (size_t)M * ldq;
     tail = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tail) + 15) & ~(uintptr_t)15);
     b.rs = tail; b.bb = tail + 2 * CG_MAXCOLS; b.conv = tail + 3 * CG_MAXCOLS;
+    void* d_tile_buf = tail + 3 * CG_MAXCOLS + 16;
 
     // this rank's slab of the contraction (rows of S), multiples of 16 rows
     int k0 = 0, k1 = n;
@@ -217,22 +219,35 @@ int sd_cg_solve(sd_ctx* ctx, sd_comm* comm, float* G, int64_t ldg, int n, int co
     cg_init_finish_kernel<<<1, 256, 0, ctx->stream>>>(b, M);
     SD_LAUNCH_CHECK(ctx, "cg_init_finish_kernel");
 
-    static const float tol = getenv("SD_B200_CG_TOL") ? (float)atof(getenv("SD_B200_CG_TOL")) : 5e-7f;
+    static const float tol = getenv("SD_B200_CG_TOL") ? (float)atof(getenv("SD_B200_CG_TOL")) : 2e-6f;
     static const int max_iter = getenv("SD_B200_CG_MAXIT") ? atoi(getenv("SD_B200_CG_MAXIT")) : 600;
     // split the contraction in two when one pass of tiles would leave more than half of the SMs idle
     const int tiles = sd_div_up(n, 256) * sd_div_up(M, 128);
     const int ksplit = (nranks == 1 && 2 * tiles <= ctx->sm_count) ? 2 : 1;
-    float* h_conv = reinterpret_cast<float*>(reinterpret_cast<char*>(ctx->h_scratch) + 192);
-    int it = 0, rc = SD_OK, prev_it = 0;
+    // the product is the same launch every iteration: Qt[M x n] = P[k0:k1, :]^T S[k0:k1, :]  ( = (S P)^T summed over the ranks'
+    // slabs: S is symmetric ); prepared once (tensor maps, tile list)
+    alignas(64) unsigned char plan[SD_TC_PLAN_BYTES];
+    bool no_tiles = true;
+    int rc = SD_OK;
+    if (k1 > k0) {
+        rc = sd_gemm_tn_tc_prepare(ctx, b.P + (size_t)k0 * Mp, Mp, G + (size_t)k0 * ldg, ldg, k1 - k0, M, n, b.Qt, ldq, 1.0f,
+                                   ksplit > 1 ? 1.0f : 0.0f, 3, true, false, nullptr, ksplit, d_tile_buf, plan, &no_tiles);
+        if (rc) return rc;
+    }
+    // convergence read-backs: slot it % 8 holds {max relative residual, breakdown flag} after iteration it; the host looks at the
+    // slot of LAG iterations ago, so the GPU never waits for the host
+    constexpr int LAG = 3;
+    float* h_conv = reinterpret_cast<float*>(reinterpret_cast<char*>(ctx->h_scratch) + 2048);
+    for (int i = 0; i < 8; ++i)
+        if (!ctx->cg_ev[i]) SD_CUDA(ctx, cudaEventCreateWithFlags(&ctx->cg_ev[i], cudaEventDisableTiming));
+    int it = 0, prev_it = 0, done_at = -1;
     float prev_conv = 0.f;
-    bool converged = false;
-    for (; it < max_iter && !converged; ++it) {
+    bool converged = false, failed = false;
+    for (; it < max_iter && !converged && !failed; ++it) {
         const int parity = it & 1;
-        if (ksplit > 1 || k1 <= k0) SD_CUDA(ctx, cudaMemsetAsync(b.Qt, 0, (size_t)M * ldq * sizeof(float), ctx->stream));
-        if (k1 > k0) {
-            // Qt[M x n] = P[k0:k1, :]^T S[k0:k1, :]   ( = (S P)^T summed over the ranks' slabs: S is symmetric )
-            rc = sd_gemm_tn_tc(ctx, b.P + (size_t)k0 * Mp, Mp, G + (size_t)k0 * ldg, ldg, k1 - k0, M, n, b.Qt, ldq, 1.0f,
-                               ksplit > 1 ? 1.0f : 0.0f, 3, true, false, nullptr, ksplit);
+        if (ksplit > 1 || no_tiles) SD_CUDA(ctx, cudaMemsetAsync(b.Qt, 0, (size_t)M * ldq * sizeof(float), ctx->stream));
+        if (!no_tiles) {
+            rc = sd_gemm_tn_tc_launch(ctx, plan);
             if (rc) return rc;
         }
         if (nranks > 1) {
@@ -245,23 +260,32 @@ int sd_cg_solve(sd_ctx* ctx, sd_comm* comm, float* G, int64_t ldg, int n, int co
         SD_LAUNCH_CHECK(ctx, "cg_update_xr_kernel");
         cg_update_p_kernel<<<b.nblk, blk, 0, ctx->stream>>>(b, n, M, Mp, parity);
         SD_LAUNCH_CHECK(ctx, "cg_update_p_kernel");
-        if (it >= 5 && (it % 3) == 2) {                  // look at the residual every third iteration
-            SD_CUDA(ctx, cudaMemcpyAsync(h_conv, b.conv, 2 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-            SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-            if (h_conv[1] != 0.f || !(h_conv[0] == h_conv[0])) { if (iters) *iters = it + 1; return SD_ERR_NUMERIC; }
-            converged = h_conv[0] <= tol;
-            // a system that would need more than max_iter iterations at the observed rate is the factorisation's job
-            if (!converged && it >= 30 && prev_conv > 0.f) {
-                const double rate = pow((double)h_conv[0] / (double)prev_conv, 1.0 / (double)(it - prev_it));
-                if (rate >= 1.0 || (double)it + log((double)tol / (double)h_conv[0]) / log(rate) > (double)max_iter) {
-                    if (iters) *iters = it + 1;
-                    return SD_ERR_NUMERIC;
-                }
+        SD_CUDA(ctx, cudaMemcpyAsync(h_conv + 2 * (it & 7), b.conv, 2 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        SD_CUDA(ctx, cudaEventRecord(ctx->cg_ev[it & 7], ctx->stream));
+        const int look = it - LAG;
+        if (look >= 4) {
+            SD_CUDA(ctx, cudaEventSynchronize(ctx->cg_ev[look & 7]));
+            const float cv = h_conv[2 * (look & 7)], bad = h_conv[2 * (look & 7) + 1];
+            if (bad != 0.f || !(cv == cv)) { failed = true; break; }
+            if (cv <= tol) { converged = true; done_at = look + 1; }
+            else if (look >= 30 && prev_conv > 0.f && look > prev_it) {
+                // a system that would need more than max_iter iterations at the observed rate is the factorisation's job
+                const double rate = pow((double)cv / (double)prev_conv, 1.0 / (double)(look - prev_it));
+                if (rate >= 1.0 || (double)look + log((double)tol / (double)cv) / log(rate) > (double)max_iter) { failed = true; break; }
             }
-            prev_conv = h_conv[0];
-            prev_it = it;
+            if ((look % 8) == 0) { prev_conv = cv; prev_it = look; }
         }
     }
+    if (!converged && !failed) {
+        // drain: the last LAG iterations have not been looked at yet
+        SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        for (int look = it - LAG < 0 ? 0 : it - LAG; look < it; ++look) {
+            const float cv = h_conv[2 * (look & 7)], bad = h_conv[2 * (look & 7) + 1];
+            if (bad != 0.f || !(cv == cv)) failed = true;
+            else if (cv <= tol) converged = true;
+        }
+    }
+    (void)done_at;
     if (iters) *iters = it;
     if (!converged) return SD_ERR_NUMERIC;
     *W_out = b.X;

@@ -520,21 +520,32 @@ bool sd_syrk_tc_supported(const float* d_S, int64_t lds, int K, int MI, int NJ, 
     return K >= 1 && (reinterpret_cast<uintptr_t>(d_S) & 15) == 0 && (lds % 4) == 0;
 }
 
+// A prepared launch of the kernel: tensor maps, tile list (already on the device) and arguments.  Preparing costs three
+// cuTensorMapEncodeTiled calls, the tile enumeration and a small host->device copy; iterative callers (sd_cg.cu) prepare once.
+struct sd_tc_plan {
+    CUtensorMap map_a, map_b, map_c;
+    TcArgs args;
+    int grid;
+};
+static_assert(sizeof(sd_tc_plan) <= SD_TC_PLAN_BYTES, "sd_tc_plan storage");
+
 // C[i,j] = beta*C[i,j] + alpha * sum_{k<K} SA[k,i] * SB[k,j],  i < MI, j < NJ.   SA: K x MI (lda), SB: K x NJ (ldb), both row-major,
 // i.e. both operands MN-major.  upper_only keeps the tiles that intersect j >= i (SYRK: SA == SB).  `rows` (optional) keeps the
 // tiles whose C rows belong to this rank's block rows (distributed trailing update).  C may alias SB when every CTA's column
 // range of SB is read completely before its tile is written: true for MI <= 128 (one tile row; each tile's operand columns are
-// its own output columns) -- the in-place block-row solve of the Cholesky relies on that.
-int sd_gemm_tn_tc(sd_ctx* ctx, const float* d_SA, int64_t lda, const float* d_SB, int64_t ldb, int K, int MI, int NJ,
-                  float* d_C, int64_t ldc, float alpha, float beta, int passes, bool unbiased_split, bool upper_only,
-                  const sd_row_filter* rows, int ksplit)
+// its own output columns).  d_tiles: device buffer for the tile list (at least sd_tc_max_tiles(MI, NJ) int2), or NULL to use the
+// context's workspace.  *empty is set when no tile survives the filters (nothing to launch).
+int sd_gemm_tn_tc_prepare(sd_ctx* ctx, const float* d_SA, int64_t lda, const float* d_SB, int64_t ldb, int K, int MI, int NJ,
+                          float* d_C, int64_t ldc, float alpha, float beta, int passes, bool unbiased_split, bool upper_only,
+                          const sd_row_filter* rows, int ksplit, void* d_tiles_buf, void* plan_storage, bool* empty)
 {
+    sd_tc_plan* plan = reinterpret_cast<sd_tc_plan*>(plan_storage);
+    *empty = true;
     if (MI <= 0 || NJ <= 0 || K <= 0) return SD_OK;
     SD_REQUIRE(ctx, passes == 1 || passes == 3, "passes must be 1 or 3");
-    CUtensorMap map_a, map_b;
-    int rc = make_map(ctx, &map_a, d_SA, lda, K, MI);
+    int rc = make_map(ctx, &plan->map_a, d_SA, lda, K, MI);
     if (rc) return rc;
-    rc = make_map(ctx, &map_b, d_SB, ldb, K, NJ);
+    rc = make_map(ctx, &plan->map_b, d_SB, ldb, K, NJ);
     if (rc) return rc;
 
     // tile list, ordered by super-tiles so that concurrently running tiles share operand columns in L2
@@ -549,12 +560,12 @@ int sd_gemm_tn_tc(sd_ctx* ctx, const float* d_SA, int64_t lda, const float* d_SB
                     if (!upper_only || tj * BN + BN - 1 >= ti * BM) tiles.push_back(make_int2(ti, tj));
             }
     if (tiles.empty()) return SD_OK;
-    // the list travels through a small pinned ring so that the copy never blocks the host behind running kernels
-    int2* d_tiles = (int2*)sd_workspace(ctx, SD_WS_DIAGINV, tiles.size() * sizeof(int2));
+    int2* d_tiles = (int2*)d_tiles_buf;
+    if (!d_tiles) d_tiles = (int2*)sd_workspace(ctx, SD_WS_DIAGINV, tiles.size() * sizeof(int2));
     if (!d_tiles) return SD_ERR_CUDA;
     SD_CUDA(ctx, cudaMemcpyAsync(d_tiles, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
 
-    TcArgs a;
+    TcArgs& a = plan->args;
     a.K = K; a.MI = MI; a.NJ = NJ; a.C = d_C; a.ldc = ldc; a.alpha = alpha; a.beta = beta; a.passes = passes;
     a.unbiased = (ctx->gram_mode == 3 || unbiased_split) ? 1 : 0;
     const int num_k = sd_div_up(K, BK);
@@ -564,21 +575,40 @@ int sd_gemm_tn_tc(sd_ctx* ctx, const float* d_SA, int64_t lda, const float* d_SB
     a.ksplit = sd_div_up(num_k, a.kps);                   // every range non-empty
     a.tiles = d_tiles; a.num_tiles = (int)tiles.size() * a.ksplit;
     const int sms = ctx->sm_count - ctx->syrk_sm_reserve > 0 ? ctx->sm_count - ctx->syrk_sm_reserve : 1;
-    const int grid = a.num_tiles < sms ? a.num_tiles : sms;
+    plan->grid = a.num_tiles < sms ? a.num_tiles : sms;
     // C goes back through the TMA when it can be described by a tensor map (16-byte aligned base and pitch)
-    CUtensorMap map_c = map_b;
+    plan->map_c = plan->map_b;
     a.tma_c = 0;
     if ((beta == 0.f || beta == 1.f) && (ldc % 4) == 0 && (reinterpret_cast<uintptr_t>(d_C) & 15) == 0 && !getenv("SD_B200_NO_TMA_C")) {
-        rc = make_map_c(ctx, &map_c, d_C, ldc, MI, NJ);
+        rc = make_map_c(ctx, &plan->map_c, d_C, ldc, MI, NJ);
         if (rc) return rc;
         a.tma_c = beta == 1.f ? 2 : 1;
     }
     // split K: the ranges of one tile add into C in any order, which is only reproducible for two of them (a + b == b + a)
     SD_REQUIRE(ctx, a.ksplit == 1 || (a.tma_c == 2 && a.ksplit == 2), "split-K needs beta == 1, the TMA reduce-add write-back and two ranges");
     SD_CUDA(ctx, cudaFuncSetAttribute(syrk_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
-    syrk_tc2_kernel<<<grid, T2_THREADS, SMEM2_BYTES, ctx->stream>>>(map_a, map_b, map_c, a);
+    *empty = false;
+    return SD_OK;
+}
+
+int sd_gemm_tn_tc_launch(sd_ctx* ctx, const void* plan_storage)
+{
+    const sd_tc_plan* plan = reinterpret_cast<const sd_tc_plan*>(plan_storage);
+    syrk_tc2_kernel<<<plan->grid, T2_THREADS, SMEM2_BYTES, ctx->stream>>>(plan->map_a, plan->map_b, plan->map_c, plan->args);
     SD_LAUNCH_CHECK(ctx, "syrk_tc2_kernel");
     return SD_OK;
+}
+
+int sd_gemm_tn_tc(sd_ctx* ctx, const float* d_SA, int64_t lda, const float* d_SB, int64_t ldb, int K, int MI, int NJ,
+                  float* d_C, int64_t ldc, float alpha, float beta, int passes, bool unbiased_split, bool upper_only,
+                  const sd_row_filter* rows, int ksplit)
+{
+    alignas(64) unsigned char storage[SD_TC_PLAN_BYTES];
+    bool empty = true;
+    int rc = sd_gemm_tn_tc_prepare(ctx, d_SA, lda, d_SB, ldb, K, MI, NJ, d_C, ldc, alpha, beta, passes, unbiased_split, upper_only, rows, ksplit,
+                                   nullptr, storage, &empty);
+    if (rc || empty) return rc;
+    return sd_gemm_tn_tc_launch(ctx, storage);
 }
 
 int sd_syrk_tc(sd_ctx* ctx, const float* d_S, int64_t lds, int K, int MI, int NJ, float* d_C, int64_t ldc,

@@ -43,6 +43,7 @@ struct sd_ctx {
     int gram_mode = 0;
     int solver_mode = 0;           // systems with D > 256: 0 = blocked Cholesky, 1 = conjugate gradients (Cholesky if they stall)
     int cg_iterations = 0;         // of the last solve (0: the factorisation ran)
+    cudaEvent_t cg_ev[8] = {};     // convergence read-backs of the CG loop (the host runs a few iterations ahead of them)
     bool disable_roi = false;      // sd_detect_batch_host: always upload whole frames
     int64_t roi_fallbacks = 0;     // faces repeated from the full frame because a patch left its ROI
     float timings[4] = {0, 0, 0, 0};
@@ -117,6 +118,13 @@ int sd_check_hog_status(sd_ctx* ctx, const char* what);   // sd_api.cu: synchron
 
 // numerical rank of the symmetric matrix whose upper triangle is in d_G (pivoted Cholesky, sd_rank.cu); rank -1: not computed
 int sd_gram_rank(sd_ctx* ctx, const float* d_G, int64_t ldg, int D, int* rank_out, float* first_pivot, float* last_pivot);
+
+// prepared launches of the tensor-core TN-GEMM (sd_gram_tc.cu): plan_storage = SD_TC_PLAN_BYTES bytes, 64-byte aligned
+#define SD_TC_PLAN_BYTES 640
+int sd_gemm_tn_tc_prepare(sd_ctx* ctx, const float* d_SA, int64_t lda, const float* d_SB, int64_t ldb, int K, int MI, int NJ,
+                          float* d_C, int64_t ldc, float alpha, float beta, int passes, bool unbiased_split, bool upper_only,
+                          const sd_row_filter* rows, int ksplit, void* d_tiles_buf, void* plan_storage, bool* empty);
+int sd_gemm_tn_tc_launch(sd_ctx* ctx, const void* plan_storage);
 
 // multi-GPU helpers (sd_comm.cu); a null communicator is a single rank
 int sd_comm_rank_of(const sd_comm* c);
