@@ -49,6 +49,7 @@ struct HogArgs {
     const int* rtab;            // per sample: resize tables [5][fs] (hog_geometry_kernel)
     const float* btab;          // per launch: spatial binning weights [nc][fs], then lo[nc], hi[nc] (hog_bintab_kernel)
     int tma_count;              // number of usable tensor-map size classes (0: the window is staged by load loops)
+    int flags;                  // experiment switches: 1 = column-fixed resize, 2 = fused gradient + segment vote
     float* A;
     long long ld;
     int* geometry;
@@ -403,7 +404,7 @@ __global__ void __launch_bounds__(kHogThreads) hog_patch_kernel(const HogArgs a,
                     if (!ok && clock64() - t0 > 4000000000LL) __trap();
                 }
             }
-            if (fs <= 64) {
+            if (fs <= 64 && (a.flags & 1)) {
                 // a thread keeps ONE output column (its two source taps and weights stay in registers) and walks down the rows
                 const int dx = tid & 63, g = tid >> 6;
                 if (dx < fs) {
@@ -474,6 +475,7 @@ __global__ void __launch_bounds__(kHogThreads) hog_patch_kernel(const HogArgs a,
     }
     __syncthreads();
 
+    if (a.flags & 2) {
     // ---- S2 + S3, fused: gradient, orientation arg-max and modulus per interior pixel (hog.c:631-672; both from the device-
     //      generated tables: the gradient of an 8-bit patch is a pair of integers in [-255, 255]) and the bilinear spatial vote
     //      (hog.c:697-724), which is separable:
@@ -554,6 +556,65 @@ __global__ void __launch_bounds__(kHogThreads) hog_patch_kernel(const HogArgs a,
         }
     }
     __syncthreads();
+
+    } else {
+    // ---- S2: gradient + orientation arg-max per interior pixel (hog.c:631-672): arg-max and modulus come from the
+    //      device-generated tables (the gradient of an 8-bit patch is a pair of integers in [-255, 255]) ---------
+    for (int y = 1 + warp; y <= fs - 2; y += kHogWarps) {
+        for (int x = 1 + lane; x <= fs - 2; x += 32) {
+            const int idx = y * fs + x;
+            const int gx = (int)s_patch[idx + 1] - (int)s_patch[idx - 1];
+            const int gy = (int)s_patch[idx + fs] - (int)s_patch[idx - fs];
+            s_bin[idx] = __ldg(a.lut + (gy + 255) * kLutDim + (gx + 255));
+            s_gmag[idx] = __ldg(a.mag_lut + (gx * gx + gy * gy));
+        }
+    }
+    if (a.bins) {
+        __syncthreads();
+        for (int idx = tid; idx < fs * fs; idx += kHogThreads) {
+            const int y = idx / fs, x = idx - y * fs;
+            const bool interior = x >= 1 && x <= fs - 2 && y >= 1 && y <= fs - 2;
+            a.bins[patch_id * fs * fs + idx] = interior ? s_bin[idx] : (int8_t)-1;
+        }
+    }
+    __syncthreads();
+
+    // ---- S3: bilinear spatial vote (hog.c:697-724), separable:  hist[b][cj][ci] = sum_y wy[cj][y] * ( sum_x wx[ci][x] * g[y][x] * [bin[y][x] == b] ).
+    //      Pass 1: one thread per (cell column ci, interior row y) walks the <= 2*cs pixels of that row that vote into ci and adds
+    //      g * wx into ITS OWN column of T[bin][task] (bank == task mod 32: conflict free, no atomics, fixed order).
+    //      Pass 2: one thread per (bin, cell) folds the rows with wy.  The reference adds (g * wx) * wy per pixel in raster
+    //      order; this is the same sum associated differently (~1e-7 relative), deterministic.
+    {
+        const int nrow = fs - 2, ntask = nrow * nc, tpad = lay.tpad;
+        for (int task = tid; task < ntask; task += kHogThreads) {
+            const int ci = task / nrow, y = 1 + task - ci * nrow;
+            const int xlo = s_lo[ci], xhi = s_hi[ci];
+            const int8_t* bp = s_bin + y * fs + xlo;
+            const float* gp = s_gmag + y * fs + xlo;
+            const float* wp = s_wcell + ci * fs + xlo;
+            float* T = s_T + task;
+#pragma unroll 2
+            for (int x = xlo; x <= xhi; ++x) {
+                const int b = max((int)*bp++, 0);                     // zero gradient: bin -1, modulus 0 -> adds +0 to bin 0
+                float* q = T + b * tpad;
+                *q = __fadd_rn(*q, __fmul_rn(*gp++, *wp++));
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < 2 * K * cells; i += kHogThreads) {
+            const int b = i / cells, c = i - b * cells;
+            const int cj = c / nc, ci = c - cj * nc;                  // cell row (y), cell column (x)
+            const int ylo = s_lo[cj], yhi = s_hi[cj];
+            const float* Tp = s_T + b * tpad + ci * nrow + (ylo - 1);
+            const float* wy = s_wcell + cj * fs + ylo;
+            float acc = 0.f;
+            for (int y = ylo; y <= yhi; ++y) acc = __fadd_rn(acc, __fmul_rn(*Tp++, *wy++));
+            s_hist[b * cells + c] = acc;
+        }
+    }
+    __syncthreads();
+
+    }
 
     // ---- S4: undirected cell energy (hog.c:875-890) -------------------------------------------
     for (int c = tid; c < cells; c += kHogThreads) {
@@ -751,6 +812,7 @@ int launch_hog(sd_ctx* ctx, const sd_image_batch* images, const int32_t* d_image
     HogMaps maps;
     memset(&maps, 0, sizeof(maps));
     a.tma_count = 0;
+    { static const int f = getenv("SD_B200_HOG_FLAGS") ? atoi(getenv("SD_B200_HOG_FLAGS")) : 0; a.flags = f; }
     if (!images->d_roi && !images->d_frames && (reinterpret_cast<uintptr_t>(images->d_data) & 15) == 0 && (images->row_stride % 16) == 0 &&
         (images->image_stride % 16) == 0 && (images->count == 1 || images->image_stride > 0) && !getenv("SD_B200_HOG_NO_TMA")) {
         PFN_hogEncodeTiled enc = hog_encode_fn();
