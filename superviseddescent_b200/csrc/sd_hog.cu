@@ -49,7 +49,6 @@ struct HogArgs {
     const int* rtab;            // per sample: resize tables [5][fs] (hog_geometry_kernel)
     const float* btab;          // per launch: spatial binning weights [nc][fs], then lo[nc], hi[nc] (hog_bintab_kernel)
     int tma_count;              // number of usable tensor-map size classes (0: the window is staged by load loops)
-    int flags;                  // experiment switches: 1 = column-fixed resize, 2 = fused gradient + segment vote
     float* A;
     long long ld;
     int* geometry;
@@ -135,14 +134,6 @@ __global__ void hog_bintab_kernel(int fs, int nc, int cs, float* __restrict__ bt
         lohi[c] = lo;
         lohi[nc + c] = hi;
     }
-    // segments: the interior coordinates whose own bin is s, s = -1 .. nc-1 (a pixel of segment s votes into cells s and s+1)
-    for (int s = (int)threadIdx.x - 1; s < nc; s += blockDim.x) {
-        int lo = fs, hi = -1;
-        for (int t = 1; t <= fs - 2; ++t)
-            if (s_sbin[t] == s) { if (t < lo) lo = t; hi = t; }
-        lohi[2 * nc + (s + 1)] = lo;
-        lohi[2 * nc + (nc + 1) + (s + 1)] = hi;
-    }
 }
 
 // sqrtf of every possible squared gradient modulus of an 8-bit patch (gx, gy in [-255, 255]): hog.c:645 takes sqrtf of the
@@ -187,7 +178,7 @@ __global__ void hog_lut_kernel(const LutArgs t, int8_t* __restrict__ lut)
 
 // shared-memory carve-up (same function on host and device)
 struct HogSmem {
-    int patch, bin, r1, xofs, yofs0, yofs1, xa, yb, wcell, lo, hi, seg, hist, energy, fac, vote, feat, mbar, total;
+    int patch, bin, r1, xofs, yofs0, yofs1, xa, yb, wcell, lo, hi, hist, energy, fac, vote, feat, mbar, total;
     int tpad;      // tasks of the horizontal vote pass, padded to a multiple of 32
 };
 
@@ -211,13 +202,12 @@ __host__ __device__ inline HogSmem hog_smem_layout(int fs, int nc, int K, int dd
     s.wcell = o;  o += nc * fs * 4;                         // weight of pixel t for cell index c (0 if it does not vote)
     s.lo = o;     o += nc * 4;
     s.hi = o;     o += nc * 4;
-    s.seg = o;    o += 2 * (nc + 1) * 4;                    // first / last interior coordinate of segment s = -1 .. nc-1
     s.hist = o;   o += cells * 2 * K * 4;
     s.energy = o; o = align_up(o + cells * 4, 16);
     s.fac = o;    o += cells * 4 * 8;
     s.tpad = align_up((fs - 2) * nc, 32);
     o = align_up(o, 16);
-    s.vote = o;   o += 2 * 2 * K * s.tpad * 4;              // horizontal pass of the vote: T1 | T2 [bin][(cell column, row)]
+    s.vote = o;   o += 2 * K * s.tpad * 4;                  // horizontal pass of the vote: T[bin][(cell column, row)]
     s.feat = o;   o += cells * dd * 4;
     s.mbar = align_up(o, 8); o = s.mbar + 8;
     s.total = align_up(o, 16);
@@ -234,7 +224,7 @@ __host__ __device__ constexpr int hog_tma_box(int c) { return c == 0 ? 32 : c ==
 struct HogMaps { CUtensorMap m[kTmaClasses]; };
 
 template <int KT, int NCT, int CST>
-__global__ void __launch_bounds__(kHogThreads) hog_patch_kernel(const HogArgs a, const __grid_constant__ HogMaps maps)
+__global__ void __launch_bounds__(kHogThreads, 6) hog_patch_kernel(const HogArgs a, const __grid_constant__ HogMaps maps)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     const int K = KT > 0 ? KT : a.K;
@@ -255,7 +245,6 @@ __global__ void __launch_bounds__(kHogThreads) hog_patch_kernel(const HogArgs a,
     float* s_wcell = reinterpret_cast<float*>(smem + lay.wcell);
     int* s_lo = reinterpret_cast<int*>(smem + lay.lo);
     int* s_hi = reinterpret_cast<int*>(smem + lay.hi);
-    int* s_seg = reinterpret_cast<int*>(smem + lay.seg);
     float* s_hist = reinterpret_cast<float*>(smem + lay.hist);
     float* s_energy = reinterpret_cast<float*>(smem + lay.energy);
     double* s_fac = reinterpret_cast<double*>(smem + lay.fac);
@@ -343,9 +332,8 @@ __global__ void __launch_bounds__(kHogThreads) hog_patch_kernel(const HogArgs a,
         for (int i = tid; i < nc * fs; i += kHogThreads) s_wcell[i] = __ldg(a.btab + i);
         const int* __restrict__ lohi = reinterpret_cast<const int*>(a.btab + nc * fs);
         if (tid < nc) { s_lo[tid] = __ldg(lohi + tid); s_hi[tid] = __ldg(lohi + nc + tid); }
-        if (tid < 2 * (nc + 1)) s_seg[tid] = __ldg(lohi + 2 * nc + tid);
         float4* T4 = reinterpret_cast<float4*>(s_T);
-        for (int i = tid; i < K * lay.tpad; i += kHogThreads) T4[i] = make_float4(0.f, 0.f, 0.f, 0.f);     // 4K * tpad floats
+        for (int i = tid; i < K * lay.tpad / 2; i += kHogThreads) T4[i] = make_float4(0.f, 0.f, 0.f, 0.f);     // 2K * tpad floats
     }
     {
         const bool resident = x0 >= rx && y0 >= ry && x0 + P <= rx + rw && y0 + P <= ry + rh && x0 >= 0 && y0 >= 0 && x0 + P <= W && y0 + P <= H;
@@ -404,7 +392,7 @@ __global__ void __launch_bounds__(kHogThreads) hog_patch_kernel(const HogArgs a,
                     if (!ok && clock64() - t0 > 4000000000LL) __trap();
                 }
             }
-            if (fs <= 64 && (a.flags & 1)) {
+            if (fs <= 64) {
                 // a thread keeps ONE output column (its two source taps and weights stay in registers) and walks down the rows
                 const int dx = tid & 63, g = tid >> 6;
                 if (dx < fs) {
@@ -475,89 +463,6 @@ __global__ void __launch_bounds__(kHogThreads) hog_patch_kernel(const HogArgs a,
     }
     __syncthreads();
 
-    if (a.flags & 2) {
-    // ---- S2 + S3, fused: gradient, orientation arg-max and modulus per interior pixel (hog.c:631-672; both from the device-
-    //      generated tables: the gradient of an 8-bit patch is a pair of integers in [-255, 255]) and the bilinear spatial vote
-    //      (hog.c:697-724), which is separable:
-    //          hist[b][cj][ci] = sum_y wy[cj][y] * ( sum_x wx[ci][x] * g[y][x] * [bin[y][x] == b] ).
-    //      Pass 1 visits every interior pixel ONCE.  The pixels of a row whose own bin is s ("segment" s) vote into cell columns s
-    //      (weight w1) and s+1 (weight w2); one thread per (row, segment) -- the two border segments share a thread -- adds g * w1
-    //      into T1[bin][s][row] and g * w2 into T2[bin][s+1][row], locations no other thread touches (no atomics, fixed order;
-    //      consecutive lanes own consecutive rows: bank = row mod 32).  Pass 2: one thread per (bin, cell) folds the rows of T1 + T2
-    //      with wy.  The reference adds (g * wx) * wy per pixel in raster order; this is the same sum associated differently
-    //      (~1e-7 relative), deterministic.
-    if (a.bins) {                                                     // parity tap: per-pixel orientation bins
-        for (int idx = tid; idx < fs * fs; idx += kHogThreads) {
-            const int y = idx / fs, x = idx - y * fs;
-            int bin = -1;
-            if (x >= 1 && x <= fs - 2 && y >= 1 && y <= fs - 2) {
-                const int gx = (int)s_patch[idx + 1] - (int)s_patch[idx - 1];
-                const int gy = (int)s_patch[idx + fs] - (int)s_patch[idx - fs];
-                bin = __ldg(a.lut + (gy + 255) * kLutDim + (gx + 255));
-            }
-            a.bins[patch_id * fs * fs + idx] = (int8_t)bin;
-        }
-    }
-    {
-        const int nrow = fs - 2, ntask = nrow * nc, tpad = lay.tpad;
-        float* s_T2 = s_T + 2 * K * tpad;
-        constexpr int CH = 4;                                         // pixels whose table look-ups are in flight together
-        for (int task = tid; task < ntask; task += kHogThreads) {
-            const int t = task / nrow, y = 1 + task - t * nrow;
-            // sub-range 0: segment t < nc-1, or for the border thread (t == nc-1) segment nc-1; sub-range 1 (border thread only):
-            // segment -1.  cA >= 0: own cell (T1), cB >= 0: next cell (T2).
-            for (int part = 0; part < (t == nc - 1 ? 2 : 1); ++part) {
-                const int seg = (t == nc - 1) ? (part == 0 ? nc - 1 : -1) : t;
-                const int xa0 = s_seg[seg + 1], xb0 = s_seg[(nc + 1) + seg + 1];
-                const int cA = seg, cB = seg + 1 < nc ? seg + 1 : -1;
-                const float* wA = s_wcell + (cA >= 0 ? cA : 0) * fs;
-                const float* wB = s_wcell + (cB >= 0 ? cB : 0) * fs;
-                float* TA = s_T + (cA >= 0 ? cA : 0) * nrow + (y - 1);
-                float* TB = s_T2 + (cB >= 0 ? cB : 0) * nrow + (y - 1);
-                const uint8_t* prow = s_patch + y * fs;
-                for (int x0 = xa0; x0 <= xb0; x0 += CH) {
-                    int bn[CH];
-                    float mg[CH];
-#pragma unroll
-                    for (int k = 0; k < CH; ++k) {
-                        const int x = x0 + k;
-                        bn[k] = 0;
-                        mg[k] = 0.f;
-                        if (x <= xb0) {
-                            const int gx = (int)prow[x + 1] - (int)prow[x - 1];
-                            const int gy = (int)prow[x + fs] - (int)prow[x - fs];
-                            bn[k] = __ldg(a.lut + (gy + 255) * kLutDim + (gx + 255));
-                            mg[k] = __ldg(a.mag_lut + (gx * gx + gy * gy));
-                        }
-                    }
-#pragma unroll
-                    for (int k = 0; k < CH; ++k) {
-                        const int x = x0 + k;
-                        if (x <= xb0) {
-                            const int bo = max(bn[k], 0) * tpad;      // zero gradient: bin -1, modulus 0 -> adds +0 to bin 0
-                            if (cA >= 0) TA[bo] = __fadd_rn(TA[bo], __fmul_rn(mg[k], wA[x]));
-                            if (cB >= 0) TB[bo] = __fadd_rn(TB[bo], __fmul_rn(mg[k], wB[x]));
-                        }
-                    }
-                }
-            }
-        }
-        __syncthreads();
-        for (int i = tid; i < 2 * K * cells; i += kHogThreads) {
-            const int b = i / cells, c = i - b * cells;
-            const int cj = c / nc, ci = c - cj * nc;                  // cell row (y), cell column (x)
-            const int ylo = s_lo[cj], yhi = s_hi[cj];
-            const float* Tp = s_T + b * tpad + ci * nrow + (ylo - 1);
-            const float* Tq = s_T2 + b * tpad + ci * nrow + (ylo - 1);
-            const float* wy = s_wcell + cj * fs + ylo;
-            float acc = 0.f;
-            for (int y = ylo; y <= yhi; ++y) acc = __fadd_rn(acc, __fmul_rn(__fadd_rn(*Tp++, *Tq++), *wy++));
-            s_hist[b * cells + c] = acc;
-        }
-    }
-    __syncthreads();
-
-    } else {
     // ---- S2: gradient + orientation arg-max per interior pixel (hog.c:631-672): arg-max and modulus come from the
     //      device-generated tables (the gradient of an 8-bit patch is a pair of integers in [-255, 255]) ---------
     for (int y = 1 + warp; y <= fs - 2; y += kHogWarps) {
@@ -613,8 +518,6 @@ __global__ void __launch_bounds__(kHogThreads) hog_patch_kernel(const HogArgs a,
         }
     }
     __syncthreads();
-
-    }
 
     // ---- S4: undirected cell energy (hog.c:875-890) -------------------------------------------
     for (int c = tid; c < cells; c += kHogThreads) {
@@ -795,7 +698,7 @@ int launch_hog(sd_ctx* ctx, const sd_image_batch* images, const int32_t* d_image
     a.mag_lut = (const float*)ctx->hog_lut[0];
 
     // per-sample tables (half size, cv::resize taps) and the per-launch spatial binning table
-    const size_t geom_bytes = (size_t)N * sizeof(int) + (size_t)N * 5 * fs * sizeof(int) + (size_t)(a.nc * fs + 4 * a.nc + 2) * sizeof(float);
+    const size_t geom_bytes = (size_t)N * sizeof(int) + (size_t)N * 5 * fs * sizeof(int) + (size_t)(a.nc * fs + 2 * a.nc) * sizeof(float);
     int* d_half = (int*)sd_workspace(ctx, SD_WS_GEOM, geom_bytes);
     if (!d_half) return SD_ERR_CUDA;
     int* d_rtab = d_half + N;
@@ -812,7 +715,6 @@ int launch_hog(sd_ctx* ctx, const sd_image_batch* images, const int32_t* d_image
     HogMaps maps;
     memset(&maps, 0, sizeof(maps));
     a.tma_count = 0;
-    { static const int f = getenv("SD_B200_HOG_FLAGS") ? atoi(getenv("SD_B200_HOG_FLAGS")) : 0; a.flags = f; }
     if (!images->d_roi && !images->d_frames && (reinterpret_cast<uintptr_t>(images->d_data) & 15) == 0 && (images->row_stride % 16) == 0 &&
         (images->image_stride % 16) == 0 && (images->count == 1 || images->image_stride > 0) && !getenv("SD_B200_HOG_NO_TMA")) {
         PFN_hogEncodeTiled enc = hog_encode_fn();
@@ -847,6 +749,9 @@ int launch_hog(sd_ctx* ctx, const sd_image_batch* images, const int32_t* d_image
 #undef SD_HOG_PICK
     }
     SD_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, lay.total));
+    // the kernel is latency-bound (many short phases between barriers): resident CTAs per SM are what hide it -- take the whole
+    // shared-memory carve-out (six 33 KB CTAs fit 228 KB; with the default carve-out only five were resident)
+    SD_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     kern<<<(unsigned)blocks, kHogThreads, lay.total, ctx->stream>>>(a, maps);
     SD_LAUNCH_CHECK(ctx, "hog_patch_kernel");
     return SD_OK;

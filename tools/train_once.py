@@ -11,5 +11,5 @@ lv = int(os.environ.get("LEVELS", "1"))
 cfg["cell_sizes"], cfg["rel"] = cfg["cell_sizes"][:lv], cfg["rel"][:lv]
 if "N" in os.environ:
     cfg["n"] = int(os.environ["N"])
-r = bench.run_train(sd, ctx, model, 1, 0, torch.device("cuda", 0), torch.cuda.synchronize, lambda v: v, None, cfg)
+r = bench.run_train(sd, ctx, model, 1, 0, torch.device("cuda", 0), torch.cuda.synchronize, lambda v: v, None, cfg, solver=os.environ.get("SOLVER", "cholesky"))
 print(r["value"], r["last_level_solver_ms"], r["gpu_launches"], r["train_residual"], r.get("roofline"))
