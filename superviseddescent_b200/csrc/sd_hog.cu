@@ -224,7 +224,7 @@ __host__ __device__ constexpr int hog_tma_box(int c) { return c == 0 ? 32 : c ==
 struct HogMaps { CUtensorMap m[kTmaClasses]; };
 
 template <int KT, int NCT, int CST>
-__global__ void __launch_bounds__(kHogThreads, 6) hog_patch_kernel(const HogArgs a, const __grid_constant__ HogMaps maps)
+__global__ void __launch_bounds__(kHogThreads) hog_patch_kernel(const HogArgs a, const __grid_constant__ HogMaps maps)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     const int K = KT > 0 ? KT : a.K;
@@ -749,9 +749,8 @@ int launch_hog(sd_ctx* ctx, const sd_image_batch* images, const int32_t* d_image
 #undef SD_HOG_PICK
     }
     SD_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, lay.total));
-    // the kernel is latency-bound (many short phases between barriers): resident CTAs per SM are what hide it -- take the whole
-    // shared-memory carve-out (six 33 KB CTAs fit 228 KB; with the default carve-out only five were resident)
-    SD_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    // (Measured, profiles/r02_summary.md: forcing six resident CTAs per SM with the whole shared-memory carve-out is SLOWER than
+    // five with the default split -- the orientation / modulus tables live in L1, which the larger carve-out takes away.)
     kern<<<(unsigned)blocks, kHogThreads, lay.total, ctx->stream>>>(a, maps);
     SD_LAUNCH_CHECK(ctx, "hog_patch_kernel");
     return SD_OK;
