@@ -116,7 +116,8 @@ __global__ void __launch_bounds__(CG_BX * CG_BY) cg_update_xr_kernel(CgBuf b, in
     __shared__ float s_alpha[CG_MAXCOLS];
     for (int c = threadIdx.y * CG_BX + threadIdx.x; c < CG_MAXCOLS; c += CG_BX * CG_BY) {
         double pq = 0.0;
-        for (int k = 0; k < b.nblk; ++k) pq += b.part[(long long)k * CG_MAXCOLS + c];
+        if (c < M)
+            for (int k = 0; k < b.nblk; ++k) pq += b.part[(long long)k * CG_MAXCOLS + c];
         const float rs = b.rs[parity * CG_MAXCOLS + c];
         float alpha = 0.f;
         if (c < M && rs > 0.f) {
@@ -150,7 +151,8 @@ __global__ void __launch_bounds__(CG_BX * CG_BY) cg_update_p_kernel(CgBuf b, int
     __shared__ float s_rel[CG_MAXCOLS];
     for (int c = threadIdx.y * CG_BX + threadIdx.x; c < CG_MAXCOLS; c += CG_BX * CG_BY) {
         double rn = 0.0;
-        for (int k = 0; k < b.nblk; ++k) rn += b.part[((long long)b.nblk + k) * CG_MAXCOLS + c];
+        if (c < M)
+            for (int k = 0; k < b.nblk; ++k) rn += b.part[((long long)b.nblk + k) * CG_MAXCOLS + c];
         const float rs = b.rs[parity * CG_MAXCOLS + c];
         s_beta[c] = (c < M && rs > 0.f) ? (float)(rn / (double)rs) : 0.f;
         const float bbv = b.bb[c];
@@ -186,7 +188,7 @@ int sd_cg_solve(sd_ctx* ctx, sd_comm* comm, float* G, int64_t ldg, int n, int co
     const int64_t ldq = ((int64_t)n + 3) / 4 * 4;
     const int nranks = sd_comm_size_of(comm), me = sd_comm_rank_of(comm);
     CgBuf b;
-    b.nblk = 2 * ctx->sm_count;
+    b.nblk = ctx->sm_count / 2 > 16 ? ctx->sm_count / 2 : 16;      // few blocks: every block re-adds all partial sums (fixed order)
     const size_t vec = (size_t)n * Mp;
     const size_t tile_cap = ((size_t)sd_div_up(n, 256) + 1) * ((size_t)sd_div_up(M, 128) + 1) * 2;       // int2 entries, as floats
     const size_t floats = 3 * vec + (size_t)M * ldq + 4 * CG_MAXCOLS + 64 + tile_cap + 8;
