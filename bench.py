@@ -196,9 +196,9 @@ def run_reference(args):
 
 
 # static profile facts about the level-0 HOG kernel: NOT measured in the bench run, quoted from the committed ncu summary
-HOG_STATIC_PROFILE = {"source": "profiles/r01_summary.md section 12 (one `ncu --set full` capture of hog_patch_kernel<4,5,11>, 2048 faces)",
-                      "dram_bytes_per_face": (160.259584e6 + 51.714560e6) / 2048, "issue_slots_busy_pct": 76.4,
-                      "warp_instructions_per_patch": 22723}
+HOG_STATIC_PROFILE = {"source": "profiles/r02_summary.md section 2 (one `ncu --set full` capture of hog_patch_kernel<4,5,11>, 2048 faces)",
+                      "dram_bytes_per_face": (170.898432e6 + 52.981504e6) / 2048, "issue_slots_busy_pct": 61.5,
+                      "warp_instructions_per_patch": 16166, "shared_wavefronts_pct_of_lsu_path": 76}
 
 TRAIN_CFGS = {
     # SURVEY 8d config 4 / BASELINE configs[3]
@@ -352,7 +352,7 @@ def run_train(sd, ctx, model, world, rank, dev, barrier, max_over_ranks, comm, c
                            "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (dense bf16; the kernel runs kind::tf32 at half that rate, three passes)" if peaks else "fallback 1500 (B200_PROFILING.md)",
                            "ms_per_launch": solver_ms["At * A"], "algorithmic_flops_per_launch": alg,
                            "executed_tf32_tflops": syrk_executed_flops(n_loc, D, 2 * L) / t / 1e12,
-                           "static_profile": {"source": "profiles/r01_summary.md section 6", "tensor_pipe_active_pct": 72.7}}
+                           "static_profile": {"source": "profiles/r02_summary.md section 3 (ncu capture of the Gram launch)", "tensor_pipe_active_pct": 72.98}}
     out["algorithmic_tflop"] = {"gram_syrk": S * (cfg["n"] * D * (D + 1.0) + 2.0 * cfg["n"] * D * 2 * L) / 1e12, "cholesky_and_solve": S * (D ** 3 / 3.0 + 2.0 * D * D * 2 * L) / 1e12}
     if e2e:
         # the same run from HOST buffers: crops and landmark rows in pinned memory, uploads inside the timed region, the trained
