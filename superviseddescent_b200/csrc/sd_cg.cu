@@ -225,7 +225,7 @@ int sd_cg_solve(sd_ctx* ctx, sd_comm* comm, float* G, int64_t ldg, int n, int co
     static const int max_iter = getenv("SD_B200_CG_MAXIT") ? atoi(getenv("SD_B200_CG_MAXIT")) : 600;
     // split the contraction in two when one pass of tiles would leave more than half of the SMs idle
     const int tiles = sd_div_up(n, 256) * sd_div_up(M, 128);
-    const int ksplit = (nranks == 1 && 2 * tiles <= ctx->sm_count) ? 2 : 1;
+    const int ksplit = (2 * tiles <= ctx->sm_count && k1 - k0 >= 64) ? 2 : 1;
     // the product is the same launch every iteration: Qt[M x n] = P[k0:k1, :]^T S[k0:k1, :]  ( = (S P)^T summed over the ranks'
     // slabs: S is symmetric ); prepared once (tensor maps, tile list)
     alignas(64) unsigned char plan[SD_TC_PLAN_BYTES];

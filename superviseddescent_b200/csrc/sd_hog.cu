@@ -400,7 +400,7 @@ __global__ void __launch_bounds__(kHogThreads) hog_patch_kernel(const HogArgs a,
                     const int sx1 = min(sx + 1, P - 1);            // clamped tap has zero weight
                     const int ax = s_xa[dx].x, bx = s_xa[dx].y;
                     const uint8_t* base = s_stage + shiftb;
-#pragma unroll 2
+#pragma unroll 4
                     for (int dy = g; dy < fs; dy += kHogThreads / 64) {
                         const short2 yb = s_yb[dy];
                         const uint8_t* r0 = base + s_yofs0[dy] * pitch;
@@ -465,13 +465,32 @@ __global__ void __launch_bounds__(kHogThreads) hog_patch_kernel(const HogArgs a,
 
     // ---- S2: gradient + orientation arg-max per interior pixel (hog.c:631-672): arg-max and modulus come from the
     //      device-generated tables (the gradient of an 8-bit patch is a pair of integers in [-255, 255]) ---------
-    for (int y = 1 + warp; y <= fs - 2; y += kHogWarps) {
-        for (int x = 1 + lane; x <= fs - 2; x += 32) {
-            const int idx = y * fs + x;
-            const int gx = (int)s_patch[idx + 1] - (int)s_patch[idx - 1];
-            const int gy = (int)s_patch[idx + fs] - (int)s_patch[idx - fs];
-            s_bin[idx] = __ldg(a.lut + (gy + 255) * kLutDim + (gx + 255));
-            s_gmag[idx] = __ldg(a.mag_lut + (gx * gx + gy * gy));
+    {
+        // linear index over the interior pixels (all lanes busy); four pixels per thread in flight so that the eight table
+        // look-ups overlap (the phase was bound by their latency: profiles/r02_summary.md)
+        const int iw = fs - 2, npix = iw * iw;
+        for (int i0 = tid; i0 < npix; i0 += 4 * kHogThreads) {
+            int idx[4], gxs[4], gys[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int i = i0 + k * kHogThreads;
+                const int y = i / iw, x = i - y * iw;
+                idx[k] = (y + 1) * fs + (x + 1);
+                if (i < npix) {
+                    gxs[k] = (int)s_patch[idx[k] + 1] - (int)s_patch[idx[k] - 1];
+                    gys[k] = (int)s_patch[idx[k] + fs] - (int)s_patch[idx[k] - fs];
+                } else { gxs[k] = 0; gys[k] = 0; }
+            }
+            int8_t bn[4];
+            float mg[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                bn[k] = __ldg(a.lut + (gys[k] + 255) * kLutDim + (gxs[k] + 255));
+                mg[k] = __ldg(a.mag_lut + (gxs[k] * gxs[k] + gys[k] * gys[k]));
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (i0 + k * kHogThreads < npix) { s_bin[idx[k]] = bn[k]; s_gmag[idx[k]] = mg[k]; }
         }
     }
     if (a.bins) {
