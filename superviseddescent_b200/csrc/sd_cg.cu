@@ -44,36 +44,52 @@ __global__ void __launch_bounds__(256) cg_mirror_kernel(float* __restrict__ G, l
 
 struct CgBuf {
     float *X, *R, *P, *Qt;
-    double *part;          // [2][nblk][CG_MAXCOLS]
+    double *part;          // [2][nblk][CG_MAXCOLS]: partial sums of p.q and of r.r, one row per 32-row tile
     float *rs;             // [2][CG_MAXCOLS] ping-pong r.r
     float *bb;             // [CG_MAXCOLS]   b.b
+    float *ab;             // [2][CG_MAXCOLS] alpha, beta of the current iteration
     float *conv;           // [0] max_c sqrt(rs / bb) of the latest iteration; [1] breakdown flag
-    int nblk;
+    int nblk;              // number of 32-row tiles
 };
 
-// folds the CG_BY row lanes of a block and stores the block's partial sums
+constexpr int CG_TR = 32;                      // rows per tile of the vector kernels
+
+// The vectors are [row][column] (column fastest), the product arrives as Qt [column][row]: a tile kernel stages 32 rows of Qt
+// through shared memory (coalesced along the rows) and then works column-fastest like everything else.
+__device__ __forceinline__ void cg_stage_q(const CgBuf& b, int i0, int n, int M, long long ldq, float (*sq)[CG_TR + 1])
+{
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int c = w; c < M; c += 8) sq[c][lane] = (i0 + lane < n) ? b.Qt[(long long)c * ldq + i0 + lane] : 0.f;
+    __syncthreads();
+}
+
+// folds the 4 row lanes of a tile and stores the tile's partial sums
 __device__ __forceinline__ void cg_store_partials(const double (&acc)[CG_G], double* __restrict__ dst)
 {
-    __shared__ double red[CG_BY][CG_MAXCOLS];
+    __shared__ double red[4][CG_MAXCOLS];
+    const int cx = threadIdx.x & 63, ry = threadIdx.x >> 6;
 #pragma unroll
-    for (int g = 0; g < CG_G; ++g) red[threadIdx.y][threadIdx.x + g * CG_BX] = acc[g];
+    for (int g = 0; g < CG_G; ++g) red[ry][cx + g * CG_BX] = acc[g];
     __syncthreads();
-    if (threadIdx.y == 0)
+    if (ry == 0)
 #pragma unroll
         for (int g = 0; g < CG_G; ++g) {
-            const int c = threadIdx.x + g * CG_BX;
+            const int c = cx + g * CG_BX;
             dst[c] = red[0][c] + red[1][c] + red[2][c] + red[3][c];
         }
 }
 
-// R = P = B (the right-hand-side columns of G), X = 0, partial sums of b.b
-__global__ void __launch_bounds__(CG_BX * CG_BY) cg_init_kernel(const float* __restrict__ G, long long ldg, int n, int col0, int M, int Mp, CgBuf b)
+// R = P = B (the right-hand-side columns of G), X = 0, partial sums of b.b; one 32-row tile per block
+__global__ void __launch_bounds__(256) cg_init_kernel(const float* __restrict__ G, long long ldg, int n, int col0, int M, int Mp, CgBuf b)
 {
+    const int cx = threadIdx.x & 63, ry = threadIdx.x >> 6, i0 = blockIdx.x * CG_TR;
     double acc[CG_G] = {};
-    for (int i = blockIdx.x * CG_BY + threadIdx.y; i < n; i += gridDim.x * CG_BY)
+    for (int r = ry; r < CG_TR; r += 4) {
+        const int i = i0 + r;
+        if (i >= n) break;
 #pragma unroll
         for (int g = 0; g < CG_G; ++g) {
-            const int c = threadIdx.x + g * CG_BX;
+            const int c = cx + g * CG_BX;
             if (c < Mp) {
                 const float v = c < M ? G[(long long)i * ldg + col0 + c] : 0.f;
                 b.R[(long long)i * Mp + c] = v;
@@ -82,98 +98,111 @@ __global__ void __launch_bounds__(CG_BX * CG_BY) cg_init_kernel(const float* __r
                 acc[g] += (double)v * (double)v;
             }
         }
+    }
     cg_store_partials(acc, b.part + (long long)blockIdx.x * CG_MAXCOLS);
 }
 
-// rs[0] = bb = sum of the partials (one block)
+// one block: rs[0] = bb = sum of the tiles' partials
 __global__ void cg_init_finish_kernel(CgBuf b, int M)
 {
     const int c = threadIdx.x;
     if (c >= CG_MAXCOLS) return;
     double s = 0.0;
-    for (int k = 0; k < b.nblk; ++k) s += b.part[(long long)k * CG_MAXCOLS + c];
-    b.rs[c] = c < M ? (float)s : 0.f;
-    b.bb[c] = c < M ? (float)s : 0.f;
+    if (c < M)
+        for (int k = 0; k < b.nblk; ++k) s += b.part[(long long)k * CG_MAXCOLS + c];
+    b.rs[c] = (float)s;
+    b.bb[c] = (float)s;
     if (c == 0) { b.conv[0] = 1.f; b.conv[1] = 0.f; }
 }
 
-// partial[blk][c] = sum_i P[i][c] * Qt[c][i]
-__global__ void __launch_bounds__(CG_BX * CG_BY) cg_dot_kernel(CgBuf b, int n, int M, int Mp, long long ldq)
+// partial[tile][c] = sum over the tile's rows of P[i][c] * Qt[c][i]
+__global__ void __launch_bounds__(256) cg_dot_kernel(CgBuf b, int n, int M, int Mp, long long ldq)
 {
+    __shared__ float sq[CG_MAXCOLS][CG_TR + 1];
+    const int cx = threadIdx.x & 63, ry = threadIdx.x >> 6, i0 = blockIdx.x * CG_TR;
+    cg_stage_q(b, i0, n, M, ldq, sq);
     double acc[CG_G] = {};
-    for (int i = blockIdx.x * CG_BY + threadIdx.y; i < n; i += gridDim.x * CG_BY)
+    for (int r = ry; r < CG_TR && i0 + r < n; r += 4)
 #pragma unroll
         for (int g = 0; g < CG_G; ++g) {
-            const int c = threadIdx.x + g * CG_BX;
-            if (c < M) acc[g] += (double)b.P[(long long)i * Mp + c] * (double)b.Qt[(long long)c * ldq + i];
+            const int c = cx + g * CG_BX;
+            if (c < M) acc[g] += (double)b.P[(long long)(i0 + r) * Mp + c] * (double)sq[c][r];
         }
     cg_store_partials(acc, b.part + (long long)blockIdx.x * CG_MAXCOLS);
 }
 
-// alpha = rs / (p.q) (every block sums the partials in the same order); X += alpha P; R -= alpha Q; partials of r.r
-__global__ void __launch_bounds__(CG_BX * CG_BY) cg_update_xr_kernel(CgBuf b, int n, int M, int Mp, long long ldq, int parity)
+// one block: alpha = rs / (p.q), partials added in a fixed order
+__global__ void cg_alpha_kernel(CgBuf b, int M, int parity)
 {
-    __shared__ float s_alpha[CG_MAXCOLS];
-    for (int c = threadIdx.y * CG_BX + threadIdx.x; c < CG_MAXCOLS; c += CG_BX * CG_BY) {
+    const int c = threadIdx.x;
+    if (c >= CG_MAXCOLS) return;
+    float alpha = 0.f;
+    if (c < M) {
         double pq = 0.0;
-        if (c < M)
-            for (int k = 0; k < b.nblk; ++k) pq += b.part[(long long)k * CG_MAXCOLS + c];
+        for (int k = 0; k < b.nblk; ++k) pq += b.part[(long long)k * CG_MAXCOLS + c];
         const float rs = b.rs[parity * CG_MAXCOLS + c];
-        float alpha = 0.f;
-        if (c < M && rs > 0.f) {
+        if (rs > 0.f) {
             if (pq > 0.0) alpha = (float)((double)rs / pq);
-            else if (blockIdx.x == 0) b.conv[1] = 1.f;                    // p^T S p <= 0: the matrix is not positive definite
+            else b.conv[1] = 1.f;                                       // p^T S p <= 0: the matrix is not positive definite
         }
-        s_alpha[c] = alpha;
     }
-    __syncthreads();
+    b.ab[c] = alpha;
+}
+
+// X += alpha P; R -= alpha Q; partials of r.r
+__global__ void __launch_bounds__(256) cg_update_xr_kernel(CgBuf b, int n, int M, int Mp, long long ldq)
+{
+    __shared__ float sq[CG_MAXCOLS][CG_TR + 1];
+    const int cx = threadIdx.x & 63, ry = threadIdx.x >> 6, i0 = blockIdx.x * CG_TR;
+    cg_stage_q(b, i0, n, M, ldq, sq);
     double acc[CG_G] = {};
-    for (int i = blockIdx.x * CG_BY + threadIdx.y; i < n; i += gridDim.x * CG_BY)
+    for (int r = ry; r < CG_TR && i0 + r < n; r += 4)
 #pragma unroll
         for (int g = 0; g < CG_G; ++g) {
-            const int c = threadIdx.x + g * CG_BX;
+            const int c = cx + g * CG_BX;
             if (c < M) {
-                const float alpha = s_alpha[c];
-                const long long o = (long long)i * Mp + c;
+                const float alpha = b.ab[c];
+                const long long o = (long long)(i0 + r) * Mp + c;
                 b.X[o] = fmaf(alpha, b.P[o], b.X[o]);
-                const float r = fmaf(-alpha, b.Qt[(long long)c * ldq + i], b.R[o]);
-                b.R[o] = r;
-                acc[g] += (double)r * (double)r;
+                const float rr = fmaf(-alpha, sq[c][r], b.R[o]);
+                b.R[o] = rr;
+                acc[g] += (double)rr * (double)rr;
             }
         }
     cg_store_partials(acc, b.part + ((long long)b.nblk + blockIdx.x) * CG_MAXCOLS);
 }
 
-// beta = rs_new / rs; P = R + beta P; block 0 publishes rs_new and the convergence measure
-__global__ void __launch_bounds__(CG_BX * CG_BY) cg_update_p_kernel(CgBuf b, int n, int M, int Mp, int parity)
+// one block: beta = rs_new / rs, rs_new, the convergence measure
+__global__ void cg_beta_kernel(CgBuf b, int M, int parity)
 {
-    __shared__ float s_beta[CG_MAXCOLS];
     __shared__ float s_rel[CG_MAXCOLS];
-    for (int c = threadIdx.y * CG_BX + threadIdx.x; c < CG_MAXCOLS; c += CG_BX * CG_BY) {
+    const int c = threadIdx.x;
+    if (c < CG_MAXCOLS) {
         double rn = 0.0;
         if (c < M)
             for (int k = 0; k < b.nblk; ++k) rn += b.part[((long long)b.nblk + k) * CG_MAXCOLS + c];
         const float rs = b.rs[parity * CG_MAXCOLS + c];
-        s_beta[c] = (c < M && rs > 0.f) ? (float)(rn / (double)rs) : 0.f;
+        b.ab[CG_MAXCOLS + c] = (c < M && rs > 0.f) ? (float)(rn / (double)rs) : 0.f;
         const float bbv = b.bb[c];
         s_rel[c] = (c < M && bbv > 0.f) ? sqrtf((float)rn / bbv) : 0.f;
-        if (blockIdx.x == 0) b.rs[(parity ^ 1) * CG_MAXCOLS + c] = c < M ? (float)rn : 0.f;
+        b.rs[(parity ^ 1) * CG_MAXCOLS + c] = c < M ? (float)rn : 0.f;
     }
     __syncthreads();
-    if (blockIdx.x == 0 && threadIdx.y == 0 && threadIdx.x == 0) {
+    if (c == 0) {
         float m = 0.f;
         for (int k = 0; k < CG_MAXCOLS; ++k) m = fmaxf(m, s_rel[k]);
         b.conv[0] = m;
     }
-    for (int i = blockIdx.x * CG_BY + threadIdx.y; i < n; i += gridDim.x * CG_BY)
-#pragma unroll
-        for (int g = 0; g < CG_G; ++g) {
-            const int c = threadIdx.x + g * CG_BX;
-            if (c < Mp) {
-                const long long o = (long long)i * Mp + c;
-                b.P[o] = fmaf(s_beta[c], b.P[o], b.R[o]);
-            }
-        }
+}
+
+// P = R + beta P
+__global__ void __launch_bounds__(256) cg_update_p_kernel(CgBuf b, int n, int Mp)
+{
+    const long long total = (long long)n * Mp;
+    for (long long idx = blockIdx.x * 256LL + threadIdx.x; idx < total; idx += (long long)gridDim.x * 256) {
+        const int c = (int)(idx % Mp);
+        b.P[idx] = fmaf(b.ab[CG_MAXCOLS + c], b.P[idx], b.R[idx]);
+    }
 }
 
 }  // namespace
@@ -188,10 +217,10 @@ int sd_cg_solve(sd_ctx* ctx, sd_comm* comm, float* G, int64_t ldg, int n, int co
     const int64_t ldq = ((int64_t)n + 3) / 4 * 4;
     const int nranks = sd_comm_size_of(comm), me = sd_comm_rank_of(comm);
     CgBuf b;
-    b.nblk = ctx->sm_count / 2 > 16 ? ctx->sm_count / 2 : 16;      // few blocks: every block re-adds all partial sums (fixed order)
+    b.nblk = sd_div_up(n, CG_TR);
     const size_t vec = (size_t)n * Mp;
     const size_t tile_cap = ((size_t)sd_div_up(n, 256) + 1) * ((size_t)sd_div_up(M, 128) + 1) * 2;       // int2 entries, as floats
-    const size_t floats = 3 * vec + (size_t)M * ldq + 4 * CG_MAXCOLS + 64 + tile_cap + 8;
+    const size_t floats = 3 * vec + (size_t)M * ldq + 6 * CG_MAXCOLS + 64 + tile_cap + 8;
     const size_t bytes = floats * sizeof(float) + (size_t)2 * b.nblk * CG_MAXCOLS * sizeof(double) + 256;
     char* ws = (char*)sd_workspace(ctx, SD_WS_CG, bytes);
     if (!ws) return SD_ERR_CUDA;
@@ -200,8 +229,8 @@ int sd_cg_solve(sd_ctx* ctx, sd_comm* comm, float* G, int64_t ldg, int n, int co
     b.X = f; b.R = f + vec; b.P = f + 2 * vec; b.Qt = f + 3 * vec;
     float* tail = b.Qt + (size_t)M * ldq;
     tail = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tail) + 15) & ~(uintptr_t)15);
-    b.rs = tail; b.bb = tail + 2 * CG_MAXCOLS; b.conv = tail + 3 * CG_MAXCOLS;
-    void* d_tile_buf = tail + 3 * CG_MAXCOLS + 16;
+    b.rs = tail; b.bb = tail + 2 * CG_MAXCOLS; b.ab = tail + 3 * CG_MAXCOLS; b.conv = tail + 5 * CG_MAXCOLS;
+    void* d_tile_buf = tail + 5 * CG_MAXCOLS + 16;
 
     // this rank's slab of the contraction (rows of S), multiples of 16 rows
     int k0 = 0, k1 = n;
@@ -210,13 +239,12 @@ int sd_cg_solve(sd_ctx* ctx, sd_comm* comm, float* G, int64_t ldg, int n, int co
         k0 = me * per < n ? me * per : n;
         k1 = (me + 1) * per < n ? (me + 1) * per : n;
     }
-    const dim3 blk(CG_BX, CG_BY);
     if (k1 > k0) {
         const dim3 mg(sd_div_up(n, 32), sd_div_up(k1 - k0 / 32 * 32, 32));
         cg_mirror_kernel<<<mg, 256, 0, ctx->stream>>>(G, ldg, n, k0, k1);
         SD_LAUNCH_CHECK(ctx, "cg_mirror_kernel");
     }
-    cg_init_kernel<<<b.nblk, blk, 0, ctx->stream>>>(G, ldg, n, col0, M, Mp, b);
+    cg_init_kernel<<<b.nblk, 256, 0, ctx->stream>>>(G, ldg, n, col0, M, Mp, b);
     SD_LAUNCH_CHECK(ctx, "cg_init_kernel");
     cg_init_finish_kernel<<<1, 256, 0, ctx->stream>>>(b, M);
     SD_LAUNCH_CHECK(ctx, "cg_init_finish_kernel");
@@ -256,11 +284,15 @@ int sd_cg_solve(sd_ctx* ctx, sd_comm* comm, float* G, int64_t ldg, int n, int co
             rc = sd_comm_allreduce_f32(ctx, comm, b.Qt, (size_t)M * ldq, ctx->stream);
             if (rc) return rc;
         }
-        cg_dot_kernel<<<b.nblk, blk, 0, ctx->stream>>>(b, n, M, Mp, ldq);
+        cg_dot_kernel<<<b.nblk, 256, 0, ctx->stream>>>(b, n, M, Mp, ldq);
         SD_LAUNCH_CHECK(ctx, "cg_dot_kernel");
-        cg_update_xr_kernel<<<b.nblk, blk, 0, ctx->stream>>>(b, n, M, Mp, ldq, parity);
+        cg_alpha_kernel<<<1, 256, 0, ctx->stream>>>(b, M, parity);
+        SD_LAUNCH_CHECK(ctx, "cg_alpha_kernel");
+        cg_update_xr_kernel<<<b.nblk, 256, 0, ctx->stream>>>(b, n, M, Mp, ldq);
         SD_LAUNCH_CHECK(ctx, "cg_update_xr_kernel");
-        cg_update_p_kernel<<<b.nblk, blk, 0, ctx->stream>>>(b, n, M, Mp, parity);
+        cg_beta_kernel<<<1, 256, 0, ctx->stream>>>(b, M, parity);
+        SD_LAUNCH_CHECK(ctx, "cg_beta_kernel");
+        cg_update_p_kernel<<<2 * ctx->sm_count, 256, 0, ctx->stream>>>(b, n, Mp);
         SD_LAUNCH_CHECK(ctx, "cg_update_p_kernel");
         SD_CUDA(ctx, cudaMemcpyAsync(h_conv + 2 * (it & 7), b.conv, 2 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
         SD_CUDA(ctx, cudaEventRecord(ctx->cg_ev[it & 7], ctx->stream));

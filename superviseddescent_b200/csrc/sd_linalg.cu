@@ -1112,6 +1112,7 @@ __global__ void __launch_bounds__(256) trsm_apply_kernel(const TrsmArgs a)
 constexpr int BS_COLS = 64, BS_ULD = PB + 4;      // 16-byte aligned rows for cp.async
 struct BackArgs {
     float* G; long long ldg; int D; int M; int j; int nb; int nchunks;
+    int cg_first, cg_step;  // column groups of BS_COLS right-hand sides handled by this launch: cg_first + blockIdx.y * cg_step
     const float* Wt;        // (U_jj^-1)^T, PB x PB row-major, identity padded
     float* X;               // D x M
 };
@@ -1124,7 +1125,7 @@ __global__ void __launch_bounds__(256) backsub_step_kernel(const BackArgs a)
     float* sX = sY + PB * BS_COLS;           // [PB][BS_COLS]   X_j tile
     float* sU = sX + PB * BS_COLS;           // [PB][BS_ULD]    U[chunk rows][block columns]
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    const int c0 = blockIdx.y * BS_COLS;
+    const int c0 = (a.cg_first + (int)blockIdx.y * a.cg_step) * BS_COLS;
     const int r0 = blockIdx.x * PB;
     const bool update = (int)blockIdx.x < a.nchunks;
     for (int idx = tid; idx < PB * PB / 4; idx += 256) cp_async16(sWt + idx * 4, a.Wt + idx * 4, true);
@@ -1353,16 +1354,27 @@ int cholesky_solve(sd_ctx* ctx, float* G, int64_t ldg, int D, int M, float* X, s
     // ---- back substitution U X = Y, right-looking over block columns from the last: one launch per block ----
     const size_t smem_bs = (size_t)(PB * PB + 2 * PB * BS_COLS + PB * BS_ULD) * sizeof(float);
     SD_CUDA(ctx, cudaFuncSetAttribute(backsub_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bs));
-    for (int b = nblocks - 1; b >= 0; --b) {
+    // distributed: the column groups of the right-hand sides are independent, so rank r substitutes groups r, r + G, ... and one
+    // all-reduce of X (every entry has exactly one non-zero contributor) hands everybody the whole solution
+    const int ngroups = sd_div_up(M, BS_COLS);
+    const int my_groups = dist ? (ngroups > me ? (ngroups - me + nranks - 1) / nranks : 0) : ngroups;
+    if (dist) SD_CUDA(ctx, cudaMemsetAsync(X, 0, (size_t)D * M * sizeof(float), main_s));
+    for (int b = nblocks - 1; b >= 0 && my_groups > 0; --b) {
         BackArgs ba;
         ba.G = G; ba.ldg = ldg; ba.D = D; ba.M = M; ba.j = b * kCholNb;
         ba.nb = (D - ba.j < kCholNb) ? D - ba.j : kCholNb;
         ba.nchunks = b;                                              // full 128-row chunks above block b
+        ba.cg_first = dist ? me : 0;
+        ba.cg_step = dist ? nranks : 1;
         ba.Wt = inv + (size_t)b * 2 * PB * PB + PB * PB;
         ba.X = X;
-        const dim3 grid(b > 0 ? b : 1, sd_div_up(M, BS_COLS));
+        const dim3 grid(b > 0 ? b : 1, my_groups);
         backsub_step_kernel<<<grid, 256, smem_bs, main_s>>>(ba);
         SD_LAUNCH_CHECK(ctx, "backsub_step_kernel");
+    }
+    if (dist) {
+        rc = sd_comm_allreduce_f32(ctx, comm, X, (size_t)D * M, main_s);
+        if (rc) return rc;
     }
     return SD_OK;
 }
