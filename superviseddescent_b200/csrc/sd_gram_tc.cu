@@ -34,14 +34,30 @@ namespace {
 constexpr int BM = 128;          // rows of C per tile   (operand "A": columns i of S)
 constexpr int BN = 256;          // cols of C per tile   (operand "B": columns j of S)
 constexpr int BK = 16;           // samples (rows of S) per pipeline stage
-constexpr int STAGES = 4;
 constexpr int BOX_COLS = 32;     // 32 floats = 128 B = swizzle span
 constexpr int BOX_BYTES = BOX_COLS * 4 * BK;              // 2 KB
 constexpr int A_BLOCKS = BM / BOX_COLS;                   // 4
-constexpr int B_BLOCKS = BN / BOX_COLS;                   // 8
 constexpr int OPER_BYTES_A = A_BLOCKS * BOX_BYTES;        // 8 KB
-constexpr int OPER_BYTES_B = B_BLOCKS * BOX_BYTES;        // 16 KB
-constexpr int STAGE_BYTES = 2 * (OPER_BYTES_A + OPER_BYTES_B);   // hi + lo: 48 KB
+constexpr int PIPE_BYTES = 192 * 1024;                    // shared memory of the operand pipeline
+constexpr int MAX_STAGES = 8;
+
+// The kernel is compiled for NB = 8 (tiles of 256 columns: the Gram, the trailing updates) and for narrower "B" operands
+// (NB * 32 columns, a single tile column): a skinny product C[MI x <=64] = SA^T SB issues MMAs of N = 64 instead of 256 and turns
+// the shared memory it does not need for operand B into a deeper pipeline (the product is then bound by the read of SA).
+template <int NB>
+struct TcCfg {
+    static constexpr int B_BLOCKS = NB;
+    static constexpr int N_MMA = NB * BOX_COLS;                                    // 64 .. 256
+    static constexpr int OPER_BYTES_B = NB * BOX_BYTES;
+    static constexpr int RAW_BYTES = OPER_BYTES_A + OPER_BYTES_B;
+    static constexpr int STAGE_BYTES = 2 * RAW_BYTES;                              // hi + lo: 48 KB for NB = 8, 24 KB for NB = 2
+    static constexpr int STAGES = PIPE_BYTES / STAGE_BYTES < MAX_STAGES ? PIPE_BYTES / STAGE_BYTES : MAX_STAGES;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 1024 /*barriers*/ + 8 /*EPI_WARPS*/ * 4096 /*CBOX_BYTES*/;
+    // cute::UMMA::InstrDescriptor: c_format F32 [4,6)=1, a/b_format TF32 [7,10)/[10,13)=2, a/b_major MN [15],[16]=1,
+    // n_dim = N>>3 at [17,23), m_dim = M>>4 at [24,29)
+    static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                                      ((uint32_t)(N_MMA >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+};
 constexpr int KC_STAGES = 8;      // pipeline stages per accumulation chunk: KC = 8 * BK = 128 samples
 constexpr int EPI_WARPS = 8;
 constexpr int TMEM_COLS = 512;
@@ -151,11 +167,6 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr)
     return d;
 }
 
-// cute::UMMA::InstrDescriptor: c_format F32 [4,6)=1, a/b_format TF32 [7,10)/[10,13)=2, a/b_major MN [15],[16]=1,
-// n_dim = N>>3 at [17,23), m_dim = M>>4 at [24,29)
-constexpr uint32_t kInstrDesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
-                                ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-
 struct TcArgs {
     int K, MI, NJ;
     float* C;
@@ -168,6 +179,7 @@ struct TcArgs {
     int ksplit, kps;     // the K loop of every tile is cut into ksplit ranges of kps pipeline stages (work item t: tile t / ksplit,
                          // range t % ksplit); ksplit > 1 needs the reduce-add write-back onto a zeroed C
     int tma_c;           // 0 = register epilogue, 1 = TMA store (beta == 0), 2 = TMA reduce-add (beta == 1)
+    int a_strip;         // > 0: operand A is stored strip-major, [tile row][a_strip contraction rows][128 columns] (sd_cg.cu)
 };
 
 // =====================================================================================================
@@ -177,15 +189,14 @@ struct TcArgs {
 // profiles/r01_summary.md.)
 //   warp 0       TMA producer        (raw tiles, 24 KB per stage)
 //   warp 1       MMA issuer          (lo*hi, hi*lo, hi*hi; accumulators in TMEM, one fresh accumulator per 128-sample chunk)
-//   warps 4..7   transform           (raw -> lo, element-wise in the swizzled layout; fence.proxy.async)
+//   warps 4..7   transform           (raw -> lo, element-wise in the swizzled layout; fence.proxy.async); one warp per stage
 //   warps 8..15  epilogue            (running sums in registers, write-back through the TMA)
 // Register budget is rebalanced with setmaxnreg: producer/MMA/transform warpgroups give registers back,
 // the two epilogue warpgroups take them (128 running sums + a 32-value TMEM fragment per thread).
 // =====================================================================================================
 constexpr int T2_THREADS = 512;
-constexpr int RAW_BYTES = OPER_BYTES_A + OPER_BYTES_B;     // 24 KB
 constexpr int CBOX_BYTES = 32 * 32 * 4;                     // one 32 x 32 fp32 box of C per epilogue warp (128B-swizzled)
-constexpr int SMEM2_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 1024 /*barriers*/ + EPI_WARPS * CBOX_BYTES;
+static_assert(EPI_WARPS * CBOX_BYTES == 8 * 4096, "TcCfg::SMEM_BYTES");
 
 // explicit shared-space accesses: the tile pointers come from integer arithmetic on the dynamic shared-memory base, so
 // the compiler would otherwise emit generic LD/ST (ncu: 8 wavefronts per 128-bit request instead of 4)
@@ -201,17 +212,19 @@ __device__ __forceinline__ void sts128(uint32_t addr, const float4& v)
 }
 
 __device__ __forceinline__ float trunc_tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
-__device__ __forceinline__ float rna_tf32(float x)
-{
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
+// rna_tf32 of a finite value (what cvt.rna.tf32.f32 returns): round the magnitude to 10 mantissa bits, ties away from zero
+__device__ __forceinline__ float rna_tf32_bits(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
+// the same value as far as the tensor core is concerned (it ignores the low 13 bits of a TF32 operand)
+__device__ __forceinline__ float round_operand(float x) { return __uint_as_float(__float_as_uint(x) + 0x1000u); }
 
+template <int NB>
 __global__ void __launch_bounds__(T2_THREADS, 1)
 syrk_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_c,
                 const TcArgs a)
 {
+    using Cfg = TcCfg<NB>;
+    constexpr int STAGES = Cfg::STAGES, STAGE_BYTES = Cfg::STAGE_BYTES, RAW_BYTES = Cfg::RAW_BYTES, B_BLOCKS = Cfg::B_BLOCKS;
+    constexpr uint32_t kInstrDesc = Cfg::IDESC;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -227,7 +240,7 @@ syrk_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const bool split = a.passes == 3;
 
     if (warp == 0 && lane == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&lo_ready[s], 128); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&lo_ready[s], 32); mbar_init(&empty_bar[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -260,7 +273,8 @@ syrk_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                         unsigned char* sb = sa + OPER_BYTES_A;
                         const int k0 = kb * BK;
 #pragma unroll
-                        for (int cb = 0; cb < A_BLOCKS; ++cb) tma_load_2d(sa + cb * BOX_BYTES, &map_a, &raw_full[stage], i0 + cb * BOX_COLS, k0);
+                        for (int cb = 0; cb < A_BLOCKS; ++cb)
+                            tma_load_2d(sa + cb * BOX_BYTES, &map_a, &raw_full[stage], (a.a_strip ? 0 : i0) + cb * BOX_COLS, (a.a_strip ? tile.x * a.a_strip : 0) + k0);
 #pragma unroll
                         for (int cb = 0; cb < B_BLOCKS; ++cb) tma_load_2d(sb + cb * BOX_BYTES, &map_b, &raw_full[stage], j0 + cb * BOX_COLS, k0);
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -312,42 +326,62 @@ syrk_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     } else if (warp < 8) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 72;" ::: "memory");
         // ===================== transform: lo = a - trunc_tf32(a), element-wise on the swizzled bytes =====================
+        // Each of the four warps owns every fourth pipeline stage and transforms it alone: four stages are in flight at a time, so
+        // the shared-memory and barrier latencies of one stage hide behind the arithmetic of the others (with all four warps on
+        // the same stage the kernel ran at the pace of that chain: ncu, tensor pipe 21 % active on the skinny product).
         if (split) {
-            const int tt = threadIdx.x - 128;                 // 0..127
-            uint32_t stage = 0, phase = 0;
+            const int tw = warp - 4;                          // 0..3
+            uint32_t stage = 0, phase = 0, it = 0;
             for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
                 const int kb0 = (t % a.ksplit) * a.kps, kb1 = min(num_k, kb0 + a.kps);
-                for (int kb = kb0; kb < kb1; ++kb) {
-                    mbar_wait(&raw_full[stage], phase);
-                    const uint32_t raw = smem_u32(smem + stage * STAGE_BYTES) + tt * 16;
-                    const uint32_t lo = raw + RAW_BYTES;
-                    if (a.unbiased) {
-                        // hi = rna_tf32(a) written back in place (the tensor core's truncation is then a no-op and the
-                        // split is unbiased), lo = rna_tf32(a - hi).  One more 24 KB shared-memory write per stage:
-                        // measured 58 % tensor-pipe activity instead of 69 %, weights 3.0e-5 instead of 6.5e-5.
-#pragma unroll 4
-                        for (int i = 0; i < RAW_BYTES / 16 / 128; ++i) {
-                            const float4 v = lds128(raw + i * 2048);
-                            float4 h, l;
-                            h.x = rna_tf32(v.x); h.y = rna_tf32(v.y); h.z = rna_tf32(v.z); h.w = rna_tf32(v.w);
-                            l.x = rna_tf32(v.x - h.x); l.y = rna_tf32(v.y - h.y); l.z = rna_tf32(v.z - h.z); l.w = rna_tf32(v.w - h.w);
-                            sts128(raw + i * 2048, h);
-                            sts128(lo + i * 2048, l);
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                    if ((int)(it & 3) == tw) {
+                        mbar_wait(&raw_full[stage], phase);
+                        const uint32_t raw = smem_u32(smem + stage * STAGE_BYTES) + lane * 16;
+                        const uint32_t lo = raw + RAW_BYTES;
+                        // Round-to-nearest to TF32 of a finite value is "add half an ulp of the 10-bit mantissa to the bit pattern
+                        // and drop the low 13 bits"; the tensor core drops those bits by itself, so for an OPERAND the rounding is
+                        // one integer add (cvt.rna.tf32.f32 compiles to a compare, a predicated add and a mask per value).
+                        // Loads are batched four deep ahead of the stores.
+                        constexpr int NIT = RAW_BYTES / 16 / 32;          // 16-byte pieces per thread: 24 (NB = 2) .. 48 (NB = 8)
+                        if (a.unbiased) {
+                            // hi = rna_tf32(a) written back in place (the tensor core's truncation is then a no-op and the split
+                            // is unbiased), lo = rna_tf32(a - hi).  One more shared-memory write per stage than the variant below.
+#pragma unroll 3
+                            for (int i0 = 0; i0 < NIT; i0 += 4) {
+                                float4 v[4];
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) v[u] = lds128(raw + (i0 + u) * 512);
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) {
+                                    float4 h, l;
+                                    h.x = rna_tf32_bits(v[u].x); h.y = rna_tf32_bits(v[u].y); h.z = rna_tf32_bits(v[u].z); h.w = rna_tf32_bits(v[u].w);
+                                    l.x = round_operand(v[u].x - h.x); l.y = round_operand(v[u].y - h.y);
+                                    l.z = round_operand(v[u].z - h.z); l.w = round_operand(v[u].w - h.w);
+                                    sts128(raw + (i0 + u) * 512, h);
+                                    sts128(lo + (i0 + u) * 512, l);
+                                }
+                            }
+                        } else {
+                            // hi is the raw tile as the tensor core sees it (low 13 mantissa bits ignored); the residual is
+                            // rounded to TF32 so that the hardware's truncation of the lo operand does not bias it
+#pragma unroll 3
+                            for (int i0 = 0; i0 < NIT; i0 += 4) {
+                                float4 v[4];
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) v[u] = lds128(raw + (i0 + u) * 512);
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) {
+                                    float4 l;
+                                    l.x = round_operand(v[u].x - trunc_tf32(v[u].x)); l.y = round_operand(v[u].y - trunc_tf32(v[u].y));
+                                    l.z = round_operand(v[u].z - trunc_tf32(v[u].z)); l.w = round_operand(v[u].w - trunc_tf32(v[u].w));
+                                    sts128(lo + (i0 + u) * 512, l);
+                                }
+                            }
                         }
-                    } else {
-                        // hi is the raw tile as the tensor core sees it (low 13 mantissa bits ignored); the residual is
-                        // rounded to TF32 so that the hardware's truncation of the lo operand is a no-op
-#pragma unroll 4
-                        for (int i = 0; i < RAW_BYTES / 16 / 128; ++i) {
-                            const float4 v = lds128(raw + i * 2048);
-                            float4 l;
-                            l.x = rna_tf32(v.x - trunc_tf32(v.x)); l.y = rna_tf32(v.y - trunc_tf32(v.y));
-                            l.z = rna_tf32(v.z - trunc_tf32(v.z)); l.w = rna_tf32(v.w - trunc_tf32(v.w));
-                            sts128(lo + i * 2048, l);
-                        }
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+                        mbar_arrive(&lo_ready[stage]);
                     }
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
-                    mbar_arrive(&lo_ready[stage]);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -374,6 +408,7 @@ syrk_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + half * 128;
 #pragma unroll
                 for (int c0 = 0; c0 < 128; c0 += 32) {
+                    if (NB < 8 && half * 128 + c0 >= Cfg::N_MMA) continue;     // columns the narrow MMA never writes
                     uint32_t r[32];
                     tmem_ld_32x32b_x32(taddr + c0, r);
                     tmem_ld_wait();
@@ -396,6 +431,7 @@ syrk_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 const uint32_t box_u32 = smem_u32(box);
 #pragma unroll
                 for (int c0 = 0; c0 < 128; c0 += 32) {
+                    if (NB < 8 && half * 128 + c0 >= Cfg::N_MMA) continue;
                     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // box buffer free again
                     __syncwarp();
 #pragma unroll
@@ -526,6 +562,7 @@ struct sd_tc_plan {
     CUtensorMap map_a, map_b, map_c;
     TcArgs args;
     int grid;
+    int nb;              // kernel variant: 32-column boxes of operand B per stage (8 = full tiles)
 };
 static_assert(sizeof(sd_tc_plan) <= SD_TC_PLAN_BYTES, "sd_tc_plan storage");
 
@@ -537,13 +574,16 @@ static_assert(sizeof(sd_tc_plan) <= SD_TC_PLAN_BYTES, "sd_tc_plan storage");
 // context's workspace.  *empty is set when no tile survives the filters (nothing to launch).
 int sd_gemm_tn_tc_prepare(sd_ctx* ctx, const float* d_SA, int64_t lda, const float* d_SB, int64_t ldb, int K, int MI, int NJ,
                           float* d_C, int64_t ldc, float alpha, float beta, int passes, bool unbiased_split, bool upper_only,
-                          const sd_row_filter* rows, int ksplit, void* d_tiles_buf, void* plan_storage, bool* empty)
+                          const sd_row_filter* rows, int ksplit, void* d_tiles_buf, void* plan_storage, bool* empty, bool narrow, int a_strip_rows)
 {
     sd_tc_plan* plan = reinterpret_cast<sd_tc_plan*>(plan_storage);
     *empty = true;
     if (MI <= 0 || NJ <= 0 || K <= 0) return SD_OK;
     SD_REQUIRE(ctx, passes == 1 || passes == 3, "passes must be 1 or 3");
-    int rc = make_map(ctx, &plan->map_a, d_SA, lda, K, MI);
+    // operand A either as the row-major K x MI matrix, or strip-major: sd_div_up(MI, 128) strips of a_strip_rows x 128 floats each
+    // (rows K .. a_strip_rows - 1 and the columns beyond MI hold zeros): a CTA then streams one contiguous strip
+    SD_REQUIRE(ctx, a_strip_rows == 0 || (a_strip_rows % BK == 0 && a_strip_rows >= K), "strip-major operand: rows padded to the pipeline stage");
+    int rc = a_strip_rows ? make_map(ctx, &plan->map_a, d_SA, BM, sd_div_up(MI, BM) * a_strip_rows, BM) : make_map(ctx, &plan->map_a, d_SA, lda, K, MI);
     if (rc) return rc;
     rc = make_map(ctx, &plan->map_b, d_SB, ldb, K, NJ);
     if (rc) return rc;
@@ -568,6 +608,7 @@ int sd_gemm_tn_tc_prepare(sd_ctx* ctx, const float* d_SA, int64_t lda, const flo
     TcArgs& a = plan->args;
     a.K = K; a.MI = MI; a.NJ = NJ; a.C = d_C; a.ldc = ldc; a.alpha = alpha; a.beta = beta; a.passes = passes;
     a.unbiased = (ctx->gram_mode == 3 || unbiased_split) ? 1 : 0;
+    a.a_strip = a_strip_rows;
     const int num_k = sd_div_up(K, BK);
     if (ksplit < 1) ksplit = 1;
     if (ksplit > num_k) ksplit = num_k;
@@ -586,7 +627,15 @@ int sd_gemm_tn_tc_prepare(sd_ctx* ctx, const float* d_SA, int64_t lda, const flo
     }
     // split K: the ranges of one tile add into C in any order, which is only reproducible for two of them (a + b == b + a)
     SD_REQUIRE(ctx, a.ksplit == 1 || (a.tma_c == 2 && a.ksplit == 2), "split-K needs beta == 1, the TMA reduce-add write-back and two ranges");
-    SD_CUDA(ctx, cudaFuncSetAttribute(syrk_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+    // a single tile column of at most 192 columns can run the narrow variants
+    plan->nb = 8;
+    if (narrow && TJ == 1 && !getenv("SD_B200_NO_NARROW")) plan->nb = NJ <= 64 ? 2 : NJ <= 128 ? 4 : NJ <= 192 ? 6 : 8;
+    switch (plan->nb) {
+    case 2: SD_CUDA(ctx, cudaFuncSetAttribute(syrk_tc2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<2>::SMEM_BYTES)); break;
+    case 4: SD_CUDA(ctx, cudaFuncSetAttribute(syrk_tc2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<4>::SMEM_BYTES)); break;
+    case 6: SD_CUDA(ctx, cudaFuncSetAttribute(syrk_tc2_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<6>::SMEM_BYTES)); break;
+    default: SD_CUDA(ctx, cudaFuncSetAttribute(syrk_tc2_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<8>::SMEM_BYTES)); break;
+    }
     *empty = false;
     return SD_OK;
 }
@@ -594,7 +643,12 @@ int sd_gemm_tn_tc_prepare(sd_ctx* ctx, const float* d_SA, int64_t lda, const flo
 int sd_gemm_tn_tc_launch(sd_ctx* ctx, const void* plan_storage)
 {
     const sd_tc_plan* plan = reinterpret_cast<const sd_tc_plan*>(plan_storage);
-    syrk_tc2_kernel<<<plan->grid, T2_THREADS, SMEM2_BYTES, ctx->stream>>>(plan->map_a, plan->map_b, plan->map_c, plan->args);
+    switch (plan->nb) {
+    case 2: syrk_tc2_kernel<2><<<plan->grid, T2_THREADS, TcCfg<2>::SMEM_BYTES, ctx->stream>>>(plan->map_a, plan->map_b, plan->map_c, plan->args); break;
+    case 4: syrk_tc2_kernel<4><<<plan->grid, T2_THREADS, TcCfg<4>::SMEM_BYTES, ctx->stream>>>(plan->map_a, plan->map_b, plan->map_c, plan->args); break;
+    case 6: syrk_tc2_kernel<6><<<plan->grid, T2_THREADS, TcCfg<6>::SMEM_BYTES, ctx->stream>>>(plan->map_a, plan->map_b, plan->map_c, plan->args); break;
+    default: syrk_tc2_kernel<8><<<plan->grid, T2_THREADS, TcCfg<8>::SMEM_BYTES, ctx->stream>>>(plan->map_a, plan->map_b, plan->map_c, plan->args); break;
+    }
     SD_LAUNCH_CHECK(ctx, "syrk_tc2_kernel");
     return SD_OK;
 }
@@ -606,7 +660,7 @@ int sd_gemm_tn_tc(sd_ctx* ctx, const float* d_SA, int64_t lda, const float* d_SB
     alignas(64) unsigned char storage[SD_TC_PLAN_BYTES];
     bool empty = true;
     int rc = sd_gemm_tn_tc_prepare(ctx, d_SA, lda, d_SB, ldb, K, MI, NJ, d_C, ldc, alpha, beta, passes, unbiased_split, upper_only, rows, ksplit,
-                                   nullptr, storage, &empty);
+                                   nullptr, storage, &empty, false, 0);
     if (rc || empty) return rc;
     return sd_gemm_tn_tc_launch(ctx, storage);
 }

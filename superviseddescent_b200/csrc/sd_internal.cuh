@@ -16,7 +16,7 @@
 #define SD_MAX_BINS 16   // undirected orientations K supported by the HOG kernel
 
 enum { SD_WS_GRAM_EXT = 0, SD_WS_FEATURES, SD_WS_SCRATCH, SD_WS_DIAGINV,
-       SD_WS_PARTIAL, SD_WS_GEOM, SD_WS_GEMM_PARTIAL, SD_WS_DIAGINV2, SD_WS_PANEL, SD_WS_BIAS, SD_WS_CG, SD_WS_COUNT };
+       SD_WS_PARTIAL, SD_WS_GEOM, SD_WS_GEMM_PARTIAL, SD_WS_DIAGINV2, SD_WS_PANEL, SD_WS_BIAS, SD_WS_CG, SD_WS_CGMAT, SD_WS_COUNT };
 
 // Block-row ownership of a distributed factorisation: global row r of the matrix belongs to rank (r / block) % nranks.
 // first_row = global row of the first row of the C sub-matrix a kernel is launched on.
@@ -123,7 +123,9 @@ int sd_gram_rank(sd_ctx* ctx, const float* d_G, int64_t ldg, int D, int* rank_ou
 #define SD_TC_PLAN_BYTES 640
 int sd_gemm_tn_tc_prepare(sd_ctx* ctx, const float* d_SA, int64_t lda, const float* d_SB, int64_t ldb, int K, int MI, int NJ,
                           float* d_C, int64_t ldc, float alpha, float beta, int passes, bool unbiased_split, bool upper_only,
-                          const sd_row_filter* rows, int ksplit, void* d_tiles_buf, void* plan_storage, bool* empty);
+                          const sd_row_filter* rows, int ksplit, void* d_tiles_buf, void* plan_storage, bool* empty,
+                          bool narrow = false /* a single tile column of <= 192 columns may use the narrow-N kernel variants */,
+                          int a_strip_rows = 0 /* > 0: operand A strip-major, see sd_gram_tc.cu */);
 int sd_gemm_tn_tc_launch(sd_ctx* ctx, const void* plan_storage);
 
 // multi-GPU helpers (sd_comm.cu); a null communicator is a single rank
