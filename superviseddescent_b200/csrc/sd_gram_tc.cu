@@ -189,7 +189,7 @@ struct TcArgs {
 // profiles/r01_summary.md.)
 //   warp 0       TMA producer        (raw tiles, 24 KB per stage)
 //   warp 1       MMA issuer          (lo*hi, hi*lo, hi*hi; accumulators in TMEM, one fresh accumulator per 128-sample chunk)
-//   warps 4..7   transform           (raw -> lo, element-wise in the swizzled layout; fence.proxy.async); one warp per stage
+//   warps 4..7   transform           (raw -> lo, element-wise in the swizzled layout; fence.proxy.async)
 //   warps 8..15  epilogue            (running sums in registers, write-back through the TMA)
 // Register budget is rebalanced with setmaxnreg: producer/MMA/transform warpgroups give registers back,
 // the two epilogue warpgroups take them (128 running sums + a 32-value TMEM fragment per thread).
@@ -240,7 +240,7 @@ syrk_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const bool split = a.passes == 3;
 
     if (warp == 0 && lane == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&lo_ready[s], 32); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&lo_ready[s], 128); mbar_init(&empty_bar[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -326,62 +326,59 @@ syrk_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     } else if (warp < 8) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 72;" ::: "memory");
         // ===================== transform: lo = a - trunc_tf32(a), element-wise on the swizzled bytes =====================
-        // Each of the four warps owns every fourth pipeline stage and transforms it alone: four stages are in flight at a time, so
-        // the shared-memory and barrier latencies of one stage hide behind the arithmetic of the others (with all four warps on
-        // the same stage the kernel ran at the pace of that chain: ncu, tensor pipe 21 % active on the skinny product).
+        // All four warps work on the same stage (one warp per stage, four stages in flight, was measured slower on the Gram:
+        // 12.4 vs 11.0 ms -- the kernel is bound by shared-memory bandwidth, not by this chain).
         if (split) {
-            const int tw = warp - 4;                          // 0..3
-            uint32_t stage = 0, phase = 0, it = 0;
+            const int tt = threadIdx.x - 128;                 // 0..127
+            uint32_t stage = 0, phase = 0;
             for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
                 const int kb0 = (t % a.ksplit) * a.kps, kb1 = min(num_k, kb0 + a.kps);
-                for (int kb = kb0; kb < kb1; ++kb, ++it) {
-                    if ((int)(it & 3) == tw) {
-                        mbar_wait(&raw_full[stage], phase);
-                        const uint32_t raw = smem_u32(smem + stage * STAGE_BYTES) + lane * 16;
-                        const uint32_t lo = raw + RAW_BYTES;
-                        // Round-to-nearest to TF32 of a finite value is "add half an ulp of the 10-bit mantissa to the bit pattern
-                        // and drop the low 13 bits"; the tensor core drops those bits by itself, so for an OPERAND the rounding is
-                        // one integer add (cvt.rna.tf32.f32 compiles to a compare, a predicated add and a mask per value).
-                        // Loads are batched four deep ahead of the stores.
-                        constexpr int NIT = RAW_BYTES / 16 / 32;          // 16-byte pieces per thread: 24 (NB = 2) .. 48 (NB = 8)
-                        if (a.unbiased) {
-                            // hi = rna_tf32(a) written back in place (the tensor core's truncation is then a no-op and the split
-                            // is unbiased), lo = rna_tf32(a - hi).  One more shared-memory write per stage than the variant below.
-#pragma unroll 3
-                            for (int i0 = 0; i0 < NIT; i0 += 4) {
-                                float4 v[4];
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&raw_full[stage], phase);
+                    const uint32_t raw = smem_u32(smem + stage * STAGE_BYTES) + tt * 16;
+                    const uint32_t lo = raw + RAW_BYTES;
+                    // Round-to-nearest to TF32 of a finite value is "add half an ulp of the 10-bit mantissa to the bit pattern and drop
+                    // the low 13 bits"; the tensor core drops those bits by itself, so for an OPERAND the rounding is one integer add
+                    // (cvt.rna.tf32.f32 compiles to a compare, a predicated add and a mask per value: with it ncu showed the four
+                    // transform warps, not the tensor core, setting the pace).  Loads are batched four deep ahead of the stores.
+                    constexpr int NIT = RAW_BYTES / 16 / 128;
+                    if (a.unbiased) {
+                        // hi = rna_tf32(a) written back in place (the tensor core's truncation is then a no-op and the split is
+                        // unbiased), lo = rna_tf32(a - hi).  One more shared-memory write per stage than the variant below.
 #pragma unroll
-                                for (int u = 0; u < 4; ++u) v[u] = lds128(raw + (i0 + u) * 512);
+                        for (int i0 = 0; i0 < NIT; i0 += 4) {
+                            float4 v[4];
 #pragma unroll
-                                for (int u = 0; u < 4; ++u) {
-                                    float4 h, l;
-                                    h.x = rna_tf32_bits(v[u].x); h.y = rna_tf32_bits(v[u].y); h.z = rna_tf32_bits(v[u].z); h.w = rna_tf32_bits(v[u].w);
-                                    l.x = round_operand(v[u].x - h.x); l.y = round_operand(v[u].y - h.y);
-                                    l.z = round_operand(v[u].z - h.z); l.w = round_operand(v[u].w - h.w);
-                                    sts128(raw + (i0 + u) * 512, h);
-                                    sts128(lo + (i0 + u) * 512, l);
-                                }
-                            }
-                        } else {
-                            // hi is the raw tile as the tensor core sees it (low 13 mantissa bits ignored); the residual is
-                            // rounded to TF32 so that the hardware's truncation of the lo operand does not bias it
-#pragma unroll 3
-                            for (int i0 = 0; i0 < NIT; i0 += 4) {
-                                float4 v[4];
+                            for (int u = 0; u < 4; ++u) if (i0 + u < NIT) v[u] = lds128(raw + (i0 + u) * 2048);
 #pragma unroll
-                                for (int u = 0; u < 4; ++u) v[u] = lds128(raw + (i0 + u) * 512);
-#pragma unroll
-                                for (int u = 0; u < 4; ++u) {
-                                    float4 l;
-                                    l.x = round_operand(v[u].x - trunc_tf32(v[u].x)); l.y = round_operand(v[u].y - trunc_tf32(v[u].y));
-                                    l.z = round_operand(v[u].z - trunc_tf32(v[u].z)); l.w = round_operand(v[u].w - trunc_tf32(v[u].w));
-                                    sts128(lo + (i0 + u) * 512, l);
-                                }
+                            for (int u = 0; u < 4; ++u) if (i0 + u < NIT) {
+                                float4 h, l;
+                                h.x = rna_tf32_bits(v[u].x); h.y = rna_tf32_bits(v[u].y); h.z = rna_tf32_bits(v[u].z); h.w = rna_tf32_bits(v[u].w);
+                                l.x = round_operand(v[u].x - h.x); l.y = round_operand(v[u].y - h.y);
+                                l.z = round_operand(v[u].z - h.z); l.w = round_operand(v[u].w - h.w);
+                                sts128(raw + (i0 + u) * 2048, h);
+                                sts128(lo + (i0 + u) * 2048, l);
                             }
                         }
-                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
-                        mbar_arrive(&lo_ready[stage]);
+                    } else {
+                        // hi is the raw tile as the tensor core sees it (low 13 mantissa bits ignored); the residual is
+                        // rounded to TF32 so that the hardware's truncation of the lo operand does not bias it
+#pragma unroll
+                        for (int i0 = 0; i0 < NIT; i0 += 4) {
+                            float4 v[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) if (i0 + u < NIT) v[u] = lds128(raw + (i0 + u) * 2048);
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) if (i0 + u < NIT) {
+                                float4 l;
+                                l.x = round_operand(v[u].x - trunc_tf32(v[u].x)); l.y = round_operand(v[u].y - trunc_tf32(v[u].y));
+                                l.z = round_operand(v[u].z - trunc_tf32(v[u].z)); l.w = round_operand(v[u].w - trunc_tf32(v[u].w));
+                                sts128(lo + (i0 + u) * 2048, l);
+                            }
+                        }
                     }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+                    mbar_arrive(&lo_ready[stage]);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
