@@ -269,11 +269,7 @@ int sd_cg_solve(sd_ctx* ctx, sd_comm* comm, float* G, int64_t ldg, int n, int co
 
     // this rank's slab of the contraction (rows of S), multiples of 16 rows
     int k0 = 0, k1 = n;
-    if (nranks > 1) {
-        const int per = (sd_div_up(n, nranks) + 15) / 16 * 16;
-        k0 = me * per < n ? me * per : n;
-        k1 = (me + 1) * per < n ? (me + 1) * per : n;
-    }
+    sd_cg_slab(n, nranks, me, &k0, &k1);
     const int nstrips = sd_div_up(n, 128);
     const int kp = (k1 - k0 + 15) / 16 * 16;
     float* T = nullptr;

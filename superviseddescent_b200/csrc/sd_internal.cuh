@@ -138,6 +138,16 @@ int sd_comm_allreduce_f64(sd_ctx* ctx, sd_comm* c, double* d_buf, size_t count, 
 int sd_comm_allreduce_f32(sd_ctx* ctx, sd_comm* c, float* d_buf, size_t count, cudaStream_t stream);
 // conjugate gradients on the tensor cores (sd_cg.cu); SD_ERR_NUMERIC = did not converge, use the factorisation
 int sd_cg_solve(sd_ctx* ctx, sd_comm* comm, float* G, int64_t ldg, int n, int col0, int M, float** W_out, int* ldw_out, int* iters);
+// rows [k0, k1) of the n x n system whose part of the product S P rank `me` computes in the shared CG route (multiples of 16 rows)
+inline void sd_cg_slab(int n, int nranks, int me, int* k0, int* k1)
+{
+    *k0 = 0; *k1 = n;
+    if (nranks > 1) {
+        const int per = ((n + nranks - 1) / nranks + 15) / 16 * 16;
+        *k0 = me * per < n ? me * per : n;
+        *k1 = (me + 1) * per < n ? (me + 1) * per : n;
+    }
+}
 // true when sd_reduce_scatter_gram leaves the rows block-row-cyclic (large, 16-byte aligned systems); smaller ones are all-reduced
 bool sd_gram_is_scattered(int D, int64_t ldg, const float* d_G);
 

@@ -591,18 +591,33 @@ __global__ void bias_extract_kernel(const float* __restrict__ G, long long ldg, 
 
 // rows i < D-1 (owned ones): G[i][j] -= s_i * t_j / pivot for j in [i, D-1) (t = s) and j in [D, D+M) (t = bias row of the
 // right-hand sides); column D-1 keeps s: it rides through the factorisation as one more right-hand side.
+// part (shared CG route, where a rank only ever reads what its slab [k0, k1) of the product touches): 0 = everything,
+// 1 = the slab's rows, the slab's columns above them and the right-hand sides, 2 = the rest (before a fall-back to the factorisation).
 __global__ void __launch_bounds__(256) bias_downdate_kernel(float* __restrict__ G, long long ldg, int D, int M,
-                                                            const double* __restrict__ sv, int own_block, int nranks, int rank)
+                                                            const double* __restrict__ sv, int own_block, int nranks, int rank,
+                                                            int part, int k0, int k1)
 {
     const double inv_p = 1.0 / sv[D - 1];
     for (int i = blockIdx.x; i < D - 1; i += gridDim.x) {
         if (nranks > 1 && (i / own_block) % nranks != rank) continue;
         const double f = sv[i] * inv_p;
         float* row = G + (long long)i * ldg;
-        for (int j = i + threadIdx.x; j < D + M; j += 256) {
-            if (j == D - 1) continue;
-            row[j] = (float)((double)row[j] - f * sv[j]);
+        const bool slab_row = i >= k0 && i < k1;
+        // up to three column ranges [a, b) of this row
+        int ra[3], rb[3], nr = 0;
+        if (part == 0 || (part == 1 && slab_row)) { ra[0] = i; rb[0] = D + M; nr = 1; }
+        else if (part == 1) {
+            if (i < k0) { ra[nr] = k0; rb[nr] = k1; ++nr; }
+            ra[nr] = D; rb[nr] = D + M; ++nr;
+        } else if (!slab_row) {                                           // part 2: what part 1 left out of [i, D)
+            if (i < k0) { ra[nr] = i; rb[nr] = k0; ++nr; ra[nr] = k1; rb[nr] = D; ++nr; }
+            else { ra[nr] = i; rb[nr] = D; ++nr; }
         }
+        for (int q = 0; q < nr; ++q)
+            for (int j = ra[q] + threadIdx.x; j < rb[q]; j += 256) {
+                if (j == D - 1) continue;
+                row[j] = (float)((double)row[j] - f * sv[j]);
+            }
     }
 }
 
@@ -1486,6 +1501,9 @@ static int solve_gram_impl(sd_ctx* ctx, sd_comm* comm, float* d_G, int64_t ldg, 
     SD_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch, 0, sizeof(int), ctx->stream));
     SD_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
     int nparts = 0;
+    // the norm is a sum over rows: the ranks of the distributed routes take the row blocks they own (in route 2 every rank holds the
+    // whole matrix, but reading an eighth of it and all-reducing one double is cheaper than reading all of it)
+    const bool share_norm = dist || (route == 2 && nranks > 1 && D > kLuMaxDim);
     SD_REQUIRE(ctx, !d_mu || D > kLuMaxDim, "centred features are for the factorisation route (D > 256)");
     if (reg->type == 1) {
         nparts = D < 296 ? D : 296;                                   // 2 x 148 SMs; at most 384 partials fit the scratch
@@ -1499,14 +1517,14 @@ static int solve_gram_impl(sd_ctx* ctx, sd_comm* comm, float* d_G, int64_t ldg, 
                 int rc0 = sd_comm_allreduce_f64(ctx, comm, sv0, (size_t)(D + M), ctx->stream);
                 if (rc0) return rc0;
             }
-            frob_upper_centred_kernel<<<nparts, 1024, 0, ctx->stream>>>(d_G, ldg, D, partial, 2 * kCholNb, dist ? nranks : 1, sd_comm_rank_of(comm),
+            frob_upper_centred_kernel<<<nparts, 1024, 0, ctx->stream>>>(d_G, ldg, D, partial, 2 * kCholNb, share_norm ? nranks : 1, sd_comm_rank_of(comm),
                                                                         d_mu, sv0, (double)n_train_global);
             SD_LAUNCH_CHECK(ctx, "frob_upper_centred_kernel");
         } else {
-            frob_upper_kernel<<<nparts, 1024, 0, ctx->stream>>>(d_G, ldg, D, partial, 2 * kCholNb, dist ? nranks : 1, sd_comm_rank_of(comm));
+            frob_upper_kernel<<<nparts, 1024, 0, ctx->stream>>>(d_G, ldg, D, partial, 2 * kCholNb, share_norm ? nranks : 1, sd_comm_rank_of(comm));
             SD_LAUNCH_CHECK(ctx, "frob_upper_kernel");
         }
-        if (dist) {
+        if (share_norm) {
             sum_partials_kernel<<<1, 32, 0, ctx->stream>>>(partial, nparts);
             SD_LAUNCH_CHECK(ctx, "sum_partials_kernel");
             int rc = sd_comm_allreduce_f64(ctx, comm, partial, 1, ctx->stream);
@@ -1546,11 +1564,17 @@ static int solve_gram_impl(sd_ctx* ctx, sd_comm* comm, float* d_G, int64_t ldg, 
             rc = sd_comm_allreduce_f64(ctx, comm, sv, (size_t)(D + M), ctx->stream);
             if (rc) return rc;
         }
-        bias_downdate_kernel<<<4 * ctx->sm_count, 256, 0, ctx->stream>>>(d_G, ldg, D, M, sv, 2 * kCholNb, nr, me);
+        const bool try_cg = !dist && (ctx->solver_mode == 1 || route == 2) && M <= 192;
+        // shared CG: this rank reads only its slab's rows and columns of the matrix; the rest is downdated if the factorisation
+        // has to take over
+        int k0 = 0, k1 = D - 1;
+        const bool partial_downdate = try_cg && route == 2 && nranks > 1;
+        if (partial_downdate) sd_cg_slab(D - 1, nranks, me, &k0, &k1);
+        bias_downdate_kernel<<<4 * ctx->sm_count, 256, 0, ctx->stream>>>(d_G, ldg, D, M, sv, 2 * kCholNb, nr, me, partial_downdate ? 1 : 0, k0, k1);
         SD_LAUNCH_CHECK(ctx, "bias_downdate_kernel");
         bool solved = false;
         ctx->cg_iterations = 0;
-        if (!dist && (ctx->solver_mode == 1 || route == 2) && M <= 192) {
+        if (try_cg) {
             // conjugate gradients on the (well conditioned) centred system; falls back to the factorisation when it stalls
             float* W = nullptr;
             int ldw = 0, its = 0;
@@ -1566,6 +1590,10 @@ static int solve_gram_impl(sd_ctx* ctx, sd_comm* comm, float* d_G, int64_t ldg, 
             }
         }
         if (!solved) {
+            if (partial_downdate) {
+                bias_downdate_kernel<<<4 * ctx->sm_count, 256, 0, ctx->stream>>>(d_G, ldg, D, M, sv, 2 * kCholNb, nr, me, 2, k0, k1);
+                SD_LAUNCH_CHECK(ctx, "bias_downdate_kernel");
+            }
             rc = cholesky_solve(ctx, d_G, ldg, D - 1, M + 1, Xp, dist ? comm : nullptr);
             if (rc) return rc;
             bias_finish_kernel<<<M + 2 * ctx->sm_count, 256, 0, ctx->stream>>>(Xp, M + 1, 1, D, M, sv, d_X, d_mu, d_Xc);
