@@ -348,11 +348,14 @@ def run_train(sd, ctx, model, world, rank, dev, barrier, max_over_ranks, comm, c
             pass
         peak = float(peaks.get("bf16_tflops_sustained", 0) or 0) or 1500.0
         out["roofline"] = {"kernel": "syrk_tc2_kernel ([AtA|Atb] of the last level, tcgen05 3xTF32)", "bound": "tensor", "achieved": alg / t / 1e12, "peak": peak,
-                           "unit": "TFLOP/s", "frac": alg / t / 1e12 / peak, "traffic": None,
+                           "unit": "TFLOP/s", "frac": alg / t / 1e12 / peak,
+                           # DRAM bytes of this launch from the committed ncu capture: only valid for the shape it was taken on
+                           "traffic": 8569163000 + 584547000 if (world == 1 and cfg is TRAIN_CFGS["train"]) else None,
                            "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (dense bf16; the kernel runs kind::tf32 at half that rate, three passes)" if peaks else "fallback 1500 (B200_PROFILING.md)",
                            "ms_per_launch": solver_ms["At * A"], "algorithmic_flops_per_launch": alg,
                            "executed_tf32_tflops": syrk_executed_flops(n_loc, D, 2 * L) / t / 1e12,
-                           "static_profile": {"source": "profiles/r02_summary.md section 3 (ncu capture of the Gram launch)", "tensor_pipe_active_pct": 72.98}}
+                           "static_profile": {"source": "profiles/r02_summary.md section 3 (ncu --set full capture of the config-4 Gram launch on one GPU: tensor-pipe activity and the DRAM bytes reported as traffic)",
+                                              "tensor_pipe_active_pct": 84.15}}
     out["algorithmic_tflop"] = {"gram_syrk": S * (cfg["n"] * D * (D + 1.0) + 2.0 * cfg["n"] * D * 2 * L) / 1e12, "cholesky_and_solve": S * (D ** 3 / 3.0 + 2.0 * D * D * 2 * L) / 1e12}
     if e2e:
         # the same run from HOST buffers: crops and landmark rows in pinned memory, uploads inside the timed region, the trained
