@@ -38,6 +38,15 @@ def panel_owner(row: int, world_size: int, panel: int = PANEL) -> int:
     return (row // panel) % world_size
 
 
+def cg_slab(n: int, world_size: int, rank: int, align: int = 16) -> Tuple[int, int]:
+    """Rows [k0, k1) of the n x n system whose part of the product S P `rank` computes in the shared conjugate-gradient route
+    (multiples of `align` rows: one pipeline stage of the tensor-core product).  Mirror of sd_cg_slab() in csrc/sd_internal.cuh."""
+    if world_size <= 1:
+        return 0, n
+    per = ((n + world_size - 1) // world_size + align - 1) // align * align
+    return min(rank * per, n), min((rank + 1) * per, n)
+
+
 def band_offsets(D: int, W: int, band: int = PANEL) -> List[int]:
     """Offsets (in floats) of the packed row bands that travel in the Gram exchange: band p = rows [p*band, ...) from
     column p*band to W.  Mirror of band_layout() in csrc/sd_comm.cu; offsets[-1] is the total."""

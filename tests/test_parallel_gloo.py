@@ -1,7 +1,7 @@
 """world_size-2 gloo test (CPU) of the multi-GPU protocol: sample sharding, the band-packed exchange of
 [A^T A | A^T b] (all-reduce for the replicated route, per-band reduce to the block-row-cyclic owner for the distributed
-one), the global-N lambda rule, and a numpy model of the distributed blocked Cholesky's ownership / broadcast protocol
-(SURVEY.md 8e, 8f/f3).
+one), the global-N lambda rule, a numpy model of the distributed blocked Cholesky's ownership / broadcast protocol and a
+numpy model of the shared conjugate-gradient route.
 
 No GPU here, so the per-rank Gram is formed with numpy and the collectives run over gloo; the layout and ownership
 helpers are the product's (superviseddescent_b200/parallel.py mirrors csrc/sd_comm.cu).  The CUDA implementation of the
@@ -164,3 +164,115 @@ def test_two_rank_gram_exchange_and_distributed_solve_match_single_process():
         assert np.array_equal(gathered, A[:, :4])
     assert np.array_equal(results[0][2], results[1][2])      # replicated solve: bit-identical on every rank
     assert np.array_equal(results[0][4], results[1][4])      # distributed solve: every rank ends with the same X
+
+
+def _cg_worker(rank, world, port, n, d, m, out):
+    """numpy model of route 2 (csrc/sd_linalg.cu solve_gram_impl + csrc/sd_cg.cu): global centring, all-reduced Gram, bias column
+    eliminated first, every rank downdates ONLY what its slab of the product reads (everything else is poisoned with NaN here),
+    strip-major copy of the slab built from the upper triangle, CG with one all-reduce of Q per iteration."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from superviseddescent_b200 import parallel
+    rng = np.random.default_rng(9)
+    A = np.minimum(np.abs(rng.standard_normal((n, d))) * 0.08, 0.2)
+    A[:, -1] = 1.0
+    B = 0.05 * rng.standard_normal((n, m))
+    b, e = parallel.shard_range(n, world, rank)
+    # sd_centre_features: global column means (one all-reduce), bias column untouched
+    sums = torch.from_numpy(A[b:e].sum(0))
+    dist.all_reduce(sums)
+    mu = sums.numpy() / n
+    mu[-1] = 0.0
+    Ac = A[b:e] - mu
+    G = torch.from_numpy(np.hstack([Ac.T @ Ac, Ac.T @ B[b:e]]))
+    dist.all_reduce(G)
+    G = np.triu(G.numpy()[:, :d]), G.numpy()[:, d:]                # upper triangle + right-hand sides, as the exchange delivers
+    U, R = G
+    # lambda from the norm of the UNcentred matrix; the ranks split the rows of the sum (route 2: share_norm)
+    full = U + np.triu(U, 1).T
+    un = full + n * np.outer(mu, mu)
+    un[:, -1] += n * mu
+    un[-1, :] += n * mu
+    part = torch.tensor([float(sum((un[i, i:] ** 2).sum() * 2 - un[i, i] ** 2 for i in range(d) if (i // 4) % world == rank))], dtype=torch.float64)
+    dist.all_reduce(part)
+    lam = 1.5 * np.sqrt(part.item()) / n
+    assert abs(lam - 1.5 * np.linalg.norm(un) / n) <= 1e-12 * lam
+    # last column first: s = bias column, pivot = n; what remains is (d-1) x (d-1)
+    nn = d - 1
+    s_col, piv, rb = U[:nn, -1].copy(), U[-1, -1], R[-1].copy()
+    S = U[:nn, :nn] + lam * np.eye(nn)
+    Y = R[:nn].copy()
+    k0, k1 = parallel.cg_slab(nn, world, rank, align=4)
+    need = np.zeros((nn, nn), bool)
+    need[k0:k1, :] = True
+    need[:, k0:k1] = True
+    need &= np.triu(np.ones((nn, nn), bool))
+    S = np.where(need, S - np.outer(s_col, s_col) / piv, np.nan)     # partial downdate: the rest is never prepared ...
+    Y = Y - np.outer(s_col, rb) / piv
+    # cg_pack_kernel: T[strip][k - k0][c] = S[k][strip*W + c] from the upper triangle only
+    W = 8
+    kp = (k1 - k0 + 3) // 4 * 4
+    T = np.zeros(((nn + W - 1) // W, kp, W))
+    for k in range(k0, k1):
+        for j in range(nn):
+            T[j // W, k - k0, j % W] = S[k, j] if j >= k else S[j, k]
+    assert not np.isnan(T).any()                                       # ... and never read
+    # lockstep CG on all right-hand sides; Q = sum over ranks of S[k0:k1, :]^T P[k0:k1, :]
+    X = np.zeros_like(Y); Rr = Y.copy(); P = Y.copy()
+    rs = (Rr * Rr).sum(0); bb = rs.copy()
+    its = 0
+    for its in range(1, 200):
+        Q = np.zeros_like(P)
+        for st in range(T.shape[0]):
+            cols = slice(st * W, min(st * W + W, nn))
+            Q[cols] = T[st, :k1 - k0, :cols.stop - cols.start].T @ P[k0:k1]
+        Qt = torch.from_numpy(Q)
+        dist.all_reduce(Qt)
+        Q = Qt.numpy()
+        alpha = rs / (P * Q).sum(0)
+        X += alpha * P
+        Rr -= alpha * Q
+        rn = (Rr * Rr).sum(0)
+        if np.sqrt(rn / bb).max() <= 1e-10:
+            break
+        P = Rr + (rn / rs) * P
+        rs = rn
+    bias = (rb - s_col @ X) / piv - mu[:nn] @ X                        # bias_finish_kernel, shifted back to uncentred rows
+    out.put((rank, its, np.vstack([X, bias])))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_cg_slab_covers_rows_once():
+    from superviseddescent_b200 import parallel
+    for n in (1, 15, 16, 17050, 52700):
+        for w in (1, 2, 3, 8):
+            slabs = [parallel.cg_slab(n, w, r) for r in range(w)]
+            assert slabs[0][0] == 0 and slabs[-1][1] == n
+            assert all(slabs[i][1] == slabs[i + 1][0] for i in range(w - 1))
+            assert all(k0 % 16 == 0 or k0 == n for k0, _ in slabs)       # empty slabs start at n
+    assert parallel.cg_slab(17050, 8, 7) == (15008, 17050)                           # 2,144 rows per rank at config 4
+
+
+def test_two_rank_shared_cg_route_matches_direct_solve():
+    n, d, m, world = 400, 61, 6, 2
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_cg_worker, args=(r, world, port, n, d, m, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [out.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    rng = np.random.default_rng(9)
+    A = np.minimum(np.abs(rng.standard_normal((n, d))) * 0.08, 0.2)
+    A[:, -1] = 1.0
+    B = 0.05 * rng.standard_normal((n, m))
+    X_ref = _solve(np.hstack([A.T @ A, A.T @ B]), d, 1.5, n)
+    for rank, its, X in results:
+        assert 1 < its < 100
+        assert np.max(np.abs(X - X_ref)) <= 1e-8 * np.max(np.abs(X_ref))
+    assert np.array_equal(results[0][2], results[1][2])      # every rank ends with the same model
