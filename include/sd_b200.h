@@ -238,12 +238,15 @@ SD_API int sd_set_gram_mode(sd_ctx* ctx, int mode);
 /* ---- multi-GPU training: the exchange at superviseddescent.hpp:207 ----------------------------------------
  * One process per GPU, samples (rows of A) sharded over the ranks.  [A^T A | A^T b] is a sum over the shards, so per cascade
  * level there is ONE collective on it; lambda uses the global sample count.  The collectives are NCCL (bound at run time:
- * libnccl.so.2 must be loadable when nranks > 1).  Two routes:
+ * libnccl.so.2 must be loadable when nranks > 1).  Three routes:
  *   replicated : sd_gram -> sd_allreduce_gram -> sd_solve_gram on every rank (small systems; the solve does not scale)
+ *   shared CG  : sd_gram -> sd_allreduce_gram -> conjugate gradients whose product S P is split over the ranks by slabs of the
+ *                contraction, one all-reduce of 2L x D floats per iteration (sd_learn_dist / sd_learn_centred with
+ *                distributed_solve = 2); falls back to the replicated factorisation when CG does not converge
  *   distributed: sd_gram -> sd_reduce_scatter_gram -> sd_solve_gram_dist: the 256-row panels of [AtA|Atb] are owned
  *                block-row-cyclically (panel p by rank p % nranks); the owner factors its panel, broadcasts it, every rank
  *                updates the block rows it owns (blocked right-looking Cholesky, same kernels as on one GPU); every rank
- *                ends with the same X.  sd_learn_dist runs either route from the local rows.
+ *                ends with the same X.  sd_learn_dist runs any of the routes from the local rows.
  * Determinism: for a fixed nranks the result is reproducible bit for bit; it differs from the one-GPU result only by the
  * summation order of the partial Gram matrices (~1e-7 relative). */
 #define SD_COMM_ID_BYTES 128
@@ -278,7 +281,7 @@ SD_API int sd_learn_dist(sd_ctx* ctx, sd_comm* comm, const float* d_A, int64_t l
  *   0 = blocked Cholesky (default): the direct solve that stands in for Eigen::PartialPivLU (regressors.hpp:224-225);
  *   1 = conjugate gradients on the tensor cores: after the bias column has been eliminated the regularised Gram matrix of the
  *       centred features is very well conditioned under the MatrixNorm rule (condition number ~ N / 350 for RCR features), so a
- *       few dozen products with the D x D matrix replace the D^3 / 3 factorisation; it stops at a relative residual of 5e-7 and
+ *       few dozen products with the D x D matrix replace the D^3 / 3 factorisation; it stops at a relative residual of 2e-6 and
  *       falls back to the Cholesky if the recurrence breaks down or stalls (ill-conditioned systems, tiny lambda).
  * sd_learn_dist: distributed_solve 2 = the ranks share the CG iterations (rows of the matrix sharded, one all-reduce of
  * 2L x D floats per iteration).  sd_solver_iterations: CG iterations of the last solve (0 = the factorisation ran). */

@@ -192,7 +192,7 @@ def test_two_ranks_match_one_rank():
             print(f"{name} distributed_solve={ds}: X(2 ranks) vs X(1 rank) {e_single:.2e}; vs float64 {e_truth:.2e}; lambda {lam0:.6g} / {lam_s:.6g} / {lam_t:.6g}; "
                   f"CG iterations {r0[(name, ds, 'its')]}")
             assert (r0[(name, ds, "its")] > 0) == (ds == 2)
-            assert e_single <= (1e-5 if ds < 2 else 2e-5)                   # CG stops at a relative residual of 5e-7
+            assert e_single <= (1e-5 if ds < 2 else 2e-5)                   # CG stops at a relative residual of 2e-6
             assert e_truth <= 1e-4
             assert abs(lam0 - lam_s) <= 1e-6 * lam_s
     for r in (r0, r1):
