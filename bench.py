@@ -351,6 +351,7 @@ def run_train(sd, ctx, model, world, rank, dev, barrier, max_over_ranks, comm, c
                            "unit": "TFLOP/s", "frac": alg / t / 1e12 / peak,
                            # DRAM bytes of this launch from the committed ncu capture: only valid for the shape it was taken on
                            "traffic": 8569163000 + 584547000 if (world == 1 and cfg is TRAIN_CFGS["train"]) else None,
+                           "traffic_source": "profiles/r02_summary.md section 3 (ncu --set full capture of this launch shape on one GPU), not this run",
                            "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (dense bf16; the kernel runs kind::tf32 at half that rate, three passes)" if peaks else "fallback 1500 (B200_PROFILING.md)",
                            "ms_per_launch": solver_ms["At * A"], "algorithmic_flops_per_launch": alg,
                            "executed_tf32_tflops": syrk_executed_flops(n_loc, D, 2 * L) / t / 1e12,
@@ -596,7 +597,9 @@ def run_ours(args):
                 "bound": "issue", "bound_note": "instruction-issue / fp32-ALU + shared-memory bound (~40 flop per algorithmic byte, SURVEY 8d), not HBM; "
                                                  "achieved/peak/frac are the HBM figures the contract asks for, frac_binding is the fp32 one",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "ms_per_launch": hog_ms,
-                "traffic": None, "algorithmic_bytes_per_launch": alg_bytes,
+                # DRAM bytes per launch from the committed `ncu --set full` capture (2048 faces), scaled per face: a capture, not this run
+                "traffic": HOG_STATIC_PROFILE["dram_bytes_per_face"] * B, "traffic_source": HOG_STATIC_PROFILE["source"],
+                "algorithmic_bytes_per_launch": alg_bytes,
                 "achieved_fp32_tflops": alg_flops / (hog_ms * 1e-3) / 1e12, "fp32_peak_tflops": fp32_peak,
                 "frac_binding": alg_flops / (hog_ms * 1e-3) / 1e12 / fp32_peak,
                 "static_profile": dict(HOG_STATIC_PROFILE, dram_bytes_this_batch=HOG_STATIC_PROFILE["dram_bytes_per_face"] * B,
