@@ -313,6 +313,9 @@ int sd_cg_solve(sd_ctx* ctx, sd_comm* comm, float* G, int64_t ldg, int n, int co
         if (!no_tiles) {
             rc = sd_gemm_tn_tc_launch(ctx, plan);
             if (rc) return rc;
+        } else {
+            // a rank without slab (more ranks than 16-row groups) contributes zeros; Q holds last iteration's sum by now
+            SD_CUDA(ctx, cudaMemsetAsync(b.Q, 0, vec * sizeof(float), ctx->stream));
         }
         if (nranks > 1) {
             rc = sd_comm_allreduce_f32(ctx, comm, b.Q, vec, ctx->stream);
